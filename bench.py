@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: point-clouds/sec, SampleNet forward (train mode: generator -> soft projection)
++ Chamfer simplification loss at B=32 per GPU, N=1024 -> 64, k=8 (BASELINE.json metric; registration flavour).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Prints ONE JSON line from rank 0 (see the repo task contract).  Key points:
+  * a step = one pass of the hot path over one batch of synthetic clouds, through the public API
+    (samplenet_b200.GraphedStep: net(x) + net.get_simplification_loss captured into one CUDA graph);
+  * `value`: inputs resident in HBM (a rotating pool of batches larger than the 126 MB L2, so every step reads cold inputs);
+  * `e2e`: the same step fed from PINNED HOST memory, host->device copy and device->host read of the loss inside the
+    timed region, synchronised every step (the reference trainer calls loss.item() every step, main.py:354);
+  * multi-GPU: batch-sharded replicas (weak scaling, 32 clouds per GPU), no data-path collective in forward + loss;
+    timing = max over ranks of CUDA-event time;
+  * `roofline`: the dominant kernel timed live with CUDA events; `cpu_baseline`: the same step on the host cores
+    (torch CPU layer stack + C oracle kNN/projection + the reference's own CPU Chamfer from oracle/_ref);
+  * `--impl reference`: that CPU path as the measured arm (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B, N, M, K_NN = 32, 1024, 64, 8
+BOTTLENECK = 128
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "point-clouds/sec SampleNet fwd+Chamfer (B=32, N=1024->64)"
+WORKLOAD = "registration SampleNet fwd(train)+soft-proj+simplification loss, B=32/GPU, N=1024->64, k=8, fp32"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def synth_batch(seed, b=B, n=N):
+    """rand-0.5, then OnUnitCube.method2 per cloud (registration/src/pctransforms.py:162-166)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(b, n, 3, generator=g) - 0.5
+    s = (x.max(dim=1)[0] - x.min(dim=1)[0]).max(dim=1)[0].view(-1, 1, 1)
+    v = x / s
+    return (v - v.mean(dim=1, keepdim=True)).contiguous()
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(steps, warmup, threads=None):
+    from oracle import oracle as orc
+    from oracle.torch_reference import ReferenceGenerator, cpu_step
+
+    orc._lib()
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    gen = ReferenceGenerator(M, BOTTLENECK).train()
+    xs = [synth_batch(100 + i) for i in range(4)]
+    for i in range(warmup):
+        cpu_step(gen, xs[i % 4], K_NN, 1.0)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_step(gen, xs[i % 4], K_NN, 1.0)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, torch.get_num_threads(), ("reference" if orc.have_ref() else "port")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    val, ms, cores, kind = cpu_reference_arm(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "clouds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B, "note": "CPU arm: rank 0 only, one replica, every step a full B=32 batch"},
+        "cpu_baseline": {"value": val, "unit": "clouds/s", "cores": cores, "kind": kind,
+                         "sample": "%d full steps of B=32: torch CPU layer stack (all threads) + C-oracle kNN/soft-proj (1 thread) + "
+                                   "reference CPU Chamfer from oracle/_ref (1 thread, as shipped)" % args.steps},
+        "e2e": {"value": val, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def time_kernels(sb, net, x, pk):
+    """CUDA-event timing of each stage, launched alone through the C-ABI wrappers, L2 flushed between iterations."""
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=x.device)
+    conv_specs, fc_specs = net._layer_specs()
+    out = {}
+
+    def timed(fn, iters=20):
+        ts = []
+        for _ in range(iters + 3):
+            flush.fill_(1)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b_.record(); b_.synchronize()
+            ts.append(a.elapsed_time(b_))
+        return float(np.mean(ts[3:]))
+
+    with torch.no_grad():
+        sigma = net.project.sigma().detach().reshape(1).contiguous()
+        simp = net(x)[0].detach()
+        out["generator_ms"] = timed(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M))
+        out["knn_softproj_ms"] = timed(lambda: sb.ops.knn_soft_project_forward(x, simp, K_NN, "bnc", sigma, want=("proj", "idx", "weights", "dist")))
+        out["chamfer_ms"] = timed(lambda: sb.ops.nn_distance_forward(simp, x))
+        out["loss_fused_ms"] = timed(lambda: sb.ops.simplification_loss_forward(simp, x, 1.0))
+        # per conv layer: run prefixes of the stack (layer l alone = prefix(l) - prefix(l-1))
+        pref = [timed(lambda l=l: sb.ops.generator_forward(x, "bnc", conv_specs[:l], [dict(weight=torch.eye(conv_specs[l - 1]["weight"].shape[0], device=x.device), bias=None, bn=None, relu=False)], True, 0), iters=10)
+                for l in range(1, 6)]
+        out["conv_prefix_ms"] = pref
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import samplenet_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    sb._lib.lib()
+    pk = peaks()
+    torch.manual_seed(0)
+    net = sb.SampleNet(M, BOTTLENECK, group_size=K_NN, initial_temperature=1.0, input_shape="bnc", output_shape="bnc").to(dev).train()
+    step = sb.GraphedStep(net, B, N)
+
+    # rotating input pool larger than L2, on device (value leg) and in pinned host memory (e2e leg)
+    nbytes = B * N * 3 * 4
+    pool_n = (int(1.2 * L2_BYTES) + nbytes - 1) // nbytes
+    host_pool = torch.empty(pool_n, B, N, 3).pin_memory()
+    base = [synth_batch(1000 * rank + i) for i in range(8)]
+    for i in range(pool_n):
+        host_pool[i].copy_(base[i % 8].roll(i // 8, dims=1))
+    dev_pool = host_pool.to(dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value leg: inputs already resident in HBM
+    for i in range(args.warmup):
+        step(dev_pool[i % pool_n])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_val = timed_region(lambda i: step(dev_pool[(args.warmup + i) % pool_n]), args.steps)
+    # ---- e2e leg: pinned host batch -> device, step, loss -> host, every step
+    for i in range(args.warmup):
+        step.run_from_host(host_pool[i % pool_n])
+    ms_e2e = timed_region(lambda i: step.run_from_host(host_pool[(args.warmup + i) % pool_n]), args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        return
+    value = world * B * args.steps / (ms_val * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel, timed live (alone, L2 flushed)
+    kt = time_kernels(sb, net, dev_pool[0], pk)
+    pref = kt["conv_prefix_ms"]
+    layer_ms = [pref[0]] + [max(pref[i] - pref[i - 1], 1e-6) for i in range(1, 5)]
+    widths = [3, 64, 64, 64, 128, BOTTLENECK]
+    layer_flops = [2.0 * B * N * widths[i] * widths[i + 1] for i in range(5)]
+    dom = int(np.argmax(layer_ms))
+    gen_flops = sum(layer_flops)
+    ach_tf = layer_flops[dom] / (layer_ms[dom] * 1e-3) / 1e12
+    roofline = {
+        "kernel": "conv_layer_kernel (generator layer %d: %d->%d, exact-fp32 CUDA-core path)" % (dom + 1, widths[dom], widths[dom + 1]),
+        "bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops"],
+        "peak_source": pk["source"] + " cuBLAS bf16 burst; this kernel is fp32 on CUDA cores (round 1), so the fraction is the gap "
+                       "the tcgen05 path has to close", "traffic": None,
+        "generator_tflops": gen_flops / (kt["generator_ms"] * 1e-3) / 1e12,
+    }
+    pair_bytes_sp = B * (12 * N + 12 * M + 12 * M)
+    pair_bytes_cd = B * (12 * (N + M) + 8 * (N + M))
+    roofline_pairwise = {
+        "knn_softproj": {"bound": "hbm", "achieved": pair_bytes_sp / (kt["knn_softproj_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": pair_bytes_sp / (kt["knn_softproj_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": kt["knn_softproj_ms"],
+                         "algorithmic_bytes": pair_bytes_sp},
+        "chamfer": {"bound": "hbm", "achieved": pair_bytes_cd / (kt["chamfer_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": pair_bytes_cd / (kt["chamfer_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": kt["chamfer_ms"],
+                    "algorithmic_bytes": pair_bytes_cd},
+        "note": "0.4-0.7 MB per launch: these launches are latency-bound at B=32 (SURVEY.md section 7); fractions reported as required",
+    }
+    # ---- CPU baseline beside it (bounded: a few full B=32 steps)
+    cpu_val, cpu_ms, cores, kind = cpu_reference_arm(6, 2)
+    line = {
+        "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": "batch-sharded replicas x%d (no collective in fwd+loss)" % world,
+                   "l2": "rotating pool of %d distinct input batches (%.0f MB > 126 MB L2); weights (1 MB) stay resident as in training" % (pool_n, pool_n * nbytes / 1e6),
+                   "api": "samplenet_b200.GraphedStep (SampleNet.forward + get_simplification_loss in one CUDA graph)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "clouds/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                "sync": "every step (loss read on the host)"},
+        "gpu_launches": int(step.launches_per_step) * args.steps,
+        "launches_per_step": int(step.launches_per_step),
+        "roofline": roofline,
+        "roofline_pairwise": roofline_pairwise,
+        "kernel_ms": {"generator": kt["generator_ms"], "conv_layers": layer_ms, "knn_softproj": kt["knn_softproj_ms"], "chamfer": kt["chamfer_ms"],
+                      "chamfer+reduce": kt["loss_fused_ms"]},
+        "cpu_baseline": {"value": cpu_val, "unit": "clouds/s", "cores": cores, "kind": kind,
+                         "sample": "6 full steps of B=32 on the host: torch CPU layer stack (%d threads) + C-oracle kNN/soft-proj (1 thread) + "
+                                   "reference CPU Chamfer (oracle/_ref, 1 thread)" % cores, "ms_per_step": cpu_ms},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Plain-torch CPU restatement of the reference's SampleNet step (test infrastructure, NOT product):
+
+    registration/src/samplenet.py:82-161   forward (train mode): conv/BN/ReLU x5 -> max -> FC/BN/ReLU x3 -> FC -> soft projection
+    registration/src/samplenet.py:171-181  get_simplification_loss
+
+The layer stack is stock torch (nn.Conv1d / BatchNorm1d / Linear run by torch's CPU kernels, exactly what the reference
+executes on CPU); kNN + soft projection go through the C oracle (the reference's knn_cuda / pointnet2 are CUDA-only);
+Chamfer goes through the reference's own CPU code in oracle/_ref when present, else the C oracle.
+Used by bench.py (cpu_baseline and --impl reference) and by tests.  Only importable from those places.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import oracle as orc
+
+
+class ReferenceGenerator(nn.Module):
+    """Same parameter names / registration order as registration/src/samplenet.py:40-60."""
+
+    def __init__(self, num_out_points, bottleneck_size):
+        super().__init__()
+        self.num_out_points = num_out_points
+        w = [3, 64, 64, 64, 128, bottleneck_size]
+        for i in range(5):
+            setattr(self, "conv%d" % (i + 1), nn.Conv1d(w[i], w[i + 1], 1))
+        for i in range(5):
+            setattr(self, "bn%d" % (i + 1), nn.BatchNorm1d(w[i + 1]))
+        f = [bottleneck_size, 256, 256, 256, 3 * num_out_points]
+        for i in range(4):
+            setattr(self, "fc%d" % (i + 1), nn.Linear(f[i], f[i + 1]))
+        for i in range(3):
+            setattr(self, "bn_fc%d" % (i + 1), nn.BatchNorm1d(256))
+
+    def forward(self, x_bcn):
+        y = x_bcn
+        for i in range(1, 6):
+            y = F.relu(getattr(self, "bn%d" % i)(getattr(self, "conv%d" % i)(y)))
+        y = torch.max(y, 2)[0]
+        for i in range(1, 4):
+            y = F.relu(getattr(self, "bn_fc%d" % i)(getattr(self, "fc%d" % i)(y)))
+        y = self.fc4(y)
+        return y.view(-1, 3, self.num_out_points)
+
+
+def cpu_step(gen, x_bnc, k, sigma, gamma=1.0, delta=0.0):
+    """One forward (train mode) + simplification loss on the CPU.  x_bnc: torch (B,N,3) float32.  Returns (simp, proj, loss)."""
+    with torch.no_grad():
+        simp = gen(x_bnc.permute(0, 2, 1)).permute(0, 2, 1).contiguous().numpy()
+    x = x_bnc.numpy()
+    _, idx = orc.knn_point(k, x, simp, contract=False, tie_mode=0)
+    proj, _, _ = orc.soft_project(x, simp, idx, float(sigma))
+    if orc.have_ref():
+        c12, _, c21, _ = orc.ref_chamfer_forward(simp, x)
+    else:
+        c12, _, c21, _ = orc.nn_distance(simp, x)
+    m = simp.shape[1]
+    loss = np.float32(c12.mean(dtype=np.float32) + c12.max(axis=1).mean(dtype=np.float32) + np.float32(gamma + delta * m) * c21.mean(dtype=np.float32))
+    return simp, proj, loss

@@ -1,0 +1,253 @@
+// api.cu -- the extern "C" boundary of libsamplenet_b200.so (see include/samplenet_b200.h).
+// Argument validation + dispatch only; kernels live in chamfer.cu / softproj.cu / encoder.cu / emd.cu / matching.cu.
+#include "common.cuh"
+#include <string.h>
+
+namespace snb {
+
+static thread_local char g_err[512] = "";
+static thread_local unsigned long long g_launches = 0;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+
+// kernels (defined in the other translation units)
+int launch_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2, int *idx2, int flags,
+                           cudaStream_t stream);
+int launch_chamfer_backward(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1, const int *idx1,
+                            const float *grad_dist2, const int *idx2, float *grad_xyz1, float *grad_xyz2, cudaStream_t stream);
+int launch_simplification_reduce(int b, int n, int m, const float *dist1, const float *dist2, float w, float *out4, cudaStream_t stream);
+int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma, int hard,
+                        const float *feats, int f, float *proj, float *prop, int *knn_idx, float *knn_val, float *weights,
+                        float *dist_over_sigma, int flags, cudaStream_t stream);
+size_t softproj_bwd_workspace(int b, int n, int m, int k, int f);
+int launch_softproj_backward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
+                             const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
+                             const float *grad_prop, float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
+                             void *workspace, cudaStream_t stream);
+int launch_group_point(int b, int n, int c, int m, int ns, int layout, const float *points, const int *idx, float *out, cudaStream_t stream);
+int launch_group_point_grad(int b, int n, int c, int m, int ns, int layout, const float *grad_out, const int *idx, float *grad_points,
+                            cudaStream_t stream);
+size_t encoder_workspace_bytes(int b, int n, int num_layers, const snb200_layer *layers);
+int launch_encoder_forward(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *feat,
+                           void *workspace, cudaStream_t stream);
+size_t fc_head_workspace_bytes(int b, int num_layers, const snb200_layer *layers);
+int launch_fc_head_forward(int b, const float *in, int num_layers, const snb200_layer *layers, int training, float *out, int out_transpose_inner,
+                           void *workspace, cudaStream_t stream);
+size_t approxmatch_workspace_bytes(int b, int n, int m);
+int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace, cudaStream_t stream);
+int launch_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *cost, float *partial, cudaStream_t stream);
+int launch_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2, cudaStream_t stream);
+int launch_nn_matching(int b, int n, int t, int k, const float *full_pc, const int *nn_idx, int complete_fps, float *out, int *out_idx,
+                       cudaStream_t stream);
+
+static int check_layers(const char *who, int num_layers, const snb200_layer *layers, int max_layers)
+{
+    SNB_REQUIRE(layers != nullptr && num_layers >= 1 && num_layers <= max_layers, "%s: num_layers=%d out of range [1,%d]", who, num_layers, max_layers);
+    for (int l = 0; l < num_layers; l++) {
+        SNB_REQUIRE(layers[l].c_in >= 1 && layers[l].c_out >= 1, "%s: layer %d has non-positive width", who, l);
+        SNB_REQUIRE(layers[l].weight != nullptr, "%s: layer %d has no weight", who, l);
+        SNB_REQUIRE(l == 0 || layers[l].c_in == layers[l - 1].c_out, "%s: layer %d c_in=%d does not match previous c_out=%d", who, l,
+                    layers[l].c_in, layers[l - 1].c_out);
+        SNB_REQUIRE((layers[l].bn_weight == nullptr) == (layers[l].bn_bias == nullptr), "%s: layer %d needs both BN weight and bias", who, l);
+    }
+    return SNB200_OK;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+#define SNB_API extern "C" __attribute__((visibility("default")))
+
+SNB_API const char *snb200_last_error(void) { return g_err; }
+SNB_API int snb200_version(void) { return 100; }
+SNB_API unsigned long long snb200_launch_count(void) { return g_launches; }
+
+SNB_API int snb200_nn_distance_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2, int *idx2,
+                                       int flags, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1, "nn_distance_forward: bad sizes b=%d n=%d m=%d", b, n, m);
+    SNB_REQUIRE(b <= 65535, "nn_distance_forward: batch %d exceeds the grid limit 65535", b);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "nn_distance_forward: null pointer");
+    return launch_chamfer_forward(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, flags, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_nn_distance_backward(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1, const int *idx1,
+                                        const float *grad_dist2, const int *idx2, float *grad_xyz1, float *grad_xyz2, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "nn_distance_backward: bad sizes b=%d n=%d m=%d", b, n, m);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && grad_xyz1 && grad_xyz2, "nn_distance_backward: null pointer");
+    return launch_chamfer_backward(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_simplification_loss_workspace_bytes(int, int, int) { return 0; }
+
+SNB_API int snb200_simplification_loss_forward(int b, int n, const float *samp, int m, const float *ref, float weight21, float *dist1, int *idx1,
+                                               float *dist2, int *idx2, float *out4, void *, size_t, int flags, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 1 && n >= 1 && m >= 1 && b <= 65535, "simplification_loss_forward: bad sizes b=%d n=%d m=%d", b, n, m);
+    SNB_REQUIRE(samp && ref && dist1 && idx1 && dist2 && idx2 && out4, "simplification_loss_forward: null pointer");
+    int rc = launch_chamfer_forward(b, n, samp, m, ref, dist1, idx1, dist2, idx2, flags, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_simplification_reduce(b, n, m, dist1, dist2, weight21, out4, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_knn_soft_project_forward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
+                                            int hard, const float *feats, int f, float *proj, float *prop, int *knn_idx, float *knn_val,
+                                            float *weights, float *dist_over_sigma, int flags, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "knn_soft_project_forward: bad sizes b=%d n=%d m=%d", b, n, m);
+    SNB_REQUIRE(k >= 1 && k <= 32, "knn_soft_project_forward: group size k=%d outside the supported range [1,32]", k);
+    SNB_REQUIRE(k <= n, "knn_soft_project_forward: k=%d exceeds the number of points n=%d", k, n);
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "knn_soft_project_forward: unknown layout %d", layout);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(points && query, "knn_soft_project_forward: null input");
+    const bool needs_sigma = proj || prop || weights || dist_over_sigma;
+    SNB_REQUIRE(!needs_sigma || sigma, "knn_soft_project_forward: sigma is required for projection outputs");
+    SNB_REQUIRE(!prop || (feats && f >= 1), "knn_soft_project_forward: prop requested without features");
+    return launch_knn_softproj(b, n, m, k, layout, points, query, sigma, hard, feats, f, proj, prop, knn_idx, knn_val, weights, dist_over_sigma,
+                               flags, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_soft_project_backward_workspace_bytes(int b, int n, int m, int k, int f) { return softproj_bwd_workspace(b, n, m, k, f); }
+
+SNB_API int snb200_soft_project_backward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
+                                         const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
+                                         const float *grad_prop, float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
+                                         void *workspace, size_t workspace_bytes, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 1 && n >= 1 && m >= 1 && k >= 1 && k <= 32 && b <= 65535, "soft_project_backward: bad sizes b=%d n=%d m=%d k=%d", b, n, m, k);
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "soft_project_backward: unknown layout %d", layout);
+    SNB_REQUIRE(points && query && sigma && knn_idx && weights, "soft_project_backward: null input");
+    SNB_REQUIRE(grad_proj || grad_prop, "soft_project_backward: no upstream gradient");
+    SNB_REQUIRE(!grad_prop || (feats && f >= 1), "soft_project_backward: grad_prop without features");
+    if (workspace_bytes < softproj_bwd_workspace(b, n, m, k, f) || !workspace) {
+        set_error("soft_project_backward: workspace %zu < %zu bytes", workspace_bytes, softproj_bwd_workspace(b, n, m, k, f));
+        return SNB200_EWORKSPACE;
+    }
+    return launch_softproj_backward(b, n, m, k, layout, points, query, sigma, feats, f, knn_idx, weights, grad_proj, grad_prop, grad_points,
+                                    grad_query, grad_feats, grad_sigma, workspace, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_group_point(int b, int n, int c, int m, int ns, int layout, const float *points, const int *idx, float *out, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && c >= 1 && m >= 1 && ns >= 1, "group_point: bad sizes");
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "group_point: unknown layout %d", layout);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(points && idx && out, "group_point: null pointer");
+    return launch_group_point(b, n, c, m, ns, layout, points, idx, out, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_group_point_grad(int b, int n, int c, int m, int ns, int layout, const float *grad_out, const int *idx, float *grad_points,
+                                    snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && c >= 1 && m >= 1 && ns >= 1 && b <= 65535, "group_point_grad: bad sizes");
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "group_point_grad: unknown layout %d", layout);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(grad_out && idx && grad_points, "group_point_grad: null pointer");
+    return launch_group_point_grad(b, n, c, m, ns, layout, grad_out, idx, grad_points, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_encoder_workspace_bytes(int b, int n, int num_layers, const snb200_layer *layers)
+{
+    if (check_layers("encoder_workspace_bytes", num_layers, layers, SNB200_MAX_CONV_LAYERS) || b < 1 || n < 1) return 0;
+    return encoder_workspace_bytes(b, n, num_layers, layers);
+}
+
+SNB_API int snb200_encoder_forward(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *feat,
+                                   void *workspace, size_t workspace_bytes, snb200_stream_t stream)
+{
+    int rc = check_layers("encoder_forward", num_layers, layers, SNB200_MAX_CONV_LAYERS);
+    if (rc) return rc;
+    SNB_REQUIRE(b >= 1 && n >= 1, "encoder_forward: bad sizes b=%d n=%d", b, n);
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "encoder_forward: unknown layout %d", layout);
+    SNB_REQUIRE(layers[0].c_in == 3, "encoder_forward: first layer must take 3 input channels, got %d", layers[0].c_in);
+    SNB_REQUIRE(x && feat, "encoder_forward: null pointer");
+    for (int l = 0; l < num_layers; l++)
+        SNB_REQUIRE(training || !layers[l].bn_weight || (layers[l].bn_running_mean && layers[l].bn_running_var),
+                    "encoder_forward: eval mode needs running statistics (layer %d)", l);
+    const size_t need = encoder_workspace_bytes(b, n, num_layers, layers);
+    if (!workspace || workspace_bytes < need) { set_error("encoder_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
+    return launch_encoder_forward(b, n, layout, x, num_layers, layers, training, feat, workspace, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_fc_head_workspace_bytes(int b, int num_layers, const snb200_layer *layers)
+{
+    if (check_layers("fc_head_workspace_bytes", num_layers, layers, SNB200_MAX_FC_LAYERS) || b < 1) return 0;
+    return fc_head_workspace_bytes(b, num_layers, layers);
+}
+
+SNB_API int snb200_fc_head_forward(int b, const float *in, int num_layers, const snb200_layer *layers, int training, float *out,
+                                   int out_transpose_inner, void *workspace, size_t workspace_bytes, snb200_stream_t stream)
+{
+    int rc = check_layers("fc_head_forward", num_layers, layers, SNB200_MAX_FC_LAYERS);
+    if (rc) return rc;
+    SNB_REQUIRE(b >= 1 && b <= 256, "fc_head_forward: batch %d outside the supported range [1,256]", b);
+    SNB_REQUIRE(in && out, "fc_head_forward: null pointer");
+    SNB_REQUIRE(out_transpose_inner >= 0 && (out_transpose_inner == 0 || layers[num_layers - 1].c_out % out_transpose_inner == 0),
+                "fc_head_forward: out_transpose_inner=%d does not divide the output width %d", out_transpose_inner, layers[num_layers - 1].c_out);
+    for (int l = 0; l < num_layers; l++) {
+        SNB_REQUIRE(training || !layers[l].bn_weight || (layers[l].bn_running_mean && layers[l].bn_running_var),
+                    "fc_head_forward: eval mode needs running statistics (layer %d)", l);
+        SNB_REQUIRE(!(training && layers[l].bn_weight && b < 2), "fc_head_forward: training-mode BatchNorm needs more than 1 row (layer %d)", l);
+    }
+    const size_t need = fc_head_workspace_bytes(b, num_layers, layers);
+    if (!workspace || workspace_bytes < need) { set_error("fc_head_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
+    return launch_fc_head_forward(b, in, num_layers, layers, training, out, out_transpose_inner, workspace, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_approxmatch_workspace_bytes(int b, int n, int m) { return approxmatch_workspace_bytes(b, n, m); }
+
+SNB_API int snb200_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace, size_t workspace_bytes,
+                               snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1, "approxmatch: bad sizes b=%d n=%d m=%d", b, n, m);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(xyz1 && xyz2 && match, "approxmatch: null pointer");
+    if (!workspace || workspace_bytes < approxmatch_workspace_bytes(b, n, m)) {
+        set_error("approxmatch: workspace %zu < %zu bytes", workspace_bytes, approxmatch_workspace_bytes(b, n, m));
+        return SNB200_EWORKSPACE;
+    }
+    return launch_approxmatch(b, n, m, xyz1, xyz2, match, workspace, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_matchcost_workspace_bytes(int b) { return (size_t)b * 16 * sizeof(float); }
+
+SNB_API int snb200_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *cost, void *workspace,
+                             size_t workspace_bytes, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "matchcost: bad sizes b=%d n=%d m=%d", b, n, m);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(xyz1 && xyz2 && match && cost, "matchcost: null pointer");
+    if (!workspace || workspace_bytes < snb200_matchcost_workspace_bytes(b)) { set_error("matchcost: workspace too small"); return SNB200_EWORKSPACE; }
+    return launch_matchcost(b, n, m, xyz1, xyz2, match, cost, reinterpret_cast<float *>(workspace), (cudaStream_t)stream);
+}
+
+SNB_API int snb200_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2,
+                                 snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "matchcostgrad: bad sizes b=%d n=%d m=%d", b, n, m);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(xyz1 && xyz2 && match && grad1 && grad2, "matchcostgrad: null pointer");
+    return launch_matchcostgrad(b, n, m, xyz1, xyz2, match, grad1, grad2, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_nn_matching(int b, int n, int t, int k, const float *full_pc, const int *nn_idx, int complete_fps, float *out, int *out_idx,
+                               snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 0 && n >= 1 && t >= 1 && k >= 1, "nn_matching: bad sizes b=%d n=%d t=%d k=%d", b, n, t, k);
+    SNB_REQUIRE(complete_fps || k <= t, "nn_matching: without FPS completion k=%d must not exceed the number of indices t=%d", k, t);
+    SNB_REQUIRE(k <= n, "nn_matching: k=%d exceeds the number of points n=%d", k, n);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(full_pc && nn_idx && out, "nn_matching: null pointer");
+    return launch_nn_matching(b, n, t, k, full_pc, nn_idx, complete_fps, out, out_idx, (cudaStream_t)stream);
+}

@@ -1,0 +1,422 @@
+"""torch-facing wrappers of the C-ABI kernels: argument checks, output allocation, autograd Functions.
+
+Every function launches on torch's CURRENT CUDA stream and never synchronises, so whole steps can be captured into
+CUDA graphs.  CPU tensors are rejected: there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BCN, BNC, DIST_FMA, DIST_UNFUSED, Layer, check, lib
+
+_LAYOUTS = {"bnc": BNC, "bcn": BCN}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("samplenet_b200: %s is on %s; the ops are CUDA-only (no CPU fallback)" % (name, t.device))
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _layout(s):
+    try:
+        return _LAYOUTS[s]
+    except KeyError:
+        raise ValueError("layout must be 'bnc' or 'bcn', got %r" % (s,))
+
+
+# ----------------------------------------------------------------------------------------------------- Chamfer
+def nn_distance_forward(xyz1, xyz2, unfused=False):
+    """dist1 (B,n), idx1 (B,n) int32, dist2 (B,m), idx2 (B,m) int32 for BNC clouds xyz1 (B,n,3), xyz2 (B,m,3)."""
+    xyz1, xyz2 = _req(xyz1, "xyz1"), _req(xyz2, "xyz2")
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[2] != 3 or xyz2.shape[2] != 3:
+        raise ValueError("nn_distance expects (batch, points, 3) tensors, got %s and %s" % (tuple(xyz1.shape), tuple(xyz2.shape)))
+    if xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("nn_distance: batch sizes differ (%d vs %d)" % (xyz1.shape[0], xyz2.shape[0]))
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    with torch.cuda.device(xyz1.device):
+        dist1 = torch.empty(b, n, device=xyz1.device, dtype=torch.float32)
+        dist2 = torch.empty(b, m, device=xyz1.device, dtype=torch.float32)
+        idx1 = torch.empty(b, n, device=xyz1.device, dtype=torch.int32)
+        idx2 = torch.empty(b, m, device=xyz1.device, dtype=torch.int32)
+        check(lib().snb200_nn_distance_forward(b, n, _p(xyz1), m, _p(xyz2), _p(dist1), _p(idx1), _p(dist2), _p(idx2),
+                                               DIST_UNFUSED if unfused else DIST_FMA, _stream()), "nn_distance_forward")
+    return dist1, idx1, dist2, idx2
+
+
+def nn_distance_backward(xyz1, xyz2, g1, idx1, g2, idx2):
+    xyz1, xyz2, g1, g2 = _req(xyz1, "xyz1"), _req(xyz2, "xyz2"), _req(g1, "grad_dist1"), _req(g2, "grad_dist2")
+    idx1, idx2 = _req(idx1, "idx1", torch.int32), _req(idx2, "idx2", torch.int32)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    with torch.cuda.device(xyz1.device):
+        gx1 = torch.empty_like(xyz1)
+        gx2 = torch.empty_like(xyz2)
+        check(lib().snb200_nn_distance_backward(b, n, _p(xyz1), m, _p(xyz2), _p(g1), _p(idx1), _p(g2), _p(idx2), _p(gx1), _p(gx2),
+                                                _stream()), "nn_distance_backward")
+    return gx1, gx2
+
+
+class NNDistanceFunction(torch.autograd.Function):
+    """Mirrors ChamferDistanceFunction (registration/src/chamfer_distance/chamfer_distance.py:14-61) and the TF op pair
+    NnDistance / NnDistanceGrad (classification/structural_losses/tf_nndistance.py:12-47): returns all four outputs;
+    the index outputs are non-differentiable."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, unfused=False):
+        dist1, idx1, dist2, idx2 = nn_distance_forward(xyz1, xyz2, unfused)
+        ctx.save_for_backward(xyz1.contiguous(), xyz2.contiguous(), idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, idx1, dist2, idx2
+
+    @staticmethod
+    def backward(ctx, g1, gi1, g2, gi2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        if g1 is None:
+            g1 = torch.zeros(idx1.shape, device=xyz1.device, dtype=torch.float32)
+        if g2 is None:
+            g2 = torch.zeros(idx2.shape, device=xyz1.device, dtype=torch.float32)
+        gx1, gx2 = nn_distance_backward(xyz1, xyz2, g1, idx1, g2, idx2)
+        return gx1, gx2, None
+
+
+def simplification_loss_forward(samp, ref, weight21, unfused=False):
+    """Fused Chamfer + reductions.  Returns (out4, dist1, idx1, dist2, idx2); out4 = [mean c12, mean max c12, mean c21, loss]."""
+    samp, ref = _req(samp, "samp_pc"), _req(ref, "ref_pc")
+    if samp.dim() != 3 or ref.dim() != 3 or samp.shape[2] != 3 or ref.shape[2] != 3 or samp.shape[0] != ref.shape[0]:
+        raise ValueError("simplification loss expects (B,M,3) and (B,N,3) tensors")
+    b, n, _ = samp.shape
+    m = ref.shape[1]
+    dev = samp.device
+    with torch.cuda.device(dev):
+        dist1 = torch.empty(b, n, device=dev); dist2 = torch.empty(b, m, device=dev)
+        idx1 = torch.empty(b, n, device=dev, dtype=torch.int32); idx2 = torch.empty(b, m, device=dev, dtype=torch.int32)
+        out4 = torch.empty(4, device=dev)
+        check(lib().snb200_simplification_loss_forward(b, n, _p(samp), m, _p(ref), float(weight21), _p(dist1), _p(idx1), _p(dist2), _p(idx2),
+                                                       _p(out4), None, 0, DIST_UNFUSED if unfused else DIST_FMA, _stream()),
+              "simplification_loss_forward")
+    return out4, dist1, idx1, dist2, idx2
+
+
+class SimplificationLossFunction(torch.autograd.Function):
+    """loss = mean(c12) + mean_b(max c12) + w * mean(c21), c12/c21 = Chamfer(samp, ref)
+    (registration/src/samplenet.py:171-181).  Backward routes through the deterministic Chamfer backward kernel."""
+
+    @staticmethod
+    def forward(ctx, samp, ref, weight21):
+        out4, dist1, idx1, dist2, idx2 = simplification_loss_forward(samp, ref, weight21)
+        ctx.save_for_backward(samp.contiguous(), ref.contiguous(), dist1, idx1, idx2)
+        ctx.w = float(weight21)
+        return out4[3].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        samp, ref, dist1, idx1, idx2 = ctx.saved_tensors
+        b, n = dist1.shape
+        m = idx2.shape[1]
+        # d loss / d dist1[b,j] = 1/(b n) + [j == argmax_j dist1[b]] / b ;  d loss / d dist2 = w / (b m)
+        g1 = torch.full((b, n), 1.0 / (b * n), device=samp.device)
+        am = dist1.argmax(dim=1, keepdim=True)
+        g1.scatter_add_(1, am, torch.full((b, 1), 1.0 / b, device=samp.device))
+        g2 = torch.full((b, m), ctx.w / (b * m), device=samp.device)
+        g1 = g1 * g
+        g2 = g2 * g
+        gs, gr = nn_distance_backward(samp, ref, g1, idx1, g2, idx2)
+        return gs, gr, None
+
+
+# ----------------------------------------------------------------------------------------------------- kNN / projection
+def knn_soft_project_forward(points, query, k, layout, sigma=None, hard=False, feats=None, want=("proj",), unfused=False):
+    """One fused launch.  `want` is a subset of {"proj","prop","idx","val","weights","dist"}; returns a dict of tensors."""
+    lay = _layout(layout)
+    points, query = _req(points, "point_cloud"), _req(query, "query_cloud")
+    if points.dim() != 3 or query.dim() != 3 or points.shape[0] != query.shape[0]:
+        raise ValueError("soft projection expects 3-D clouds with equal batch sizes")
+    cdim = 2 if lay == BNC else 1
+    if points.shape[cdim] != 3 or query.shape[cdim] != 3:
+        raise ValueError("soft projection: channel dimension must be 3 for layout %r, got %s / %s" % (layout, tuple(points.shape), tuple(query.shape)))
+    b = points.shape[0]
+    n = points.shape[1] if lay == BNC else points.shape[2]
+    m = query.shape[1] if lay == BNC else query.shape[2]
+    k = int(k)
+    dev = points.device
+    f = 0
+    if feats is not None:
+        feats = _req(feats, "point_features")
+        f = feats.shape[2] if lay == BNC else feats.shape[1]
+        nf = feats.shape[1] if lay == BNC else feats.shape[2]
+        if nf != n or feats.shape[0] != b:
+            raise ValueError("point_features must cover the same points as point_cloud")
+    if sigma is not None:
+        sigma = _req(sigma.reshape(1), "sigma")
+    out = {}
+    with torch.cuda.device(dev):
+        if "proj" in want:
+            out["proj"] = torch.empty_like(query)
+        if "prop" in want:
+            out["prop"] = torch.empty((b, m, f) if lay == BNC else (b, f, m), device=dev)
+        if "idx" in want:
+            out["idx"] = torch.empty(b, m, k, device=dev, dtype=torch.int32)
+        if "val" in want:
+            out["val"] = torch.empty(b, m, k, device=dev)
+        if "weights" in want:
+            out["weights"] = torch.empty(b, m, k, device=dev)
+        if "dist" in want:
+            out["dist"] = torch.empty(b, m, k, device=dev)
+        check(lib().snb200_knn_soft_project_forward(
+            b, n, m, k, lay, _p(points), _p(query), _p(sigma), int(bool(hard)), _p(feats), f, _p(out.get("proj")), _p(out.get("prop")),
+            _p(out.get("idx")), _p(out.get("val")), _p(out.get("weights")), _p(out.get("dist")), DIST_UNFUSED if unfused else DIST_FMA,
+            _stream()), "knn_soft_project_forward")
+    return out
+
+
+def soft_project_backward(points, query, sigma, feats, idx, weights, grad_proj, grad_prop, layout, need_points, need_query, need_feats,
+                          need_sigma):
+    lay = _layout(layout)
+    b = points.shape[0]
+    n = points.shape[1] if lay == BNC else points.shape[2]
+    m = query.shape[1] if lay == BNC else query.shape[2]
+    k = idx.shape[2]
+    f = 0 if feats is None else (feats.shape[2] if lay == BNC else feats.shape[1])
+    dev = points.device
+    with torch.cuda.device(dev):
+        gp = torch.empty_like(points) if need_points else None
+        gq = torch.empty_like(query) if need_query else None
+        gf = torch.empty_like(feats) if (need_feats and feats is not None) else None
+        gs = torch.empty(1, device=dev) if need_sigma else None
+        wsb = lib().snb200_soft_project_backward_workspace_bytes(b, n, m, k, f)
+        ws = torch.empty(max(int(wsb), 4), device=dev, dtype=torch.uint8)
+        gproj = None if grad_proj is None else _req(grad_proj, "grad_proj")
+        gprop = None if grad_prop is None else _req(grad_prop, "grad_prop")
+        check(lib().snb200_soft_project_backward(
+            b, n, m, k, lay, _p(points), _p(query), _p(sigma), _p(feats), f, _p(idx), _p(weights), _p(gproj), _p(gprop), _p(gp), _p(gq),
+            _p(gf), _p(gs), _p(ws), int(wsb), _stream()), "soft_project_backward")
+    return gp, gq, gf, gs
+
+
+class SoftProjectFunction(torch.autograd.Function):
+    """(points, query, sigma[, feats]) -> (proj, prop, weights, dist, idx); differentiable in points, query, sigma, feats."""
+
+    @staticmethod
+    def forward(ctx, points, query, sigma, feats, k, layout, hard, want_proj, want_prop):
+        want = ["idx", "weights", "dist"]
+        if want_proj:
+            want.append("proj")
+        if want_prop:
+            want.append("prop")
+        points = points.contiguous(); query = query.contiguous()
+        sig = sigma.detach().reshape(1).contiguous()
+        o = knn_soft_project_forward(points, query, k, layout, sig, hard, feats, want)
+        ctx.layout = layout
+        ctx.hard = hard
+        ctx.has_feats = feats is not None
+        ctx.save_for_backward(points, query, sig, feats.contiguous() if feats is not None else None, o["idx"], o["weights"])
+        proj = o.get("proj"); prop = o.get("prop")
+        ctx.mark_non_differentiable(o["idx"])
+        ctx.sigma_shape = sigma.shape
+        dev = points.device
+        if proj is None:
+            proj = torch.empty(0, device=dev)
+        if prop is None:
+            prop = torch.empty(0, device=dev)
+        return proj, prop, o["weights"], o["dist"], o["idx"]
+
+    @staticmethod
+    def backward(ctx, g_proj, g_prop, g_w, g_d, g_i):
+        points, query, sig, feats, idx, weights = ctx.saved_tensors
+        if ctx.hard:
+            raise NotImplementedError("hard projection is not differentiable (registration/src/soft_projection.py:144-145)")
+        if g_proj is not None and g_proj.numel() == 0:
+            g_proj = None
+        if g_prop is not None and g_prop.numel() == 0:
+            g_prop = None
+        if g_proj is None and g_prop is None:
+            return (None,) * 9
+        need = ctx.needs_input_grad
+        gp, gq, gf, gs = soft_project_backward(points, query, sig, feats, idx, weights, g_proj, g_prop, ctx.layout, need[0], need[1],
+                                               need[3] and ctx.has_feats, need[2])
+        if gs is not None:
+            gs = gs.reshape(ctx.sigma_shape)
+        return gp, gq, gs, gf, None, None, None, None, None
+
+
+def group_point(points, idx, layout="bnc"):
+    lay = _layout(layout)
+    points, idx = _req(points, "points"), _req(idx, "idx", torch.int32)
+    b = points.shape[0]
+    if lay == BNC:
+        n, c = points.shape[1], points.shape[2]
+    else:
+        c, n = points.shape[1], points.shape[2]
+    _, m, ns = idx.shape
+    with torch.cuda.device(points.device):
+        out = torch.empty((b, m, ns, c) if lay == BNC else (b, c, m, ns), device=points.device)
+        check(lib().snb200_group_point(b, n, c, m, ns, lay, _p(points), _p(idx), _p(out), _stream()), "group_point")
+    return out
+
+
+def group_point_grad(points_shape, idx, grad_out, layout="bnc"):
+    lay = _layout(layout)
+    idx, grad_out = _req(idx, "idx", torch.int32), _req(grad_out, "grad_out")
+    b = points_shape[0]
+    if lay == BNC:
+        n, c = points_shape[1], points_shape[2]
+    else:
+        c, n = points_shape[1], points_shape[2]
+    _, m, ns = idx.shape
+    with torch.cuda.device(idx.device):
+        gp = torch.empty(tuple(points_shape), device=idx.device)
+        check(lib().snb200_group_point_grad(b, n, c, m, ns, lay, _p(grad_out), _p(idx), _p(gp), _stream()), "group_point_grad")
+    return gp
+
+
+class GroupPointFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, layout):
+        ctx.save_for_backward(idx)
+        ctx.shape = tuple(points.shape)
+        ctx.layout = layout
+        return group_point(points, idx, layout)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return group_point_grad(ctx.shape, idx, g, ctx.layout), None, None
+
+
+# ----------------------------------------------------------------------------------------------------- generator
+def make_layers(specs):
+    """specs: list of dicts(weight, bias, bn=(weight,bias,running_mean,running_var,eps,momentum) or None, relu=bool)."""
+    arr = (Layer * len(specs))()
+    keep = []
+    for i, s in enumerate(specs):
+        w = _req(s["weight"].reshape(s["weight"].shape[0], -1), "weight")
+        bias = _req(s["bias"], "bias") if s.get("bias") is not None else torch.zeros(w.shape[0], device=w.device)
+        keep += [w, bias]
+        arr[i].c_out, arr[i].c_in = w.shape[0], w.shape[1]
+        arr[i].weight, arr[i].bias = w.data_ptr(), bias.data_ptr()
+        bn = s.get("bn")
+        if bn is not None:
+            gw, gb, rm, rv, eps, mom = bn
+            gw, gb = _req(gw, "bn.weight"), _req(gb, "bn.bias")
+            keep += [gw, gb]
+            arr[i].bn_weight, arr[i].bn_bias = gw.data_ptr(), gb.data_ptr()
+            arr[i].bn_running_mean = None if rm is None else rm.data_ptr()
+            arr[i].bn_running_var = None if rv is None else rv.data_ptr()
+            arr[i].bn_eps, arr[i].bn_momentum = float(eps), float(0.1 if mom is None else mom)
+        else:
+            arr[i].bn_weight = arr[i].bn_bias = arr[i].bn_running_mean = arr[i].bn_running_var = None
+            arr[i].bn_eps, arr[i].bn_momentum = 0.0, 0.0
+        arr[i].relu = int(bool(s.get("relu", False)))
+    return arr, keep
+
+
+def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0):
+    """x (B,N,3)/(B,3,N) -> (B, c_out_last) : conv stack + max-pool + FC head, all on this library's kernels."""
+    lay = _layout(layout)
+    x = _req(x, "x")
+    cdim = 2 if lay == BNC else 1
+    if x.dim() != 3 or x.shape[cdim] != 3:
+        raise RuntimeError("shape of x must be of [Batch x 3 x NumInPoints]")
+    b = x.shape[0]
+    n = x.shape[1] if lay == BNC else x.shape[2]
+    dev = x.device
+    conv, keep1 = make_layers(conv_specs)
+    fc, keep2 = make_layers(fc_specs)
+    with torch.cuda.device(dev):
+        ws1b = int(lib().snb200_encoder_workspace_bytes(b, n, len(conv_specs), conv))
+        ws2b = int(lib().snb200_fc_head_workspace_bytes(b, len(fc_specs), fc))
+        ws1 = torch.empty(max(ws1b, 4), device=dev, dtype=torch.uint8)
+        ws2 = torch.empty(max(ws2b, 4), device=dev, dtype=torch.uint8)
+        feat = torch.empty(b, conv[len(conv_specs) - 1].c_out, device=dev)
+        out = torch.empty(b, fc[len(fc_specs) - 1].c_out, device=dev)
+        check(lib().snb200_encoder_forward(b, n, lay, _p(x), len(conv_specs), conv, int(bool(training)), _p(feat), _p(ws1), ws1b, _stream()),
+              "encoder_forward")
+        check(lib().snb200_fc_head_forward(b, _p(feat), len(fc_specs), fc, int(bool(training)), _p(out), int(out_transpose_inner), _p(ws2), ws2b, _stream()),
+              "fc_head_forward")
+    del keep1, keep2
+    return out, feat
+
+
+# ----------------------------------------------------------------------------------------------------- EMD
+def approx_match(xyz1, xyz2):
+    xyz1, xyz2 = _req(xyz1, "xyz1"), _req(xyz2, "xyz2")
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[2] != 3 or xyz2.shape[2] != 3 or xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("ApproxMatch expects (batch_size,num_points,3) xyz1 and xyz2 with equal batch sizes")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        match = torch.empty(b, m, n, device=dev)
+        wsb = int(lib().snb200_approxmatch_workspace_bytes(b, n, m))
+        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        check(lib().snb200_approxmatch(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(ws), wsb, _stream()), "approxmatch")
+    return match
+
+
+def match_cost_forward(xyz1, xyz2, match):
+    xyz1, xyz2, match = _req(xyz1, "xyz1"), _req(xyz2, "xyz2"), _req(match, "match")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    if tuple(match.shape) != (b, m, n):
+        raise ValueError("MatchCost expects (batch_size,#query,#dataset) match shape, got %s" % (tuple(match.shape),))
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        cost = torch.empty(b, device=dev)
+        wsb = int(lib().snb200_matchcost_workspace_bytes(b))
+        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        check(lib().snb200_matchcost(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(cost), _p(ws), wsb, _stream()), "matchcost")
+    return cost
+
+
+def match_cost_grad(xyz1, xyz2, match):
+    xyz1, xyz2, match = _req(xyz1, "xyz1"), _req(xyz2, "xyz2"), _req(match, "match")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    with torch.cuda.device(xyz1.device):
+        g1 = torch.empty_like(xyz1); g2 = torch.empty_like(xyz2)
+        check(lib().snb200_matchcostgrad(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(g1), _p(g2), _stream()), "matchcostgrad")
+    return g1, g2
+
+
+class MatchCostFunction(torch.autograd.Function):
+    """tf_approxmatch.py:35-64: cost (B,), gradients to xyz1 and xyz2 only, scaled by grad_cost[b]."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, match):
+        ctx.save_for_backward(xyz1.contiguous(), xyz2.contiguous(), match.contiguous())
+        return match_cost_forward(xyz1, xyz2, match)
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz1, xyz2, match = ctx.saved_tensors
+        g1, g2 = match_cost_grad(xyz1, xyz2, match)
+        return g1 * g.view(-1, 1, 1), g2 * g.view(-1, 1, 1), None
+
+
+# ----------------------------------------------------------------------------------------------------- inference matching
+def nn_matching(full_pc, nn_idx, k, complete_fps=True, return_idx=False):
+    """GPU twin of sputils.nn_matching: full_pc (B,N,3), nn_idx (B,T) int32 -> (B,k,3)."""
+    full_pc, nn_idx = _req(full_pc, "full_pc"), _req(nn_idx, "idx", torch.int32)
+    b, n, _ = full_pc.shape
+    t = nn_idx.shape[1]
+    with torch.cuda.device(full_pc.device):
+        out = torch.empty(b, k, 3, device=full_pc.device)
+        oi = torch.empty(b, k, device=full_pc.device, dtype=torch.int32) if return_idx else None
+        check(lib().snb200_nn_matching(b, n, t, int(k), _p(full_pc), _p(nn_idx), int(bool(complete_fps)), _p(out), _p(oi), _stream()),
+              "nn_matching")
+    return (out, oi) if return_idx else out

@@ -1,0 +1,226 @@
+"""SampleNet(nn.Module) -- drop-in for registration/src/samplenet.py:22-187, on this package's sm_100a kernels.
+
+Constructor signature, attribute names (`name`, `project`, `skip_projection`, ...), state-dict keys
+(`conv1..5`, `bn1..5`, `fc1..4`, `bn_fc1..3`, `project._temperature`), return values (`simp, proj` in training,
+`simp, match` in eval; contiguous, shaped per `output_shape`) and error behaviour follow the reference.
+What changes is what runs underneath:
+
+  reference (samplenet.py:90-104)                      | here
+  -----------------------------------------------------+------------------------------------------------------------
+  5 x (cuDNN conv1d, BatchNorm kernel, ReLU kernel),   | one CUDA kernel per conv layer with the previous layer's BN+ReLU
+  torch.max, 3 x (Linear, BN, ReLU), Linear            | fused into its load and BN statistics / max-pool into its epilogue;
+                                                       | warp-per-channel FC head  (csrc/encoder.cu)
+  KNN (python loop over B) + grouping + ~8 torch ops   | one fused kNN + softmax + weighted-gather launch (csrc/softproj.cu)
+  eval: .cpu().numpy() -> numpy FPS loop -> .cuda()    | NN search + unique + FPS completion on the GPU (csrc/matching.cu)
+  ChamferDistance: 2 launches + 4 torch reductions     | one fused two-direction launch + one reduction launch (csrc/chamfer.cu)
+
+Backward: the projection and the loss have hand-written CUDA backward kernels; the generator's backward recomputes the
+layer stack with torch's stock conv/BN/linear ops (activation checkpointing) -- the forward never uses them.
+"""
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, sputils
+from .soft_projection import SoftProjection
+
+
+class _GeneratorFunction(torch.autograd.Function):
+    """simp_flat = generator(x).  Forward: this library's kernels.  Backward: recompute with torch ops + autograd."""
+
+    @staticmethod
+    def forward(ctx, net, x, layout, training, out_inner, *params):
+        conv_specs, fc_specs = net._layer_specs()
+        out, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, training, out_inner)
+        ctx.net = net
+        ctx.layout = layout
+        ctx.training = training
+        ctx.out_inner = out_inner
+        ctx.save_for_backward(x, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *params = ctx.saved_tensors
+        net = ctx.net
+        names = [n for n, _ in net._generator_named_parameters()]
+        with torch.enable_grad():
+            xs = x.detach().requires_grad_(ctx.needs_input_grad[1])
+            ps = {n: p.detach().requires_grad_(p.requires_grad) for n, p in zip(names, params)}
+            y = net._torch_generator(xs, ctx.layout, ctx.training, ps)
+            if ctx.out_inner:
+                b = y.shape[0]
+                y = y.view(b, -1, ctx.out_inner).permute(0, 2, 1).reshape(b, -1)
+            inputs = ([xs] if xs.requires_grad else []) + [p for p in ps.values() if p.requires_grad]
+            grads = torch.autograd.grad(y, inputs, g, allow_unused=True) if inputs else []
+        grads = list(grads)
+        gx = grads.pop(0) if xs.requires_grad else None
+        gp = [grads.pop(0) if p.requires_grad else None for p in ps.values()]
+        return (None, gx, None, None, None, *gp)
+
+
+class SampleNet(nn.Module):
+    def __init__(
+        self,
+        num_out_points,
+        bottleneck_size,
+        group_size,
+        initial_temperature=1.0,
+        is_temperature_trainable=True,
+        min_sigma=1e-2,
+        input_shape="bcn",
+        output_shape="bcn",
+        complete_fps=True,
+        skip_projection=False,
+    ):
+        super().__init__()
+        self.num_out_points = num_out_points
+        self.name = "samplenet"
+
+        widths = [3, 64, 64, 64, 128, bottleneck_size]
+        for i in range(5):
+            setattr(self, "conv%d" % (i + 1), torch.nn.Conv1d(widths[i], widths[i + 1], 1))
+        for i in range(5):
+            setattr(self, "bn%d" % (i + 1), nn.BatchNorm1d(widths[i + 1]))
+
+        fcw = [bottleneck_size, 256, 256, 256, 3 * num_out_points]
+        for i in range(4):
+            setattr(self, "fc%d" % (i + 1), nn.Linear(fcw[i], fcw[i + 1]))
+        for i in range(3):
+            setattr(self, "bn_fc%d" % (i + 1), nn.BatchNorm1d(256))
+
+        # projection and matching
+        self.project = SoftProjection(group_size, initial_temperature, is_temperature_trainable, min_sigma)
+        self.skip_projection = skip_projection
+        self.complete_fps = complete_fps
+
+        # input / output shapes
+        if input_shape not in ["bcn", "bnc"]:
+            raise ValueError("allowed shape are 'bcn' (batch * channels * num_in_points), 'bnc' ")
+        if output_shape not in ["bcn", "bnc"]:
+            raise ValueError("allowed shape are 'bcn' (batch * channels * num_in_points), 'bnc' ")
+        if input_shape != output_shape:
+            warnings.warn("SampleNet: input_shape is different to output_shape.")
+        self.input_shape = input_shape
+        self.output_shape = output_shape
+
+    # ------------------------------------------------------------------------------------------ generator plumbing
+    def _convs(self):
+        return [(getattr(self, "conv%d" % i), getattr(self, "bn%d" % i)) for i in range(1, 6)]
+
+    def _fcs(self):
+        return [(getattr(self, "fc%d" % i), getattr(self, "bn_fc%d" % i) if i < 4 else None) for i in range(1, 5)]
+
+    def _generator_named_parameters(self):
+        out = []
+        for i, (lin, bn) in enumerate(self._convs() + self._fcs()):
+            out += [("l%d.w" % i, lin.weight), ("l%d.b" % i, lin.bias)]
+            if bn is not None:
+                out += [("l%d.g" % i, bn.weight), ("l%d.beta" % i, bn.bias)]
+        return out
+
+    @staticmethod
+    def _bn_tuple(bn):
+        return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum)
+
+    def _layer_specs(self):
+        conv = [dict(weight=c.weight, bias=c.bias, bn=self._bn_tuple(b), relu=True) for c, b in self._convs()]
+        fc = [dict(weight=l.weight, bias=l.bias, bn=None if b is None else self._bn_tuple(b), relu=b is not None) for l, b in self._fcs()]
+        return conv, fc
+
+    def _torch_generator(self, x, layout, training, ps):
+        """The reference layer stack (samplenet.py:90-102) in stock torch ops; used only to differentiate the generator."""
+        y = x.permute(0, 2, 1) if layout == "bnc" else x
+        layers = self._convs() + self._fcs()
+        for i, (lin, bn) in enumerate(layers):
+            w, b = ps["l%d.w" % i], ps["l%d.b" % i]
+            if i == 5:
+                y = torch.max(y, 2)[0]
+            y = F.conv1d(y, w, b) if i < 5 else F.linear(y, w, b)
+            if bn is not None:
+                if training:
+                    y = F.batch_norm(y, None, None, ps["l%d.g" % i], ps["l%d.beta" % i], True, 0.0, bn.eps)
+                else:
+                    y = F.batch_norm(y, bn.running_mean, bn.running_var, ps["l%d.g" % i], ps["l%d.beta" % i], False, 0.0, bn.eps)
+                y = F.relu(y)
+        return y
+
+    def _generate(self, x, layout, out_inner):
+        params = [p for _, p in self._generator_named_parameters()]
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        if need_grad:
+            y = _GeneratorFunction.apply(self, x, layout, self.training, out_inner, *params)
+        else:
+            conv_specs, fc_specs = self._layer_specs()
+            y, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, self.training, out_inner)
+        if self.training:
+            with torch.no_grad():
+                for _, bn in self._convs() + self._fcs():
+                    if bn is not None and bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked += 1
+        return y
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor):
+        layout = self.input_shape
+        cdim = 1 if layout == "bcn" else 2
+        if x.dim() != 3 or x.shape[cdim] != 3:
+            raise RuntimeError("shape of x must be of [Batch x 3 x NumInPoints]")
+        x = x.contiguous()
+        m = self.num_out_points
+
+        # Generated points, produced directly in the layout of the input cloud (the FC head can store its (3, M) rows
+        # transposed), so that projection / matching run without permuting the big cloud.
+        y = self._generate(x, layout, m if layout == "bnc" else 0)
+        simp_in = y.view(-1, m, 3) if layout == "bnc" else y.view(-1, 3, m)  # same layout as x
+
+        match = None
+        proj = None
+        if self.training:
+            if not self.skip_projection:
+                proj = self.project.project(x, simp_in, layout=layout)
+            else:
+                proj = simp_in
+        else:  # Inference: nearest input point per generated point, unique, FPS completion -- all on the GPU
+            x_bnc = x if layout == "bnc" else x.permute(0, 2, 1).contiguous()
+            q_bnc = simp_in if layout == "bnc" else simp_in.permute(0, 2, 1).contiguous()
+            _, idx1, _, _ = ops.nn_distance_forward(q_bnc.detach(), x_bnc.detach())
+            match = sputils.nn_matching_cuda(x_bnc.detach(), idx1, m, complete_fps=self.complete_fps)  # B x M x 3
+
+        # Change to output shapes
+        def to_out(t, t_layout):
+            if t is None or t_layout == self.output_shape:
+                return t
+            return t.permute(0, 2, 1)
+
+        simp = to_out(simp_in, layout)
+        proj = to_out(proj, layout)
+        match = to_out(match, "bnc")
+
+        simp = simp.contiguous()
+        if proj is not None:
+            proj = proj.contiguous()
+        if match is not None:
+            match = match.contiguous()
+
+        out = proj if self.training else match
+        return simp, out
+
+    def sample(self, x):
+        simp, proj = self.__call__(x)
+        return proj
+
+    # Losses: at inference time there are no sampling losses (reference samplenet.py:167-187).
+    def get_simplification_loss(self, ref_pc, samp_pc, pc_size, gamma=1, delta=0):
+        if self.skip_projection or not self.training:
+            return torch.tensor(0).to(ref_pc)
+        # ref_pc and samp_pc are B x N x 3 matrices
+        return ops.SimplificationLossFunction.apply(samp_pc, ref_pc, gamma + delta * pc_size)
+
+    def get_projection_loss(self):
+        sigma = self.project.sigma()
+        if self.skip_projection or not self.training:
+            return torch.tensor(0).to(sigma)
+        return sigma

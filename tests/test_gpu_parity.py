@@ -1,0 +1,426 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C-ABI library via the
+package's public API, against the CPU oracle on the same seeded inputs, against the committed golden fixtures
+(generated from the reference's own Python classes, tests/golden/make_golden.py), against the reference's own CPU code
+compiled into oracle/_ref, and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Bars: indices bit-exact; squared distances bit-exact against the oracle evaluated in the same arithmetic mode
+(SNB200_DIST_FMA <-> oracle contract=True, SNB200_DIST_UNFUSED <-> oracle contract=False == the reference CPU code);
+floating-point results of softmax / reductions within the tolerance written at each assert.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HAVE_REF = os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libsamplenet_ref.so"))
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def _n(t):
+    return t.detach().cpu().numpy()
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import samplenet_b200
+
+    samplenet_b200._lib.lib()  # fail loudly if the CUDA library is missing
+    return samplenet_b200
+
+
+# ------------------------------------------------------------------------------------------------ Chamfer forward
+@pytest.mark.parametrize("b,n,m", [(1, 1, 1), (2, 64, 1024), (3, 37, 129), (2, 513, 511), (1, 1024, 64), (4, 5, 3), (2, 33, 4099), (1, 6000, 70)])
+def test_chamfer_forward_bitexact(sb, oracle, b, n, m):
+    r = _rng(b * 1000 + n + m)
+    a = r.standard_normal((b, n, 3)).astype(np.float32)
+    c = r.standard_normal((b, m, 3)).astype(np.float32)
+    if n > 4:
+        a[:, 3] = a[:, 1]  # duplicated points: exact ties, lowest index must win
+    if m > 4:
+        c[:, 4] = c[:, 0]
+    for unfused in (False, True):
+        d1, i1, d2, i2 = sb.ops.nn_distance_forward(_t(a), _t(c), unfused=unfused)
+        e1, j1, e2, j2 = oracle.nn_distance(a, c, contract=not unfused)
+        assert np.array_equal(_n(i1), j1) and np.array_equal(_n(i2), j2)
+        assert np.array_equal(_n(d1), e1) and np.array_equal(_n(d2), e2)
+    if HAVE_REF:  # the reference's own CPU code, compiled unmodified
+        d1, i1, d2, i2 = sb.ops.nn_distance_forward(_t(a), _t(c), unfused=True)
+        rd1, ri1, rd2, ri2 = oracle.ref_chamfer_forward(a, c)
+        assert np.array_equal(_n(i1), ri1) and np.array_equal(_n(i2), ri2)
+        assert np.array_equal(_n(d1), rd1) and np.array_equal(_n(d2), rd2)
+
+
+def test_chamfer_lattice_ties(sb, oracle):
+    g = np.stack(np.meshgrid(np.arange(6), np.arange(6), np.arange(6), indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32)
+    q = (g[:, ::5] + np.float32(0.5)).copy()  # equidistant from 8 lattice points each
+    d1, i1, d2, i2 = sb.ops.nn_distance_forward(_t(q), _t(g))
+    e1, j1, e2, j2 = oracle.nn_distance(q, g, contract=True)
+    assert np.array_equal(_n(i1), j1) and np.array_equal(_n(i2), j2)
+
+
+def test_chamfer_backward_and_module(sb, oracle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "chamfer_reg.npz"))
+    a = _t(z["xyz1"]).requires_grad_(True)
+    c = _t(z["xyz2"]).requires_grad_(True)
+    d1, d2 = sb.ChamferDistance()(a, c)
+    # reference autograd Function ran the CPU (unfused) arithmetic: distances agree to 1 ulp-ish
+    np.testing.assert_allclose(_n(d1), z["dist1"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(_n(d2), z["dist2"], rtol=1e-6, atol=1e-7)
+    ((d1 * _t(z["w1"])).sum() + (d2 * _t(z["w2"])).sum()).backward()
+    np.testing.assert_allclose(_n(a.grad), z["grad_xyz1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_n(c.grad), z["grad_xyz2"], rtol=1e-5, atol=1e-6)
+    # larger random case against the oracle's sequential backward (many-to-one scatter)
+    r = _rng(5)
+    x1 = r.standard_normal((3, 64, 3)).astype(np.float32); x2 = r.standard_normal((3, 1500, 3)).astype(np.float32)
+    g1 = r.standard_normal((3, 64)).astype(np.float32); g2 = r.standard_normal((3, 1500)).astype(np.float32)
+    _, i1, _, i2 = oracle.nn_distance(x1, x2, contract=True)
+    gx1, gx2 = sb.ops.nn_distance_backward(_t(x1), _t(x2), _t(g1), _t(i1, torch.int32), _t(g2), _t(i2, torch.int32))
+    ox1, ox2 = oracle.nn_distance_grad(x1, x2, g1, i1, g2, i2)
+    np.testing.assert_allclose(_n(gx1), ox1, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(_n(gx2), ox2, rtol=2e-5, atol=2e-5)
+    # determinism: two runs are bit-identical (the reference's atomics are not)
+    gy1, gy2 = sb.ops.nn_distance_backward(_t(x1), _t(x2), _t(g1), _t(i1, torch.int32), _t(g2), _t(i2, torch.int32))
+    assert torch.equal(gx1, gy1) and torch.equal(gx2, gy2)
+
+
+# ------------------------------------------------------------------------------------------------ kNN / projection
+@pytest.mark.parametrize("b,n,m,k", [(2, 1024, 64, 8), (2, 1024, 32, 7), (1, 2048, 64, 16), (3, 200, 17, 3), (2, 35, 9, 1),
+                                     (1, 64, 5, 32), (1, 4100, 6, 8), (2, 9001, 3, 16), (1, 40, 40, 32)])
+@pytest.mark.parametrize("layout", ["bnc", "bcn"])
+def test_knn_and_soft_projection_vs_oracle(sb, oracle, b, n, m, k, layout):
+    r = _rng(n * 13 + m + k)
+    pts = r.standard_normal((b, n, 3)).astype(np.float32)
+    sel = r.permutation(n)[:m]
+    qry = (pts[:, sel] + 0.05 * r.standard_normal((b, m, 3))).astype(np.float32)
+    sigma = np.float32(0.37)
+    P, Q = (_t(pts), _t(qry)) if layout == "bnc" else (_t(pts.transpose(0, 2, 1)), _t(qry.transpose(0, 2, 1)))
+    for unfused in (False, True):
+        o = sb.ops.knn_soft_project_forward(P, Q, k, layout, _t([sigma]), want=("proj", "idx", "val", "weights", "dist"), unfused=unfused)
+        val, idx = oracle.knn_point(k, pts, qry, contract=not unfused, tie_mode=1)
+        assert np.array_equal(_n(o["idx"]), idx)
+        assert np.array_equal(_n(o["val"]), val)
+        proj, w, d = oracle.soft_project(pts, qry, idx, float(sigma))
+        gp = _n(o["proj"]) if layout == "bnc" else _n(o["proj"]).transpose(0, 2, 1)
+        np.testing.assert_allclose(gp, proj, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(_n(o["weights"]), w, rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(_n(o["dist"]), d, rtol=1e-6, atol=0)
+    # reference selection-sort tie order (tie_mode=0) coincides on tie-free inputs
+    _, idx0 = oracle.knn_point(k, pts, qry, contract=True, tie_mode=0)
+    assert np.array_equal(idx0, oracle.knn_point(k, pts, qry, contract=True, tie_mode=1)[1])
+
+
+def test_knn_duplicate_points_tie_contract(sb, oracle):
+    """Duplicated cloud points (pctransforms.py:145-146 creates them): sorted by (distance, index)."""
+    r = _rng(3)
+    pts = r.standard_normal((2, 128, 3)).astype(np.float32)
+    pts[:, 64:] = pts[:, :64]
+    qry = pts[:, 5:25].copy()
+    o = sb.ops.knn_soft_project_forward(_t(pts), _t(qry), 6, "bnc", want=("idx", "val"))
+    val, idx = oracle.knn_point(6, pts, qry, contract=True, tie_mode=1)
+    assert np.array_equal(_n(o["idx"]), idx) and np.array_equal(_n(o["val"]), val)
+
+
+def test_reference_selftest_known_answers_on_gpu(sb):
+    """registration/src/soft_projection.py:158-284 and classification/soft_projection.py:86-161 golden vectors."""
+    A = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [5, 4, 4], [4, 5, 4], [4, 4, 5], [8, 7, 7], [7, 8, 7], [7, 7, 8]], np.float32)
+    Bc = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [5, 5, 5], [7, 7, 8], [7, 7, 8.5]], np.float32)
+    feats = np.arange(1, 31, dtype=np.float32).reshape(6, 5)
+    exp_feat = np.array([[6.0, 7.0, 8.0, 9.0, 10.0], [2.459, 3.459, 4.459, 5.459, 6.459], [2.459, 3.459, 4.459, 5.459, 6.459],
+                         [16.0, 17.0, 18.0, 19.0, 20.0], [16.0, 17.0, 18.0, 19.0, 20.0], [16.0, 17.0, 18.0, 19.0, 20.0],
+                         [22.113, 23.113, 24.113, 25.113, 26.113], [22.113, 23.113, 24.113, 25.113, 26.113],
+                         [23.189, 24.189, 25.189, 26.189, 27.189]], np.float32)
+    exp_cloud = np.array([[0.333, 0.333, 0.333], [1, 0, 0], [1, 0, 0], [4.333, 4.333, 4.333], [7, 7, 8], [7, 7, 8]], np.float32)
+    exp_hard = np.array([[1, 0, 0], [1, 0, 0], [1, 0, 0], [5, 4, 4], [7, 7, 8], [7, 7, 8]], np.float32)
+    # torch flavour (BCN)
+    sp = sb.SoftProjection(3, initial_temperature=1.0).cuda()
+    prop = sp.propagate(_t(Bc.T[None]), _t(feats.T[None]), _t(A.T[None]))
+    assert np.abs(_n(prop)[0].T - exp_feat).max() < 6e-4
+    sd = sp.state_dict(); sd["_temperature"] = torch.tensor(0.1); sp.load_state_dict(sd)
+    proj = sp.project(_t(A.T[None]), _t(Bc.T[None]))
+    assert np.abs(_n(proj)[0].T - exp_cloud).max() < 6e-4
+    # TF flavour (BNC), batch of 2 with the scaled cloud, T=0.01, soft and hard
+    tp = sb.tf_ops.SoftProjection(3, initial_temperature=0.01).cuda()
+    pc = _t(np.stack([A, A * 3])); qc = _t(np.stack([Bc, Bc * 3]))
+    soft, w, d = tp(pc, qc)
+    hard, wh, _ = tp(pc, qc, hard=True)
+    assert w.shape == (2, 6, 3, 1) and d.shape == (2, 6, 3, 1)
+    assert np.abs(_n(soft)[0] - exp_cloud).max() < 1.1e-3 and np.abs(_n(soft)[1] - 3 * exp_cloud).max() < 3.1e-3
+    assert np.abs(_n(hard)[0] - exp_hard).max() < 1e-6 and np.abs(_n(hard)[1] - 3 * exp_hard).max() < 1e-6
+
+
+def test_soft_projection_module_vs_reference_fixture(sb, golden_dir):
+    z = np.load(os.path.join(golden_dir, "softproj_reg.npz"))
+    sp = sb.SoftProjection(int(z["k"]), initial_temperature=float(z["temperature"]), min_sigma=float(z["min_sigma"])).cuda()
+    pc = _t(z["point_cloud"]).requires_grad_(True); qc = _t(z["query_cloud"]).requires_grad_(True)
+    ft = _t(z["feats"]).requires_grad_(True)
+    pp, pf = sp(pc, qc, ft, action="project_and_propagate")
+    np.testing.assert_allclose(_n(pp), z["proj"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(_n(pf), z["prop"], rtol=2e-6, atol=2e-6)
+    ((pp * _t(z["r1"])).sum() + (pf * _t(z["r2"])).sum()).backward()
+    np.testing.assert_allclose(_n(qc.grad), z["grad_query_cloud"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(_n(pc.grad), z["grad_point_cloud"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(_n(ft.grad), z["grad_feats"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(_n(sp._temperature.grad), z["grad_temperature"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(_n(sp(pc.detach(), qc.detach())), z["only_proj"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(_n(sp(pc.detach(), qc.detach(), ft.detach(), action="propagate")), z["only_prop"], rtol=2e-6, atol=2e-6)
+    with pytest.raises(ValueError):
+        sp(pc, qc, action="nonsense")
+    d, i = sb.knn_point(4, pc.detach(), qc.detach())
+    assert d.shape == (3, 4, 17) and i.dtype == torch.int64 and bool((d[:, 1:] >= d[:, :-1]).all())
+
+
+def test_group_point_and_grad(sb, oracle):
+    r = _rng(9)
+    pts = r.standard_normal((2, 300, 7)).astype(np.float32)
+    idx = r.integers(0, 300, size=(2, 40, 5)).astype(np.int32)
+    idx[:, :, 1] = idx[:, :, 0]  # repeated indices inside a group
+    p = _t(pts).requires_grad_(True)
+    out = sb.tf_ops.group_point(p, _t(idx, torch.int32))
+    assert np.array_equal(_n(out), oracle.group_point(pts, idx))
+    go = r.standard_normal(out.shape).astype(np.float32)
+    out.backward(_t(go))
+    np.testing.assert_allclose(_n(p.grad), oracle.group_point_grad(pts.shape, idx, go), rtol=1e-5, atol=1e-5)
+    # BCN flavour (pointnet2 grouping_operation)
+    ob = sb.ops.group_point(_t(pts.transpose(0, 2, 1)), _t(idx, torch.int32), "bcn")
+    assert np.array_equal(_n(ob), oracle.group_point(pts, idx).transpose(0, 3, 1, 2))
+
+
+# ------------------------------------------------------------------------------------------------ SampleNet end to end
+def _load_net(sb, z, **kw):
+    net = sb.SampleNet(64, 128, group_size=8, initial_temperature=1.0, **kw)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_")}
+    net.load_state_dict(sd)  # reference state-dict keys load as-is
+    return net.cuda()
+
+
+def test_samplenet_config0_vs_reference_fixture(sb, golden_dir):
+    """BASELINE config 0: registration SampleNet fwd + soft-proj (+ both losses, backward), B=2, N=1024->64, k=8."""
+    z = np.load(os.path.join(golden_dir, "samplenet_reg_b2.npz"))
+    net = _load_net(sb, z, input_shape="bnc", output_shape="bnc")
+    net.train()
+    x = _t(z["x"])
+    simp, proj = net(x)
+    assert simp.is_contiguous() and proj.is_contiguous() and simp.shape == (2, 64, 3) and proj.shape == (2, 64, 3)
+    np.testing.assert_allclose(_n(simp), z["simp"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(_n(proj), z["proj"], rtol=1e-4, atol=5e-5)
+    simp.retain_grad()
+    loss_s = net.get_simplification_loss(x, simp, 64, 1, 0)
+    loss_p = net.get_projection_loss()
+    np.testing.assert_allclose(_n(loss_s), z["loss_simplification"], rtol=1e-4)
+    np.testing.assert_allclose(_n(loss_p), z["loss_projection"], rtol=1e-6)
+    # loss parity on IDENTICAL inputs (north_star: within 1e-5): feed the reference's own simp
+    loss_id = net.get_simplification_loss(x, _t(z["simp"]), 64, 1, 0)
+    assert abs(float(loss_id) - float(z["loss_simplification"])) < 1e-5 * max(1.0, abs(float(z["loss_simplification"])))
+    total = 0.01 * loss_s + 0.01 * loss_p + (proj * _t(z["rw"])).sum()
+    total.backward()
+    np.testing.assert_allclose(_n(simp.grad), z["grad_simp"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(_n(net.project._temperature.grad), z["grad_temperature"], rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(_n(net.fc4.bias.grad), z["grad_fc4_bias"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(_n(net.fc4.weight.grad[0]), z["grad_fc4_weight_row0"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(_n(net.conv1.weight.grad), z["grad_conv1_weight"], rtol=5e-3, atol=5e-4)
+    np.testing.assert_allclose(_n(net.conv5.bias.grad), z["grad_conv5_bias"], rtol=5e-3, atol=5e-4)
+    np.testing.assert_allclose(_n(net.bn3.weight.grad), z["grad_bn3_weight"], rtol=5e-3, atol=5e-4)
+    # BatchNorm running statistics after one training step (state-dict compatibility surface)
+    sd = net.state_dict()
+    for key in z.files:
+        if key.startswith("after_"):
+            np.testing.assert_allclose(_n(sd[key[6:]]).astype(np.float64), z[key].astype(np.float64), rtol=2e-4, atol=2e-6, err_msg=key)
+
+
+def test_samplenet_eval_matching_vs_reference_fixture(sb, oracle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "samplenet_reg_b2.npz"))
+    e = np.load(os.path.join(golden_dir, "samplenet_reg_b2_eval.npz"))
+    # (a) the matching kernel alone on the reference's NN indices: exact
+    out = sb.sputils.nn_matching_cuda(_t(z["x"]), _t(e["nn_idx"], torch.int32), 64, complete_fps=True)
+    assert np.array_equal(_n(out), e["match"].astype(np.float32))
+    assert np.array_equal(sb.sputils.nn_matching(z["x"], e["nn_idx"], 64), oracle.nn_matching(z["x"], e["nn_idx"], 64))
+    out2 = sb.sputils.nn_matching_cuda(_t(z["x"]), _t(e["nn_idx"], torch.int32), 64, complete_fps=False)
+    assert np.array_equal(_n(out2), np.take_along_axis(z["x"], e["nn_idx"][..., None].astype(np.int64).repeat(3, -1), axis=1))
+    # (b) the whole eval forward, starting from a state after one training step like the fixture did
+    net = _load_net(sb, z, input_shape="bnc", output_shape="bnc")
+    net.train(); net(_t(z["x"])); net.eval()
+    with torch.no_grad():
+        simp, match = net(_t(z["x"]))
+    np.testing.assert_allclose(_n(simp), e["simp_eval"], rtol=2e-4, atol=5e-5)
+    assert match.shape == (2, 64, 3)
+    # every matched point is a point of the input cloud, and (NN assignment being stable under 1e-4 perturbations for
+    # all but near-tie queries) nearly all rows coincide with the reference's
+    same = (np.abs(_n(match) - e["match"].astype(np.float32)).max(-1) == 0).mean()
+    assert same > 0.9
+    assert float(net.get_simplification_loss(_t(z["x"]), simp, 64)) == 0.0 and float(net.get_projection_loss()) == 0.0
+
+
+@pytest.mark.parametrize("shapes", [("bcn", "bcn"), ("bnc", "bcn"), ("bcn", "bnc")])
+def test_samplenet_layout_variants_agree(sb, golden_dir, shapes):
+    import warnings
+
+    z = np.load(os.path.join(golden_dir, "samplenet_reg_b2.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = _load_net(sb, z, input_shape=shapes[0], output_shape=shapes[1])
+    net.train()
+    x = _t(z["x"]) if shapes[0] == "bnc" else _t(z["x"].transpose(0, 2, 1))
+    simp, proj = net(x)
+    if shapes[1] == "bcn":
+        simp, proj = simp.permute(0, 2, 1), proj.permute(0, 2, 1)
+    np.testing.assert_allclose(_n(simp), z["simp"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(_n(proj), z["proj"], rtol=1e-4, atol=5e-5)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 4, 10, device="cuda"))
+
+
+def test_generator_vs_torch_fp32_reference(sb):
+    """The conv/BN/FC stack is a floating-point kernel: compare with plain torch fp32 (CPU) on the headline shape,
+    plus the rec widths (reconstruction/src/samplers.py:22-36) and a ragged cloud size through the C-ABI layer API."""
+    torch.manual_seed(0)
+    net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc")
+    x = torch.rand(32, 1024, 3) - 0.5
+    net.train()
+    ps = {n: p for n, p in net._generator_named_parameters()}
+    ref = net._torch_generator(x, "bnc", True, ps).detach()  # stock torch ops on CPU
+    netc = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc")
+    netc.load_state_dict(net.state_dict()); netc.cuda().train()
+    with torch.no_grad():
+        y = netc._generate(x.cuda(), "bnc", 0)
+    np.testing.assert_allclose(_n(y), ref.numpy(), rtol=2e-4, atol=2e-5)
+    # eval mode (running statistics)
+    net.eval(); netc.eval()
+    ref_e = net._torch_generator(x, "bnc", False, ps).detach()
+    with torch.no_grad():
+        y_e = netc._generate(x.cuda(), "bnc", 0)
+    # netc's running stats were updated by the training forward above, net's were not: sync them first
+    net.load_state_dict(netc.state_dict()); ref_e = net._torch_generator(x, "bnc", False, {n: p for n, p in net._generator_named_parameters()}).detach()
+    np.testing.assert_allclose(_n(y_e), ref_e.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_generator_rec_widths_and_ragged_sizes(sb):
+    torch.manual_seed(1)
+    import torch.nn.functional as F
+    widths = [3, 64, 128, 128, 256, 128]
+    b, n = 5, 777
+    x = torch.randn(b, n, 3)
+    Ws = [torch.randn(widths[i + 1], widths[i]) / widths[i] ** 0.5 for i in range(5)]
+    bs = [0.1 * torch.randn(widths[i + 1]) for i in range(5)]
+    gs = [1 + 0.2 * torch.randn(widths[i + 1]) for i in range(5)]
+    be = [0.1 * torch.randn(widths[i + 1]) for i in range(5)]
+    y = x.permute(0, 2, 1)
+    for i in range(5):
+        y = F.relu(F.batch_norm(F.conv1d(y, Ws[i][:, :, None], bs[i]), None, None, gs[i], be[i], True, 0.0, 1e-3))
+    ref = y.max(2)[0]
+    conv = [dict(weight=Ws[i].cuda(), bias=bs[i].cuda(), bn=(gs[i].cuda(), be[i].cuda(), None, None, 1e-3, 0.1), relu=True) for i in range(5)]
+    fcw = torch.eye(128).cuda()
+    fc = [dict(weight=fcw, bias=torch.zeros(128).cuda(), bn=None, relu=False)]
+    out, feat = sb.ops.generator_forward(x.cuda(), "bnc", conv, fc, True)
+    np.testing.assert_allclose(_n(feat), ref.numpy(), rtol=3e-4, atol=3e-5)
+    np.testing.assert_allclose(_n(out), ref.numpy(), rtol=3e-4, atol=3e-5)
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def test_simplification_loss_fused_and_tf_names(sb, oracle):
+    r = _rng(21)
+    ref = r.standard_normal((4, 1024, 3)).astype(np.float32)
+    samp = (ref[:, :64] + 0.1 * r.standard_normal((4, 64, 3))).astype(np.float32)
+    for gamma, delta in ((1, 0), (0.5, 0.01)):
+        out = sb.tf_ops.get_simplification_loss(_t(ref), _t(samp), 64, gamma, delta)
+        np.testing.assert_allclose(float(out), float(oracle.simplification_loss(ref, samp, 64, gamma, delta, contract=True)), rtol=3e-6)
+    d1, i1, d2, i2 = sb.tf_ops.nn_distance(_t(samp), _t(ref))
+    e1, j1, e2, j2 = oracle.nn_distance(samp, ref, contract=True)
+    assert np.array_equal(_n(i1), j1) and np.array_equal(_n(d2), e2) and i1.dtype == torch.int32
+    # autograd of the fused loss == autograd of the composed torch expression over ChamferDistance
+    s1 = _t(samp).requires_grad_(True); s2 = _t(samp).requires_grad_(True)
+    sb.tf_ops.get_simplification_loss(_t(ref), s1, 64, 1, 0).backward()
+    c12, c21 = sb.ChamferDistance()(s2, _t(ref))
+    (c12.mean() + c12.max(dim=1)[0].mean() + c21.mean()).backward()
+    np.testing.assert_allclose(_n(s1.grad), _n(s2.grad), rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("n,m", [(64, 64), (96, 32), (40, 120), (300, 300), (2048, 2048)])
+def test_emd_vs_oracle(sb, oracle, n, m):
+    r = _rng(n * 7 + m)
+    b = 2 if n < 2048 else 1
+    a = r.random((b, n, 3)).astype(np.float32)
+    c = r.random((b, m, 3)).astype(np.float32)
+    mt = sb.tf_ops.approx_match(_t(a), _t(c))
+    assert mt.shape == (b, m, n)
+    omt = oracle.approx_match(a, c)
+    # same algorithm, different summation order + exp2f vs expf: the reference flags |diff| > 1e-2 (approxmatch.cpp:222)
+    assert np.abs(_n(mt) - omt).max() < 2e-3
+    assert (np.argmax(_n(mt), axis=2) == np.argmax(omt, axis=2)).mean() > 0.995  # match assignments
+    # on IDENTICAL match input the cost and gradient kernels are compared tightly
+    x1 = _t(a).requires_grad_(True); x2 = _t(c).requires_grad_(True)
+    cost = sb.tf_ops.match_cost(x1, x2, _t(omt))
+    np.testing.assert_allclose(_n(cost), oracle.match_cost(a, c, omt), rtol=2e-5)
+    gw = r.random(b).astype(np.float32)
+    (cost * _t(gw)).sum().backward()
+    g1, g2 = oracle.match_cost_grad(a, c, omt)
+    np.testing.assert_allclose(_n(x1.grad), g1 * gw[:, None, None], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(_n(x2.grad), g2 * gw[:, None, None], rtol=2e-4, atol=2e-5)
+    # conservation: the smaller side is fully assigned
+    tot = _n(mt).sum(axis=1) if n <= m else _n(mt).sum(axis=2)
+    np.testing.assert_allclose(tot, max(n, m) // min(n, m), rtol=3e-3)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(sb):
+    """BASELINE sizes, checked through size-independent properties (the oracle would take minutes here)."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (b, n, m, k) in [(32, 1024, 64, 8), (32, 1024, 1024, 7), (50, 2048, 2048, 16)]:
+        x = torch.rand(b, n, 3, device="cuda", generator=g) - 0.5
+        q = x[:, torch.randperm(n, device="cuda")[:m]] + 0.02 * torch.randn(b, m, 3, device="cuda", generator=g)
+        d1, i1, d2, i2 = sb.ops.nn_distance_forward(q, x)
+        # (1) the reported distance is the distance to the reported index; (2) nothing is closer (torch.cdist bound)
+        gq = torch.gather(x, 1, i1.long()[..., None].expand(-1, -1, 3))
+        assert torch.allclose(((gq - q) ** 2).sum(-1), d1, rtol=1e-5, atol=1e-7)
+        full = torch.cdist(q, x) ** 2
+        assert bool((d1 <= full.min(2)[0] * (1 + 1e-4) + 1e-6).all()) and bool((d2 <= full.min(1)[0] * (1 + 1e-4) + 1e-6).all())
+        # (3) symmetry: swapping the clouds swaps the outputs bit-exactly
+        e2, j2, e1, j1 = sb.ops.nn_distance_forward(x, q)
+        assert torch.equal(d1, e1) and torch.equal(i1, j1) and torch.equal(d2, e2) and torch.equal(i2, j2)
+        # (4) kNN: sorted, first neighbour == Chamfer NN, weights sum to one, projection inside the neighbours' bounding box
+        o = sb.ops.knn_soft_project_forward(x, q, k, "bnc", torch.tensor([0.05], device="cuda"), want=("proj", "idx", "val", "weights"))
+        assert bool((o["val"][..., 1:] >= o["val"][..., :-1]).all())
+        assert torch.equal(o["idx"][..., 0], i1) and torch.equal(o["val"][..., 0], d1)
+        assert torch.allclose(o["weights"].sum(-1), torch.ones(b, m, device="cuda"), atol=1e-5)
+        nb = torch.gather(x[:, None].expand(-1, m, -1, -1), 2, o["idx"].long()[..., None].expand(-1, -1, -1, 3))
+        assert bool((o["proj"] <= nb.max(2)[0] + 1e-5).all()) and bool((o["proj"] >= nb.min(2)[0] - 1e-5).all())
+        # (5) idempotence: projecting cloud points onto the cloud with k=1 returns them
+        p1 = sb.ops.knn_soft_project_forward(x, x[:, :m].contiguous(), 1, "bnc", torch.tensor([1.0], device="cuda"))["proj"]
+        assert torch.equal(p1, x[:, :m])
+
+
+def test_cuda_graph_capture_of_a_step(sb, golden_dir):
+    z = np.load(os.path.join(golden_dir, "samplenet_reg_b2.npz"))
+    net = _load_net(sb, z, input_shape="bnc", output_shape="bnc").train()
+    x = _t(z["x"])
+    with torch.no_grad():
+        simp0, proj0 = net(x); l0 = net.get_simplification_loss(x, simp0, 64)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(x)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            simp, proj = net(x); loss = net.get_simplification_loss(x, simp, 64)
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(simp, simp0) and torch.equal(proj, proj0) and torch.equal(loss, l0)
+
+
+def test_cpu_tensors_are_rejected(sb):
+    with pytest.raises(RuntimeError):
+        sb.ChamferDistance()(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    with pytest.raises(ValueError):
+        sb.ops.knn_soft_project_forward(torch.zeros(1, 8, 3, device="cuda"), torch.zeros(1, 2, 3, device="cuda"), 33, "bnc", want=("idx",))
+    with pytest.raises(ValueError):
+        sb.ops.knn_soft_project_forward(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(1, 2, 3, device="cuda"), 5, "bnc", want=("idx",))
