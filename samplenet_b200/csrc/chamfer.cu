@@ -142,11 +142,14 @@ int launch_chamfer_forward(int b, int n, const float *xyz1, int m, const float *
     const size_t smem = (size_t)min(max_nc, kChamferTile) * 3 * sizeof(float);
     dim3 grid(P.d[0].tiles + P.d[1].tiles, b);
     const bool unfused = (flags & SNB200_DIST_UNFUSED) != 0;
-#define SNB_LAUNCH_CHAMFER(QQ, FMA)                                                                                  \
-    do {                                                                                                             \
-        cudaFuncSetAttribute(chamfer_forward_kernel<QQ, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);   \
-        chamfer_forward_kernel<QQ, FMA><<<grid, kChamferThreads, smem, stream>>>(P);                                  \
-    } while (0)
+    static PerDeviceOnce attr_once;  // 48 KB tile + the static mbarrier exceeds the default 48 KB window: opt in once
+    if (attr_once.first()) {
+        cudaFuncSetAttribute(chamfer_forward_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(chamfer_forward_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(chamfer_forward_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(chamfer_forward_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+    }
+#define SNB_LAUNCH_CHAMFER(QQ, FMA) chamfer_forward_kernel<QQ, FMA><<<grid, kChamferThreads, smem, stream>>>(P)
     if (Q == 4) {
         if (unfused) SNB_LAUNCH_CHAMFER(4, false); else SNB_LAUNCH_CHAMFER(4, true);
     } else {

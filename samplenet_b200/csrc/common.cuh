@@ -41,6 +41,19 @@ inline int check_launch(const char *what)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute is per device: run the opt-in once per (kernel family, device).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // ------------------------------------------------------------------------------------------- device side
 #ifdef __CUDACC__
 

@@ -447,12 +447,11 @@ int launch_encoder_forward(int b, int n, int layout, const float *x, int num_lay
         dim3 grid(b * P.tiles_per_cloud, (L.c_out + CC - 1) / CC);
         const int TYN = kEncThreads / (CC / 8);
         const size_t smem = ((size_t)kEncKC * TP + (size_t)kEncKC * CC + 2 * (size_t)L.c_in + (size_t)TYN * CC) * sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.first()) {
             cudaFuncSetAttribute(conv_layer_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             cudaFuncSetAttribute(conv_layer_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_done = true;
-        }
+            }
         if (smem > 100 * 1024) { set_error("encoder: layer %d too wide for the shared-memory tile (c_in=%d)", l, L.c_in); return SNB200_EUNSUPPORTED; }
         if (CC == 64) conv_layer_kernel<64><<<grid, kEncThreads, smem, stream>>>(P);
         else conv_layer_kernel<128><<<grid, kEncThreads, smem, stream>>>(P);
@@ -509,7 +508,9 @@ int launch_fc_head_forward(int b, const float *in, int num_layers, const snb200_
         P.out = (l == num_layers - 1) ? out : buf[l & 1];
         P.out_inner = (l == num_layers - 1) ? out_transpose_inner : 0;
         const size_t smem = (size_t)min(b, kFcRowChunk) * L.c_in * sizeof(float);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(fc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static PerDeviceOnce fc_once;
+        if (fc_once.first()) cudaFuncSetAttribute(fc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (smem > 96 * 1024) { set_error("fc head: layer %d too wide (c_in=%d)", l, L.c_in); return SNB200_EUNSUPPORTED; }
         fc_layer_kernel<<<(L.c_out + kFcWarps - 1) / kFcWarps, kFcWarps * 32, smem, stream>>>(P);
         int rc = check_launch("fc layer");
         if (rc) return rc;

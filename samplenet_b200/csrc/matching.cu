@@ -128,7 +128,8 @@ int launch_nn_matching(int b, int n, int t, int k, const float *full_pc, const i
 {
     const size_t smem = (size_t)n * sizeof(double) + (size_t)n * sizeof(int) + (size_t)k * sizeof(int);
     if (smem > 200 * 1024) { set_error("nn_matching: cloud of %d points does not fit the shared-memory working set", n); return SNB200_EUNSUPPORTED; }
-    if (smem > 48 * 1024) cudaFuncSetAttribute(nn_matching_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(nn_matching_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     nn_matching_kernel<<<b, kMatchThreads, smem, stream>>>(n, t, k, full_pc, nn_idx, complete_fps, out, out_idx);
     return check_launch("nn_matching");
 }

@@ -207,6 +207,13 @@ int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *poi
     dim3 grid((m + kSpWarps * qpw - 1) / (kSpWarps * qpw), b);
     const size_t smem = (size_t)min(n, kSpTile) * 3 * sizeof(float);
     const bool unfused = (flags & SNB200_DIST_UNFUSED) != 0;
+    static PerDeviceOnce attr_once;  // 48 KB tile + the static mbarrier exceeds the default 48 KB window: opt in once
+    if (attr_once.first()) {
+        cudaFuncSetAttribute(knn_softproj_kernel<SNB200_BNC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(knn_softproj_kernel<SNB200_BNC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(knn_softproj_kernel<SNB200_BCN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(knn_softproj_kernel<SNB200_BCN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+    }
     if (layout == SNB200_BNC) {
         if (unfused) knn_softproj_kernel<SNB200_BNC, false><<<grid, kSpThreads, smem, stream>>>(P);
         else knn_softproj_kernel<SNB200_BNC, true><<<grid, kSpThreads, smem, stream>>>(P);

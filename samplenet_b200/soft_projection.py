@@ -35,6 +35,7 @@ class SoftProjection(nn.Module):
             torch.tensor(initial_temperature, requires_grad=is_temperature_trainable, dtype=torch.float32)
         )
         self._min_sigma = torch.tensor(min_sigma, dtype=torch.float32)
+        self._min_sigma_value = None
         self._layout = "bcn"
 
     def forward(self, point_cloud, query_cloud, point_features=None, action="project"):
@@ -50,8 +51,11 @@ class SoftProjection(nn.Module):
             raise ValueError("action should be one of the following: 'project', 'propagate', 'project_and_propagate'")
 
     def sigma(self):
-        device = self._temperature.device
-        return torch.max(self._temperature ** 2, self._min_sigma.to(device))
+        # max(T^2, min_sigma) as in the reference (soft_projection.py:97-99).  The bound enters as a Python scalar so that
+        # no host->device copy happens per call (the reference's `.to(device)` would break CUDA-graph capture).
+        if self._min_sigma_value is None:
+            self._min_sigma_value = float(self._min_sigma)
+        return torch.clamp(self._temperature ** 2, min=self._min_sigma_value)
 
     def _run(self, point_cloud, query_cloud, point_features, want_proj, want_prop, hard=False, layout=None):
         return ops.SoftProjectFunction.apply(point_cloud, query_cloud, self.sigma(), point_features, self._group_size,

@@ -133,11 +133,20 @@ def main():
         "grad_temperature": net.project._temperature.grad.numpy(),
         "grad_simp": simp.grad.numpy(),
     }
+    # fp64 evaluation of the same generator (reference module cast to double): the yardstick for fp32 noise.  With B=2 the
+    # BatchNorm over the batch in the FC head is ill-conditioned, fp32 results scatter ~3e-4 around this.
+    import copy
+    net64 = copy.deepcopy(net).double()
+    net64.load_state_dict({k: (torch.from_numpy(v).double() if torch.from_numpy(v).is_floating_point() else torch.from_numpy(v)) for k, v in state0.items()})
+    net64.train()
+    net64.skip_projection = True
+    with torch.no_grad():
+        simp64, _ = net64(x.double())
     state1 = net.state_dict()
     run_stats = {("after_" + k): v.detach().numpy() for k, v in state1.items() if "running" in k or "num_batches" in k}
     np.savez_compressed(
         os.path.join(OUT, "samplenet_reg_b2.npz"),
-        x=x.numpy(), simp=simp.detach().numpy(), proj=proj.detach().numpy(), rw=rw.numpy(),
+        x=x.numpy(), simp_fp64=simp64.numpy(), simp=simp.detach().numpy(), proj=proj.detach().numpy(), rw=rw.numpy(),
         loss_simplification=loss_s.detach().numpy(), loss_projection=loss_p.detach().numpy(),
         **{("sd_" + k): v for k, v in state0.items()}, **grads, **run_stats,
     )
