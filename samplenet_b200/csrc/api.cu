@@ -47,6 +47,10 @@ int launch_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xy
 int launch_nn_matching(int b, int n, int t, int k, const float *full_pc, const int *nn_idx, int complete_fps, float *out, int *out_idx,
                        cudaStream_t stream);
 
+int launch_tc_gemm_debug(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D, unsigned desc_hi,
+                         int k_adv16, int swizzle, cudaStream_t stream);
+bool tc_layer_supported(int c_in, int c_out);
+
 static int check_layers(const char *who, int num_layers, const snb200_layer *layers, int max_layers)
 {
     SNB_REQUIRE(layers != nullptr && num_layers >= 1 && num_layers <= max_layers, "%s: num_layers=%d out of range [1,%d]", who, num_layers, max_layers);
@@ -178,6 +182,14 @@ SNB_API int snb200_encoder_forward(int b, int n, int layout, const float *x, int
     const size_t need = encoder_workspace_bytes(b, n, num_layers, layers);
     if (!workspace || workspace_bytes < need) { set_error("encoder_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
     return launch_encoder_forward(b, n, layout, x, num_layers, layers, training, feat, workspace, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D, unsigned desc_hi,
+                                 int k_adv16, int swizzle, snb200_stream_t stream)
+{
+    SNB_REQUIRE(rows >= 1 && tc_layer_supported(c_in, c_out), "debug_tc_gemm: unsupported shape rows=%d c_in=%d c_out=%d", rows, c_in, c_out);
+    SNB_REQUIRE(A && W && bias && D, "debug_tc_gemm: null pointer");
+    return launch_tc_gemm_debug(rows, c_in, c_out, A, W, bias, D, desc_hi, k_adv16, swizzle, (cudaStream_t)stream);
 }
 
 SNB_API size_t snb200_fc_head_workspace_bytes(int b, int num_layers, const snb200_layer *layers)

@@ -420,3 +420,16 @@ def nn_matching(full_pc, nn_idx, k, complete_fps=True, return_idx=False):
         check(lib().snb200_nn_matching(b, n, t, int(k), _p(full_pc), _p(nn_idx), int(bool(complete_fps)), _p(out), _p(oi), _stream()),
               "nn_matching")
     return (out, oi) if return_idx else out
+
+
+# ----------------------------------------------------------------------------------------------------- bring-up hook
+def debug_tc_gemm(A, W, bias, desc_hi=0, k_adv16=0, swizzle=0):
+    """D = A @ W.T + bias through the tcgen05 layer kernel (3xTF32).  A (rows, c_in), W (c_out, c_in), bias (c_out)."""
+    A, W, bias = _req(A, "A"), _req(W, "W"), _req(bias, "bias")
+    rows, c_in = A.shape
+    c_out = W.shape[0]
+    with torch.cuda.device(A.device):
+        D = torch.empty(rows, c_out, device=A.device)
+        check(lib().snb200_debug_tc_gemm(rows, c_in, c_out, _p(A), _p(W), _p(bias), _p(D), int(desc_hi), int(k_adv16), int(swizzle), _stream()),
+              "debug_tc_gemm")
+    return D

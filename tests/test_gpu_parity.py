@@ -223,25 +223,29 @@ def test_samplenet_config0_vs_reference_fixture(sb, golden_dir):
     np.testing.assert_allclose(_n(proj), z["proj"], rtol=0, atol=1.5e-3)  # end-to-end sanity (noise amplified by the kNN switch points)
     # (b) projection, losses and their gradients on the reference's own simp
     simp_ref = _t(z["simp"]).requires_grad_(True)
-    proj_id = net.project.project(x, simp_ref, layout="bnc")
+    proj_id = net.project.project(x, simp_ref.detach(), layout="bnc")
     np.testing.assert_allclose(_n(proj_id), z["proj"], rtol=2e-6, atol=2e-6)
     loss_s = net.get_simplification_loss(x, simp_ref, 64, 1, 0)
     loss_p = net.get_projection_loss()
-    assert abs(float(loss_s) - float(z["loss_simplification"])) < 1e-5 * max(1.0, abs(float(z["loss_simplification"])))  # north_star bar
+    assert abs(float(loss_s.detach()) - float(z["loss_simplification"])) < 1e-5 * max(1.0, abs(float(z["loss_simplification"])))  # north_star bar
     np.testing.assert_allclose(_n(loss_p), z["loss_projection"], rtol=1e-6)
-    total = 0.01 * loss_s + 0.01 * loss_p + (proj_id * _t(z["rw"])).sum()
-    total.backward()
-    np.testing.assert_allclose(_n(simp_ref.grad), z["grad_simp"], rtol=2e-4, atol=2e-5)
-    np.testing.assert_allclose(_n(net.project._temperature.grad), z["grad_temperature"], rtol=2e-4, atol=1e-5)
-    # (c) generator backward (recompute path) driven by the reference's upstream gradient
+    # in the reference graph the returned `simp` only feeds the simplification loss (proj hangs off the pre-permute tensor),
+    # so fixture grad_simp == 0.01 * d loss_s / d simp
+    (0.01 * loss_s).backward()
+    np.testing.assert_allclose(_n(simp_ref.grad), z["grad_simp"], rtol=2e-4, atol=1e-7)
+    # temperature: d/dT [0.01 * sigma + sum(proj * rw)] with proj computed from the reference's simp
     net.zero_grad()
-    simp2, _ = net(x)
-    simp2.backward(_t(z["grad_simp"]))
-    for name, key, tol in (("fc4.bias", "grad_fc4_bias", 1e-5), ("conv5.bias", "grad_conv5_bias", 5e-2), ("bn3.weight", "grad_bn3_weight", 5e-2)):
-        g = dict(net.named_parameters())[name].grad
+    (0.01 * loss_p + (proj_id * _t(z["rw"])).sum()).backward()
+    np.testing.assert_allclose(_n(net.project._temperature.grad), z["grad_temperature"], rtol=2e-4, atol=1e-5)
+    # (c) whole step, end to end, including the generator backward (recompute path): loose, B=2 BatchNorm noise
+    net.zero_grad()
+    simp2, proj2 = net(x)
+    total = 0.01 * net.get_simplification_loss(x, simp2, 64, 1, 0) + 0.01 * net.get_projection_loss() + (proj2 * _t(z["rw"])).sum()
+    total.backward()
+    for name, key in (("fc4.bias", "grad_fc4_bias"), ("conv5.bias", "grad_conv5_bias"), ("bn3.weight", "grad_bn3_weight"), ("conv1.weight", "grad_conv1_weight")):
+        g = _n(dict(net.named_parameters())[name].grad)
         ref = z[key]
-        assert np.abs(_n(g) - ref).max() <= tol * max(1.0, np.abs(ref).max()), (name, np.abs(_n(g) - ref).max(), np.abs(ref).max())
-    np.testing.assert_allclose(_n(net.fc4.weight.grad[0]), z["grad_fc4_weight_row0"], rtol=0, atol=5e-2 * max(1.0, np.abs(z["grad_fc4_weight_row0"]).max()))
+        assert np.abs(g - ref).max() <= 5e-2 * np.abs(ref).max() + 1e-6, (name, np.abs(g - ref).max(), np.abs(ref).max())
     # BatchNorm running statistics after training steps follow PyTorch's momentum rule: compare after ONE step on a fresh net
     net1 = _load_net(sb, z, input_shape="bnc", output_shape="bnc").train()
     net1(x)
@@ -443,3 +447,19 @@ def test_cpu_tensors_are_rejected(sb):
         sb.ops.knn_soft_project_forward(torch.zeros(1, 8, 3, device="cuda"), torch.zeros(1, 2, 3, device="cuda"), 33, "bnc", want=("idx",))
     with pytest.raises(ValueError):
         sb.ops.knn_soft_project_forward(torch.zeros(1, 4, 3, device="cuda"), torch.zeros(1, 2, 3, device="cuda"), 5, "bnc", want=("idx",))
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core layer bring-up
+@pytest.mark.parametrize("rows,c_in,c_out", [(128, 64, 64), (300, 64, 128), (256, 128, 128), (128, 32, 64), (128, 128, 256)])
+def test_tc_gemm_3xtf32(sb, rows, c_in, c_out):
+    """tcgen05.mma.kind::tf32 x3 (hi/lo split) must reproduce an fp32 GEMM to ~1e-6 relative."""
+    g = torch.Generator(device="cuda").manual_seed(rows + c_in + c_out)
+    A = torch.randn(rows, c_in, device="cuda", generator=g)
+    W = torch.randn(c_out, c_in, device="cuda", generator=g) / c_in ** 0.5
+    bias = torch.randn(c_out, device="cuda", generator=g)
+    ref = (A.double() @ W.double().T + bias.double())
+    D = sb.ops.debug_tc_gemm(A, W, bias)
+    torch.cuda.synchronize()
+    err = (D.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 5e-6 * scale, (err, scale)
