@@ -131,6 +131,17 @@ size_t snb200_encoder_workspace_bytes(int b, int n, int num_layers, const snb200
 int snb200_encoder_forward(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers,
                            int training, float *feat, void *workspace, size_t workspace_bytes, snb200_stream_t stream);
 
+/* The whole generator in one call: conv stack -> max-pool -> FC head -> out (b, c_out_last) [+ feat (b, c_conv_last), may be
+ * NULL].  Default path: layers 2.. of the conv stack on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 error-compensated,
+ * fp32 TMEM accumulators), layer 1 evaluated on the fly with its BatchNorm statistics derived from the input moments, and
+ * the pool + all FC layers in ONE thread-block-cluster launch.  flags & SNB200_GEN_EXACT_FP32 selects the exact-fp32
+ * CUDA-core conv stack instead (also taken automatically for widths the tensor path does not cover).  b <= 256. */
+#define SNB200_GEN_EXACT_FP32 1
+size_t snb200_generator_workspace_bytes(int b, int n, int num_conv, const snb200_layer *conv, int num_fc, const snb200_layer *fc);
+int snb200_generator_forward(int b, int n, int layout, const float *x, int num_conv, const snb200_layer *conv, int num_fc,
+                             const snb200_layer *fc, int training, float *out, int out_transpose_inner, float *feat, int flags,
+                             void *workspace, size_t workspace_bytes, snb200_stream_t stream);
+
 /* Bring-up / unit-test hook of the tcgen05 layer kernel (csrc/encoder_tc.cu): D (rows, c_out) = A (rows, c_in) * W (c_out, c_in)^T + bias
  * as 3xTF32 on the tensor cores.  desc_hi / k_adv16 / swizzle override the shared-memory descriptor encoding (0,0,0 = defaults);
  * they exist so that one GPU session can sweep encodings.  c_in % 8 == 0, 8 <= c_in, c_out <= 256. */

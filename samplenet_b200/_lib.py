@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsamplenet_b200.so")
 
 BNC, BCN = 0, 1
 DIST_FMA, DIST_UNFUSED = 0, 1
+GEN_EXACT_FP32 = 1
 
 _c_float_p = ctypes.c_void_p  # raw device pointers travel as integers
 _vp = ctypes.c_void_p
@@ -46,6 +47,8 @@ _SIGNATURES = {
     "snb200_group_point_grad": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "snb200_encoder_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer)]),
     "snb200_encoder_forward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, _vp, _vp, _size, _vp]),
+    "snb200_generator_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer)]),
+    "snb200_generator_forward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _int, _vp, _size, _vp]),
     "snb200_debug_tc_gemm": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, ctypes.c_uint, _int, _int, _vp]),
     "snb200_fc_head_workspace_bytes": (_size, [_int, _int, ctypes.POINTER(Layer)]),
     "snb200_fc_head_forward": (_int, [_int, _vp, _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _size, _vp]),

@@ -51,6 +51,10 @@ int launch_tc_gemm_debug(int rows, int c_in, int c_out, const float *A, const fl
                          int k_adv16, int swizzle, cudaStream_t stream);
 bool tc_layer_supported(int c_in, int c_out);
 
+size_t generator_workspace_bytes(int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc);
+int launch_generator_forward(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc,
+                             int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream);
+
 static int check_layers(const char *who, int num_layers, const snb200_layer *layers, int max_layers)
 {
     SNB_REQUIRE(layers != nullptr && num_layers >= 1 && num_layers <= max_layers, "%s: num_layers=%d out of range [1,%d]", who, num_layers, max_layers);
@@ -182,6 +186,43 @@ SNB_API int snb200_encoder_forward(int b, int n, int layout, const float *x, int
     const size_t need = encoder_workspace_bytes(b, n, num_layers, layers);
     if (!workspace || workspace_bytes < need) { set_error("encoder_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
     return launch_encoder_forward(b, n, layout, x, num_layers, layers, training, feat, workspace, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_generator_workspace_bytes(int b, int n, int num_conv, const snb200_layer *conv, int num_fc, const snb200_layer *fc)
+{
+    if (check_layers("generator_workspace_bytes", num_conv, conv, SNB200_MAX_CONV_LAYERS) || check_layers("generator_workspace_bytes", num_fc, fc, SNB200_MAX_FC_LAYERS) ||
+        b < 1 || n < 1)
+        return 0;
+    return generator_workspace_bytes(b, n, num_conv, conv, num_fc, fc);
+}
+
+SNB_API int snb200_generator_forward(int b, int n, int layout, const float *x, int num_conv, const snb200_layer *conv, int num_fc,
+                                     const snb200_layer *fc, int training, float *out, int out_transpose_inner, float *feat, int flags,
+                                     void *workspace, size_t workspace_bytes, snb200_stream_t stream)
+{
+    int rc = check_layers("generator_forward", num_conv, conv, SNB200_MAX_CONV_LAYERS);
+    if (rc) return rc;
+    rc = check_layers("generator_forward", num_fc, fc, SNB200_MAX_FC_LAYERS);
+    if (rc) return rc;
+    SNB_REQUIRE(b >= 1 && b <= 256 && n >= 1, "generator_forward: bad sizes b=%d (1..256) n=%d", b, n);
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "generator_forward: unknown layout %d", layout);
+    SNB_REQUIRE(conv[0].c_in == 3, "generator_forward: first layer must take 3 input channels, got %d", conv[0].c_in);
+    SNB_REQUIRE(fc[0].c_in == conv[num_conv - 1].c_out, "generator_forward: FC input width %d != conv output width %d", fc[0].c_in, conv[num_conv - 1].c_out);
+    SNB_REQUIRE(x && out, "generator_forward: null pointer");
+    SNB_REQUIRE(out_transpose_inner >= 0 && (out_transpose_inner == 0 || fc[num_fc - 1].c_out % out_transpose_inner == 0),
+                "generator_forward: out_transpose_inner=%d does not divide the output width %d", out_transpose_inner, fc[num_fc - 1].c_out);
+    for (int l = 0; l < num_conv; l++)
+        SNB_REQUIRE(training || !conv[l].bn_weight || (conv[l].bn_running_mean && conv[l].bn_running_var),
+                    "generator_forward: eval mode needs running statistics (conv layer %d)", l);
+    for (int l = 0; l < num_fc; l++) {
+        SNB_REQUIRE(training || !fc[l].bn_weight || (fc[l].bn_running_mean && fc[l].bn_running_var),
+                    "generator_forward: eval mode needs running statistics (fc layer %d)", l);
+        SNB_REQUIRE(!(training && fc[l].bn_weight && b < 2), "generator_forward: training-mode BatchNorm needs more than 1 row (fc layer %d)", l);
+    }
+    const size_t need = generator_workspace_bytes(b, n, num_conv, conv, num_fc, fc);
+    if (!workspace || workspace_bytes < need) { set_error("generator_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
+    return launch_generator_forward(b, n, layout, x, num_conv, conv, num_fc, fc, training, out, out_transpose_inner, feat, flags, workspace,
+                                    (cudaStream_t)stream);
 }
 
 SNB_API int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D, unsigned desc_hi,

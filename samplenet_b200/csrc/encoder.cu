@@ -15,7 +15,7 @@
 //   * a pool-finalise kernel turns statistics into the pooled feature; the FC head keeps each output channel inside one
 //     warp so that BatchNorm over the batch needs no cross-CTA traffic.
 // The tcgen05 tensor-core variant of the conv stack lives in encoder_tc.cu.
-#include "common.cuh"
+#include "encoder_internal.cuh"
 
 namespace snb {
 
@@ -409,11 +409,10 @@ size_t encoder_workspace_bytes(int b, int n, int num_layers, const snb200_layer 
     return carve_encoder_ws(nullptr, b, n, num_layers, layers).total;
 }
 
-int launch_encoder_forward(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *feat,
-                           void *workspace, cudaStream_t stream)
+int launch_simt_conv_stack(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *act0,
+                           float *act1, double *const *stats, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream)
 {
-    EncWorkspace W = carve_encoder_ws(workspace, b, n, num_layers, layers);
-    if (training) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);
+    float *act[2] = {act0, act1};
     for (int l = 0; l < num_layers; l++) {
         const snb200_layer &L = layers[l];
         ConvLayerParams P;
@@ -427,23 +426,24 @@ int launch_encoder_forward(int b, int n, int layout, const float *x, int num_lay
             P.in_has_bn = 0; P.in_relu = 0;
         } else {
             const snb200_layer &Lp = layers[l - 1];
-            P.in = W.act[(l - 1) & 1];
+            P.in = act[(l - 1) & 1];
             P.in_cloud_stride = (long long)n * Lp.c_out;
             P.in_stride_p = Lp.c_out; P.in_stride_c = 1;
             P.in_has_bn = Lp.bn_weight != nullptr;
-            P.in_stats = W.stats[l - 1];
+            P.in_stats = stats[l - 1];
             P.in_gamma = Lp.bn_weight; P.in_beta = Lp.bn_bias; P.in_run_mean = Lp.bn_running_mean; P.in_run_var = Lp.bn_running_var;
             P.in_eps = Lp.bn_eps; P.in_relu = Lp.relu; P.in_training = training;
         }
         P.weight = L.weight; P.bias = L.bias;
         const bool last = (l == num_layers - 1);
-        P.out = last ? nullptr : W.act[l & 1];
-        P.out_stats = (training && L.bn_weight) ? W.stats[l] : nullptr;
-        P.tile_max = last ? W.tile_max : nullptr;
-        P.tile_min = last ? W.tile_min : nullptr;
+        P.out = last ? nullptr : act[l & 1];
+        P.out_stats = (training && L.bn_weight) ? stats[l] : nullptr;
+        P.tile_max = last ? tile_max : nullptr;
+        P.tile_min = last ? tile_min : nullptr;
         const int CC = L.c_out > 64 ? 128 : 64;
         const int TP = enc_tp(L.c_out);
         P.tiles_per_cloud = (n + TP - 1) / TP;
+        if (last && tiles_per_cloud_out) *tiles_per_cloud_out = P.tiles_per_cloud;
         dim3 grid(b * P.tiles_per_cloud, (L.c_out + CC - 1) / CC);
         const int TYN = kEncThreads / (CC / 8);
         const size_t smem = ((size_t)kEncKC * TP + (size_t)kEncKC * CC + 2 * (size_t)L.c_in + (size_t)TYN * CC) * sizeof(float);
@@ -451,13 +451,24 @@ int launch_encoder_forward(int b, int n, int layout, const float *x, int num_lay
         if (attr_once.first()) {
             cudaFuncSetAttribute(conv_layer_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             cudaFuncSetAttribute(conv_layer_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            }
+        }
         if (smem > 100 * 1024) { set_error("encoder: layer %d too wide for the shared-memory tile (c_in=%d)", l, L.c_in); return SNB200_EUNSUPPORTED; }
         if (CC == 64) conv_layer_kernel<64><<<grid, kEncThreads, smem, stream>>>(P);
         else conv_layer_kernel<128><<<grid, kEncThreads, smem, stream>>>(P);
         int rc = check_launch("encoder conv layer");
         if (rc) return rc;
     }
+    return SNB200_OK;
+}
+
+int launch_encoder_forward(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *feat,
+                           void *workspace, cudaStream_t stream)
+{
+    EncWorkspace W = carve_encoder_ws(workspace, b, n, num_layers, layers);
+    if (training) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);
+    int tpc_last = 0;
+    int rc0 = launch_simt_conv_stack(b, n, layout, x, num_layers, layers, training, W.act[0], W.act[1], W.stats, W.tile_max, W.tile_min, &tpc_last, stream);
+    if (rc0) return rc0;
     const snb200_layer &LL = layers[num_layers - 1];
     PoolParams Q;
     memset(&Q, 0, sizeof(Q));

@@ -1,0 +1,39 @@
+// encoder_internal.cuh -- declarations shared by encoder.cu (CUDA-core path), encoder_tc.cu (tcgen05 path) and generator.cu.
+#pragma once
+#include "common.cuh"
+
+namespace snb {
+
+struct TcLayerParams {
+    // FIRST mode (x != nullptr): the A operand is layer 1 (3 -> c_in, weights w1/b1) evaluated on the fly from the cloud,
+    // its BatchNorm statistics having been derived analytically from the input moments (x_moments_kernel).
+    const float *x;             // cloud (b, n, 3) BNC or (b, 3, n) BCN, or nullptr
+    int x_layout;
+    const float *w1, *b1;       // (c_in, 3), (c_in)
+    const float *in;            // previous layer's raw output (b*n, c_in) row-major (x == nullptr)
+    int c_in, c_out;
+    int b, n, tiles_per_cloud;
+    const double *in_stats;
+    const float *in_gamma, *in_beta, *in_run_mean, *in_run_var;
+    float in_eps;
+    int in_relu, in_has_bn, in_training;
+    const float *weight, *bias;
+    float *out;                 // raw output or nullptr (last layer)
+    double *out_stats;          // or nullptr
+    float *tile_max, *tile_min; // or nullptr
+    // debug / bring-up knobs (see snb200_debug_tc_gemm): descriptor high word template and K-advance in 16-byte units
+    unsigned desc_hi;
+    int k_adv16;
+    int swizzle;                // 1 = XOR-128B data placement, 0 = plain rows
+};
+
+int launch_tc_layer(const TcLayerParams &P, cudaStream_t stream);
+bool tc_layer_supported(int c_in, int c_out);
+int tc_tiles_per_cloud(int n);
+int launch_x_moments(int b, int n, int layout, const float *x, double *mom, unsigned *counter, const float *w1, const float *b1, int c1,
+                     double *stats0, cudaStream_t stream);
+// CUDA-core conv stack: writes per-tile extrema of the last layer and (training) per-layer statistics
+int launch_simt_conv_stack(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *act0,
+                           float *act1, double *const *stats, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream);
+
+}  // namespace snb

@@ -17,31 +17,13 @@
 //             once more so that column sums / sums of squares (BatchNorm statistics) or column max/min (last layer, for the
 //             max-pool) are reduced by one thread per channel in a fixed order.
 // The layer's interface (workspace, statistics, extrema) is the one of the CUDA-core path in encoder.cu.
-#include "common.cuh"
+#include "encoder_internal.cuh"
 
 namespace snb {
 
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;   // points per CTA == UMMA M
 constexpr int kTcKC = 64;   // K chunk resident in shared memory (2 swizzle atoms of 32 fp32)
-
-struct TcLayerParams {
-    const float *in;            // previous layer's raw output (b*n, c_in) row-major
-    int c_in, c_out;
-    int b, n, tiles_per_cloud;
-    const double *in_stats;
-    const float *in_gamma, *in_beta, *in_run_mean, *in_run_var;
-    float in_eps;
-    int in_relu, in_has_bn, in_training;
-    const float *weight, *bias;
-    float *out;                 // raw output or nullptr (last layer)
-    double *out_stats;          // or nullptr
-    float *tile_max, *tile_min; // or nullptr
-    // debug / bring-up knobs (see snb200_debug_tc_gemm): descriptor high word template and K-advance in 16-byte units
-    unsigned desc_hi;
-    int k_adv16;
-    int swizzle;                // 1 = XOR-128B data placement, 0 = plain rows
-};
 
 __device__ __forceinline__ void bn_scale_shift_tc(const double *stats, int c_total, int c, double count, const float *gamma, const float *beta,
                                                   const float *run_mean, const float *run_var, float eps, int training, float &scale, float &shift)
@@ -150,6 +132,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
     unsigned char *sBlo = sBhi + 2 * kAtomB;
     float *sStage = reinterpret_cast<float *>(smem_raw);  // epilogue: [128][NOUT+1] floats, aliases the operand buffers
     __shared__ float sScale[256], sShift[256];
+    __shared__ float sX[kTcM * 3], sW1[256 * 3], sB1[256];
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_base_smem;
 
@@ -173,13 +156,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
         sScale[c] = sc;
         sShift[c] = sh;
     }
+    if (P.x) {  // stage the 128 points of this tile and the first layer's weights
+        const float *xc = P.x + (size_t)cloud * P.n * 3;
+        for (int e = tid; e < kTcM * 3; e += kTcThreads) {
+            const int r = e / 3, c = e % 3;
+            sX[e] = (r < np) ? (P.x_layout == SNB200_BNC ? xc[(size_t)(p0 + r) * 3 + c] : xc[(size_t)c * P.n + p0 + r]) : 0.f;
+        }
+        for (int e = tid; e < c_in * 3; e += kTcThreads) sW1[e] = P.w1[e];
+        for (int e = tid; e < c_in; e += kTcThreads) sB1[e] = P.b1 ? P.b1[e] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
     const uint32_t idesc = make_idesc_tf32(kTcM, NOUT);
 
-    const float *in_tile = P.in + ((size_t)cloud * P.n + p0) * c_in;
+    const float *in_tile = P.x ? nullptr : P.in + ((size_t)cloud * P.n + p0) * c_in;
     uint32_t phase = 0;
     const int nchunks = (c_in + kTcKC - 1) / kTcKC;
     for (int kc = 0; kc < nchunks; kc++) {
@@ -190,7 +182,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
             const int k = k0 + ch * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < np && k < c_in) {  // c_in is a multiple of 4 on this path
-                v = __ldg(reinterpret_cast<const float4 *>(in_tile + (size_t)row * c_in + k));
+                if (P.x) {  // layer 1 on the fly: y = (w0*x + w1*y + w2*z) + b
+                    const float px = sX[row * 3 + 0], py = sX[row * 3 + 1], pz = sX[row * 3 + 2];
+                    v.x = fmaf(sW1[(k + 0) * 3 + 2], pz, fmaf(sW1[(k + 0) * 3 + 1], py, sW1[(k + 0) * 3 + 0] * px)) + sB1[k + 0];
+                    v.y = fmaf(sW1[(k + 1) * 3 + 2], pz, fmaf(sW1[(k + 1) * 3 + 1], py, sW1[(k + 1) * 3 + 0] * px)) + sB1[k + 1];
+                    v.z = fmaf(sW1[(k + 2) * 3 + 2], pz, fmaf(sW1[(k + 2) * 3 + 1], py, sW1[(k + 2) * 3 + 0] * px)) + sB1[k + 2];
+                    v.w = fmaf(sW1[(k + 3) * 3 + 2], pz, fmaf(sW1[(k + 3) * 3 + 1], py, sW1[(k + 3) * 3 + 0] * px)) + sB1[k + 3];
+                } else {
+                    v = __ldg(reinterpret_cast<const float4 *>(in_tile + (size_t)row * c_in + k));
+                }
                 v.x = fmaf(v.x, sScale[k + 0], sShift[k + 0]); v.y = fmaf(v.y, sScale[k + 1], sShift[k + 1]);
                 v.z = fmaf(v.z, sScale[k + 2], sShift[k + 2]); v.w = fmaf(v.w, sScale[k + 3], sShift[k + 3]);
                 if (P.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -281,6 +281,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, NOUT);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Input moments -> BatchNorm statistics of the first layer, analytically.  Layer 1 is affine in the point (y = W1 p + b1),
+// so sum_y[c] = cnt*(w_c.mu + b_c) and sum_y2[c] = cnt*(var_c + mean_c^2) with var_c = w_c^T Cov(p) w_c.  Twelve sums over the
+// cloud (fp32 per thread, fp64 across threads) replace an 8.4 MB activation write + read and a full pass of statistics.
+// The last CTA to arrive converts the moments into the (sum, sumsq) layout every other layer uses.
+// mom: [0..2] sum p, [3..8] sum xx,xy,xz,yy,yz,zz ; counter: arrival count (both zeroed by the caller's memset)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) x_moments_kernel(int b, int n, int layout, const float *__restrict__ x, double *mom, unsigned *counter,
+                                                        const float *__restrict__ w1, const float *__restrict__ b1, int c1, double *stats0)
+{
+    __shared__ double s_red[9][8];
+    __shared__ bool s_last;
+    const long long total = (long long)b * n;
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long bi = i / n, p = i % n;
+        float px, py, pz;
+        if (layout == SNB200_BNC) { const float *q = x + (bi * n + p) * 3; px = q[0]; py = q[1]; pz = q[2]; }
+        else { const float *q = x + bi * n * 3 + p; px = q[0]; py = q[n]; pz = q[2 * (size_t)n]; }
+        acc[0] += px; acc[1] += py; acc[2] += pz;
+        acc[3] = fmaf(px, px, acc[3]); acc[4] = fmaf(px, py, acc[4]); acc[5] = fmaf(px, pz, acc[5]);
+        acc[6] = fmaf(py, py, acc[6]); acc[7] = fmaf(py, pz, acc[7]); acc[8] = fmaf(pz, pz, acc[8]);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        double v = (double)acc[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+        if (lane == 0) s_red[j][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0;
+        for (int w = 0; w < 8; w++) v += s_red[threadIdx.x][w];
+        atomicAdd(mom + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double cnt = (double)total;
+    volatile double *vm = mom;
+    const double mx = vm[0] / cnt, my = vm[1] / cnt, mz = vm[2] / cnt;
+    const double cxx = vm[3] / cnt - mx * mx, cxy = vm[4] / cnt - mx * my, cxz = vm[5] / cnt - mx * mz;
+    const double cyy = vm[6] / cnt - my * my, cyz = vm[7] / cnt - my * mz, czz = vm[8] / cnt - mz * mz;
+    for (int c = threadIdx.x; c < c1; c += 256) {
+        const double a0 = w1[c * 3 + 0], a1 = w1[c * 3 + 1], a2 = w1[c * 3 + 2];
+        const double mean = a0 * mx + a1 * my + a2 * mz + (b1 ? (double)b1[c] : 0.0);
+        double var = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
+        if (var < 0) var = 0;
+        stats0[c] = cnt * mean;
+        stats0[c1 + c] = cnt * (var + mean * mean);
+    }
+}
+
+int launch_x_moments(int b, int n, int layout, const float *x, double *mom, unsigned *counter, const float *w1, const float *b1, int c1,
+                     double *stats0, cudaStream_t stream)
+{
+    const long long total = (long long)b * n;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    x_moments_kernel<<<blocks, 256, 0, stream>>>(b, n, layout, x, mom, counter, w1, b1, c1, stats0);
+    return check_launch("encoder input moments");
 }
 
 static size_t tc_smem_bytes(int nout)

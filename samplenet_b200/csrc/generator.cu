@@ -1,0 +1,387 @@
+// generator.cu -- orchestration of the whole SampleNet generator (samplenet.py:90-104) and its fused FC head.
+//
+//   training step at the headline size, tensor-core path:            launches
+//     cudaMemsetAsync(statistics)                                     (memset node)
+//     x_moments_kernel            input moments -> BN1 statistics      1
+//     tc_layer_kernel x4          layers 2..5 (layer 1 fused in #2)    4
+//     fc_head_cluster_kernel      max-pool finalise + fc1..fc4         1
+//
+// The FC head (samplenet.py:99-104: 128->256->256->256->3M on B rows, BatchNorm over the batch) is tiny (7 MFLOP, 0.86 MB of
+// weights) but has four layer-to-layer dependencies; as separate launches it cost 4 x 17 us.  Here ONE thread-block
+// cluster runs all of it: every CTA owns a slice of the output channels of each layer (so BatchNorm over the batch never
+// leaves a warp: lane = batch row), activations are exchanged through a 32 KB global scratch that stays in L2, and layers
+// are separated by cluster barriers.  The same kernel first turns the last conv layer's per-tile extrema into the pooled
+// feature and applies every BatchNorm running-statistics update exactly once.
+#include "encoder_internal.cuh"
+#include <cooperative_groups.h>
+#include <string.h>
+namespace cg = cooperative_groups;
+
+namespace snb {
+
+constexpr int kHeadThreads = 128;      // 4 warps x 4 output channels
+constexpr int kHeadChPerCta = 16;
+constexpr int kHeadMaxCluster = 16;
+
+struct HeadLayer {
+    int c_in, c_out;
+    const float *weight, *bias, *gamma, *beta;
+    float *run_mean, *run_var;
+    float eps, momentum;
+    int has_bn, relu;
+};
+
+struct HeadParams {
+    int b, training;
+    // pooling of the last conv layer
+    int c_feat, tiles_per_cloud;
+    const float *tile_max, *tile_min;
+    const double *last_stats;
+    const float *last_gamma, *last_beta, *last_run_mean, *last_run_var;
+    float last_eps;
+    int last_has_bn, last_relu;
+    double count;
+    float *feat;                 // (b, c_feat) global: pooled feature (also an API output)
+    // running-statistics updates of the conv layers
+    int ru_num;
+    const double *ru_stats[SNB200_MAX_CONV_LAYERS];
+    float *ru_mean[SNB200_MAX_CONV_LAYERS];
+    float *ru_var[SNB200_MAX_CONV_LAYERS];
+    float ru_momentum[SNB200_MAX_CONV_LAYERS];
+    int ru_c[SNB200_MAX_CONV_LAYERS];
+    // FC layers
+    int num_fc;
+    HeadLayer fc[SNB200_MAX_FC_LAYERS];
+    float *act[2];               // (b, max width) scratch
+    float *out;                  // (b, c_out_last)
+    int out_inner;
+};
+
+__device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_total, int c, double count, const float *gamma, const float *beta,
+                                                    const float *run_mean, const float *run_var, float eps, int training, float &scale, float &shift)
+{
+    float mean, var;
+    if (training) {
+        const double m = stats[c] / count;
+        double v = stats[c_total + c] / count - m * m;
+        if (v < 0) v = 0;
+        mean = (float)m; var = (float)v;
+    } else {
+        mean = run_mean[c]; var = run_var[c];
+    }
+    const float invstd = 1.0f / sqrtf(var + eps);
+    scale = gamma[c] * invstd;
+    shift = beta[c] - mean * scale;
+}
+
+// RG = number of 32-row groups of the batch (b <= 32*RG)
+template <int RG>
+__global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __grid_constant__ HeadParams P)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = cluster.block_rank(), csize = cluster.num_blocks();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    extern __shared__ __align__(16) float smem[];
+    // s_in: [c_in_max][33] one row group of the input, transposed; s_w: [c_in_max][16] this CTA's weight slice, transposed
+    int cmax = P.c_feat;
+    for (int l = 0; l < P.num_fc; l++) cmax = max(cmax, P.fc[l].c_in);
+    float *s_in = smem;
+    float *s_w = smem + (size_t)cmax * 33;
+
+    // ---- phase 0: pooled feature (this CTA's share) + running statistics of the conv stack (rank 0)
+    {
+        const int total = P.b * P.c_feat;
+        for (int e = rank * kHeadThreads + tid; e < total; e += csize * kHeadThreads) {
+            const int bi = e / P.c_feat, c = e % P.c_feat;
+            float mx = -INFINITY, mn = INFINITY;
+            for (int t = 0; t < P.tiles_per_cloud; t++) {
+                mx = fmaxf(mx, __ldg(P.tile_max + ((size_t)bi * P.tiles_per_cloud + t) * P.c_feat + c));
+                mn = fminf(mn, __ldg(P.tile_min + ((size_t)bi * P.tiles_per_cloud + t) * P.c_feat + c));
+            }
+            float v = mx;
+            if (P.last_has_bn) {
+                float sc, sh;
+                head_bn_scale_shift(P.last_stats, P.c_feat, c, P.count, P.last_gamma, P.last_beta, P.last_run_mean, P.last_run_var, P.last_eps,
+                                    P.training, sc, sh);
+                v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);  // max over points of a monotone map
+            }
+            if (P.last_relu) v = fmaxf(v, 0.f);
+            P.feat[e] = v;
+        }
+    }
+    cluster.sync();
+    if (rank == 0 && P.training) {  // after the barrier: every read of the running buffers (eval mode only) is irrelevant here
+        for (int l = 0; l < P.ru_num; l++)
+            for (int c = tid; c < P.ru_c[l]; c += kHeadThreads) {
+                const double m = P.ru_stats[l][c] / P.count;
+                double v = P.ru_stats[l][P.ru_c[l] + c] / P.count - m * m;
+                if (v < 0) v = 0;
+                const double unb = P.count > 1 ? v * P.count / (P.count - 1) : v;
+                const float mom = P.ru_momentum[l];
+                if (P.ru_mean[l]) P.ru_mean[l][c] = (1.f - mom) * P.ru_mean[l][c] + mom * (float)m;
+                if (P.ru_var[l]) P.ru_var[l][c] = (1.f - mom) * P.ru_var[l][c] + mom * (float)unb;
+            }
+    }
+
+    // ---- FC layers
+    const float *cur = P.feat;
+    for (int l = 0; l < P.num_fc; l++) {
+        const HeadLayer &L = P.fc[l];
+        const bool last = (l == P.num_fc - 1);
+        float *dst = last ? P.out : P.act[l & 1];
+        const int per_cta = (L.c_out + csize - 1) / csize;
+        const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
+        for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels
+            const int nch = min(kHeadChPerCta, c_hi - cb);
+            __syncthreads();
+            // weight slice, transposed: s_w[k][j] = W[cb+j][k]; lanes along j (conflict-free stores)
+            for (int e = tid; e < L.c_in * kHeadChPerCta; e += kHeadThreads) {
+                const int j = e % kHeadChPerCta, k = e / kHeadChPerCta;
+                s_w[e] = (j < nch) ? __ldg(L.weight + (size_t)(cb + j) * L.c_in + k) : 0.f;
+            }
+            float acc[RG][4];
+#pragma unroll
+            for (int g = 0; g < RG; g++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[g][j] = 0.f;
+#pragma unroll
+            for (int g = 0; g < RG; g++) {
+                const int r0 = g * 32;
+                if (r0 < P.b) {   // uniform
+                    const int rn = min(32, P.b - r0);
+                    __syncthreads();
+                    // input rows r0..r0+rn-1, transposed: s_in[k][r]; lanes along k for coalesced reads
+                    for (int e = tid; e < rn * L.c_in; e += kHeadThreads) {
+                        const int k = e % L.c_in, r = e / L.c_in;
+                        s_in[k * 33 + r] = cur[(size_t)(r0 + r) * L.c_in + k];
+                    }
+                    __syncthreads();
+                    const int ldr = min(lane, rn - 1);
+#pragma unroll 4
+                    for (int k = 0; k < L.c_in; k++) {
+                        const float a = s_in[k * 33 + ldr];
+                        const float4 w = *reinterpret_cast<const float4 *>(s_w + k * kHeadChPerCta + warp * 4);
+                        acc[g][0] = fmaf(a, w.x, acc[g][0]); acc[g][1] = fmaf(a, w.y, acc[g][1]);
+                        acc[g][2] = fmaf(a, w.z, acc[g][2]); acc[g][3] = fmaf(a, w.w, acc[g][3]);
+                    }
+                }
+            }
+            // bias, BatchNorm over the batch (rows live in lanes x row groups), activation, store
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = cb + warp * 4 + j;
+                const bool cv = (warp * 4 + j) < nch;   // warp-uniform
+                const float bias = (cv && L.bias) ? L.bias[c] : 0.f;
+                float scale = 1.f, shift = 0.f;
+#pragma unroll
+                for (int g = 0; g < RG; g++) acc[g][j] += bias;
+                if (L.has_bn && cv) {
+                    float mean, var;
+                    if (P.training) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int g = 0; g < RG; g++)
+                            if (g * 32 + lane < P.b) s += acc[g][j];
+                        mean = warp_sum(s) / (float)P.b;
+                        float q = 0.f;
+#pragma unroll
+                        for (int g = 0; g < RG; g++)
+                            if (g * 32 + lane < P.b) { const float d = acc[g][j] - mean; q = fmaf(d, d, q); }
+                        q = warp_sum(q);
+                        var = q / (float)P.b;
+                        if (lane == 0) {
+                            const float unb = P.b > 1 ? q / (float)(P.b - 1) : var;
+                            if (L.run_mean) L.run_mean[c] = (1.f - L.momentum) * L.run_mean[c] + L.momentum * mean;
+                            if (L.run_var) L.run_var[c] = (1.f - L.momentum) * L.run_var[c] + L.momentum * unb;
+                        }
+                    } else {
+                        mean = L.run_mean[c]; var = L.run_var[c];
+                    }
+                    const float invstd = 1.0f / sqrtf(var + L.eps);
+                    scale = L.gamma[c] * invstd;
+                    shift = L.beta[c] - mean * scale;
+                }
+                if (cv) {
+#pragma unroll
+                    for (int g = 0; g < RG; g++) {
+                        const int row = g * 32 + lane;
+                        if (row < P.b) {
+                            float v = L.has_bn ? fmaf(acc[g][j], scale, shift) : acc[g][j];
+                            if (L.relu) v = fmaxf(v, 0.f);
+                            const int oc = (last && P.out_inner > 0) ? (c % P.out_inner) * (L.c_out / P.out_inner) + c / P.out_inner : c;
+                            dst[(size_t)row * L.c_out + oc] = v;
+                        }
+                    }
+                }
+            }
+        }
+        cur = dst;
+        cluster.sync();   // the next layer reads every CTA's slice
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+struct GenWorkspace {
+    float *act[2];
+    char *stats_base; size_t stats_bytes;
+    double *mom; unsigned *counter;
+    double *stats[SNB200_MAX_CONV_LAYERS];
+    float *tile_max, *tile_min;
+    float *feat;
+    float *head_act[2];
+    size_t total;
+};
+
+static GenWorkspace carve_gen_ws(void *base, int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc)
+{
+    GenWorkspace W;
+    char *p = reinterpret_cast<char *>(base);
+    size_t off = 0;
+    int maxc = 8;
+    for (int l = 0; l + 1 < nconv; l++) maxc = max(maxc, conv[l].c_out);
+    const size_t act_bytes = align_up((size_t)b * n * maxc * sizeof(float), 256);
+    W.act[0] = reinterpret_cast<float *>(p + off); off += act_bytes;
+    W.act[1] = reinterpret_cast<float *>(p + off); off += act_bytes;
+    W.stats_base = p + off;
+    size_t sb = 0;
+    W.mom = reinterpret_cast<double *>(p + off + sb); sb += 16 * sizeof(double);
+    W.counter = reinterpret_cast<unsigned *>(p + off + sb); sb += 256 - 16 * sizeof(double);
+    for (int l = 0; l < nconv; l++) {
+        W.stats[l] = reinterpret_cast<double *>(p + off + sb);
+        sb += align_up((size_t)2 * conv[l].c_out * sizeof(double), 256);
+    }
+    W.stats_bytes = sb;
+    off += sb;
+    const int c_last = conv[nconv - 1].c_out;
+    const int tpc = (n + 127) / 128;  // upper bound over both paths (128- or 256-point tiles)
+    const size_t tb = align_up((size_t)b * tpc * c_last * sizeof(float), 256);
+    W.tile_max = reinterpret_cast<float *>(p + off); off += tb;
+    W.tile_min = reinterpret_cast<float *>(p + off); off += tb;
+    W.feat = reinterpret_cast<float *>(p + off); off += align_up((size_t)b * c_last * sizeof(float), 256);
+    int maxf = 8;
+    for (int l = 0; l < nfc; l++) maxf = max(maxf, fc[l].c_out);
+    const size_t hb = align_up((size_t)b * maxf * sizeof(float), 256);
+    W.head_act[0] = reinterpret_cast<float *>(p + off); off += hb;
+    W.head_act[1] = reinterpret_cast<float *>(p + off); off += hb;
+    W.total = off;
+    return W;
+}
+
+size_t generator_workspace_bytes(int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc)
+{
+    return carve_gen_ws(nullptr, b, n, nconv, conv, nfc, fc).total;
+}
+
+static bool tc_stack_supported(int nconv, const snb200_layer *conv)
+{
+    if (nconv < 2 || conv[0].c_in != 3) return false;
+    if (conv[0].c_out % 8 != 0 || conv[0].c_out > 256) return false;
+    for (int l = 1; l < nconv; l++)
+        if (!tc_layer_supported(conv[l].c_in, conv[l].c_out)) return false;
+    return true;
+}
+
+int launch_generator_forward(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc,
+                             int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream)
+{
+    GenWorkspace W = carve_gen_ws(workspace, b, n, nconv, conv, nfc, fc);
+    if (training) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);
+    const bool use_tc = !(flags & SNB200_GEN_EXACT_FP32) && tc_stack_supported(nconv, conv);
+    int tpc = 0;
+    if (use_tc) {
+        tpc = tc_tiles_per_cloud(n);
+        const snb200_layer &L0 = conv[0];
+        if (training && L0.bn_weight) {
+            int rc = launch_x_moments(b, n, layout, x, W.mom, W.counter, L0.weight, L0.bias, L0.c_out, W.stats[0], stream);
+            if (rc) return rc;
+        }
+        for (int l = 1; l < nconv; l++) {
+            const snb200_layer &L = conv[l], &Lp = conv[l - 1];
+            TcLayerParams P;
+            memset(&P, 0, sizeof(P));
+            P.b = b; P.n = n; P.tiles_per_cloud = tpc; P.c_in = L.c_in; P.c_out = L.c_out;
+            if (l == 1) { P.x = x; P.x_layout = layout; P.w1 = L0.weight; P.b1 = L0.bias; }
+            else P.in = W.act[(l - 1) & 1];
+            P.in_has_bn = Lp.bn_weight != nullptr; P.in_stats = W.stats[l - 1];
+            P.in_gamma = Lp.bn_weight; P.in_beta = Lp.bn_bias; P.in_run_mean = Lp.bn_running_mean; P.in_run_var = Lp.bn_running_var;
+            P.in_eps = Lp.bn_eps; P.in_relu = Lp.relu; P.in_training = training;
+            P.weight = L.weight; P.bias = L.bias;
+            const bool last = (l == nconv - 1);
+            P.out = last ? nullptr : W.act[l & 1];
+            P.out_stats = (training && L.bn_weight) ? W.stats[l] : nullptr;
+            P.tile_max = last ? W.tile_max : nullptr;
+            P.tile_min = last ? W.tile_min : nullptr;
+            int rc = launch_tc_layer(P, stream);
+            if (rc) return rc;
+        }
+    } else {
+        int rc = launch_simt_conv_stack(b, n, layout, x, nconv, conv, training, W.act[0], W.act[1], W.stats, W.tile_max, W.tile_min, &tpc, stream);
+        if (rc) return rc;
+    }
+
+    // ---- fused pool + FC head
+    HeadParams H;
+    memset(&H, 0, sizeof(H));
+    const snb200_layer &LL = conv[nconv - 1];
+    H.b = b; H.training = training; H.c_feat = LL.c_out; H.tiles_per_cloud = tpc;
+    H.tile_max = W.tile_max; H.tile_min = W.tile_min; H.last_stats = W.stats[nconv - 1];
+    H.last_gamma = LL.bn_weight; H.last_beta = LL.bn_bias; H.last_run_mean = LL.bn_running_mean; H.last_run_var = LL.bn_running_var;
+    H.last_eps = LL.bn_eps; H.last_has_bn = LL.bn_weight != nullptr; H.last_relu = LL.relu;
+    H.count = (double)b * (double)n;
+    H.feat = feat_out ? feat_out : W.feat;
+    if (training)
+        for (int l = 0; l < nconv; l++) {
+            if (!conv[l].bn_weight || (!conv[l].bn_running_mean && !conv[l].bn_running_var)) continue;
+            const int i = H.ru_num++;
+            H.ru_stats[i] = W.stats[l]; H.ru_mean[i] = conv[l].bn_running_mean; H.ru_var[i] = conv[l].bn_running_var;
+            H.ru_momentum[i] = conv[l].bn_momentum; H.ru_c[i] = conv[l].c_out;
+        }
+    H.num_fc = nfc;
+    int cmax = LL.c_out, max_out = 0;
+    for (int l = 0; l < nfc; l++) {
+        HeadLayer &D = H.fc[l];
+        D.c_in = fc[l].c_in; D.c_out = fc[l].c_out; D.weight = fc[l].weight; D.bias = fc[l].bias; D.gamma = fc[l].bn_weight; D.beta = fc[l].bn_bias;
+        D.run_mean = fc[l].bn_running_mean; D.run_var = fc[l].bn_running_var; D.eps = fc[l].bn_eps; D.momentum = fc[l].bn_momentum;
+        D.has_bn = fc[l].bn_weight != nullptr; D.relu = fc[l].relu;
+        cmax = max(cmax, D.c_in);
+        max_out = max(max_out, D.c_out);
+    }
+    H.act[0] = W.head_act[0]; H.act[1] = W.head_act[1];
+    H.out = out; H.out_inner = out_transpose_inner;
+    // cluster size: enough CTAs that the widest layer is a single 16-channel pass per CTA, capped at 16 (non-portable size)
+    int csize = 1;
+    while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;
+    const size_t smem = ((size_t)cmax * 33 + (size_t)cmax * kHeadChPerCta) * sizeof(float);
+    const int rg = (b + 31) / 32;
+    if (rg > 8) { set_error("generator: batch %d exceeds the FC head limit of 256 rows", b); return SNB200_EUNSUPPORTED; }
+    if (smem > 200 * 1024) { set_error("generator: FC width %d too large for the shared-memory tile", cmax); return SNB200_EUNSUPPORTED; }
+    static PerDeviceOnce once;
+    if (once.first()) {
+cudaFuncSetAttribute(fc_head_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(fc_head_cluster_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kHeadThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (rg == 1) e = cudaLaunchKernelEx(&cfg, fc_head_cluster_kernel<1>, H);
+    else if (rg == 2) e = cudaLaunchKernelEx(&cfg, fc_head_cluster_kernel<2>, H);
+    else if (rg <= 4) e = cudaLaunchKernelEx(&cfg, fc_head_cluster_kernel<4>, H);
+    else e = cudaLaunchKernelEx(&cfg, fc_head_cluster_kernel<8>, H);
+    if (e != cudaSuccess) { set_error("generator: FC head launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SNB200_ECUDA; }
+    return check_launch("generator FC head");
+}
+
+}  // namespace snb

@@ -325,13 +325,36 @@ def make_layers(specs):
     return arr, keep
 
 
-def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0):
-    """x (B,N,3)/(B,3,N) -> (B, c_out_last) : conv stack + max-pool + FC head, all on this library's kernels."""
+def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0, exact_fp32=False):
+    """x (B,N,3)/(B,3,N) -> (out (B, c_out_last), feat (B, c_conv_last)): conv stack + max-pool + FC head in ONE C-ABI call.
+    Default: conv layers on the tensor cores (tcgen05, 3xTF32) + cluster-fused FC head; exact_fp32=True: CUDA-core conv stack."""
     lay = _layout(layout)
     x = _req(x, "x")
     cdim = 2 if lay == BNC else 1
     if x.dim() != 3 or x.shape[cdim] != 3:
         raise RuntimeError("shape of x must be of [Batch x 3 x NumInPoints]")
+    b = x.shape[0]
+    n = x.shape[1] if lay == BNC else x.shape[2]
+    dev = x.device
+    conv, keep1 = make_layers(conv_specs)
+    fc, keep2 = make_layers(fc_specs)
+    with torch.cuda.device(dev):
+        wsb = int(lib().snb200_generator_workspace_bytes(b, n, len(conv_specs), conv, len(fc_specs), fc))
+        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        feat = torch.empty(b, conv[len(conv_specs) - 1].c_out, device=dev)
+        out = torch.empty(b, fc[len(fc_specs) - 1].c_out, device=dev)
+        check(lib().snb200_generator_forward(b, n, lay, _p(x), len(conv_specs), conv, len(fc_specs), fc, int(bool(training)), _p(out),
+                                             int(out_transpose_inner), _p(feat), _lib.GEN_EXACT_FP32 if exact_fp32 else 0, _p(ws), wsb,
+                                             _stream()), "generator_forward")
+    del keep1, keep2
+    return out, feat
+
+
+def generator_forward_unfused(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0):
+    """Same result through the two stand-alone entry points snb200_encoder_forward + snb200_fc_head_forward
+    (exact-fp32 CUDA-core kernels, one launch per layer)."""
+    lay = _layout(layout)
+    x = _req(x, "x")
     b = x.shape[0]
     n = x.shape[1] if lay == BNC else x.shape[2]
     dev = x.device

@@ -33,7 +33,7 @@ class _GeneratorFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, layout, training, out_inner, *params):
         conv_specs, fc_specs = net._layer_specs()
-        out, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, training, out_inner)
+        out, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, training, out_inner, exact_fp32=net.generator_precision == "fp32")
         ctx.net = net
         ctx.layout = layout
         ctx.training = training
@@ -105,6 +105,9 @@ class SampleNet(nn.Module):
             warnings.warn("SampleNet: input_shape is different to output_shape.")
         self.input_shape = input_shape
         self.output_shape = output_shape
+        # "3xtf32": conv layers 2..5 on the tensor cores, error-compensated to fp32 accuracy (default);
+        # "fp32":   exact-fp32 CUDA-core conv stack.  Not part of the reference signature; plain attribute.
+        self.generator_precision = "3xtf32"
 
     # ------------------------------------------------------------------------------------------ generator plumbing
     def _convs(self):
@@ -154,12 +157,12 @@ class SampleNet(nn.Module):
             y = _GeneratorFunction.apply(self, x, layout, self.training, out_inner, *params)
         else:
             conv_specs, fc_specs = self._layer_specs()
-            y, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, self.training, out_inner)
-        if self.training:
-            with torch.no_grad():
-                for _, bn in self._convs() + self._fcs():
-                    if bn is not None and bn.num_batches_tracked is not None:
-                        bn.num_batches_tracked += 1
+            y, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, self.training, out_inner, exact_fp32=self.generator_precision == "fp32")
+        if self.training:  # BatchNorm bookkeeping the kernels do not do: one fused multi-tensor add for all 8 counters
+            counters = [bn.num_batches_tracked for _, bn in self._convs() + self._fcs() if bn is not None and bn.num_batches_tracked is not None]
+            if counters:
+                with torch.no_grad():
+                    torch._foreach_add_(counters, 1)
         return y
 
     # ------------------------------------------------------------------------------------------ forward
