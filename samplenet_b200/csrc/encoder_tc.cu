@@ -23,7 +23,7 @@ namespace snb {
 
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;   // points per CTA == UMMA M
-constexpr int kTcKC = 64;   // K chunk resident in shared memory (2 swizzle atoms of 32 fp32)
+constexpr int kTcKC = 32;   // K chunk resident in shared memory: one swizzle atom of 32 fp32 (128 B rows)
 
 __device__ __forceinline__ void bn_scale_shift_tc(const double *stats, int c_total, int c, double count, const float *gamma, const float *beta,
                                                   const float *run_mean, const float *run_var, float eps, int training, float &scale, float &shift)
@@ -121,16 +121,21 @@ __device__ __forceinline__ void split_store(unsigned char *hi_base, unsigned cha
 }
 
 template <int NOUT>  // padded output width: 64, 128 or 256 (UMMA N and TMEM columns)
-__global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_constant__ TcLayerParams P)
+__global__ void __launch_bounds__(kTcThreads, (NOUT <= 128 ? 2 : 1)) tc_layer_kernel(const __grid_constant__ TcLayerParams P)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // operand buffers, each [atoms=2][rows][128 B]
+    // operand buffers, one 32-wide K atom each: [rows][128 B]
     constexpr uint32_t kAtomA = kTcM * 128, kAtomB = NOUT * 128;
+    constexpr int NA = (kTcM * 8) / kTcThreads;   // float4 loads per thread for the A atom (4)
+    constexpr int NB = (NOUT * 8) / kTcThreads;   // ... for the B atom (2 / 4 / 8)
+    constexpr int LD = NOUT + 1;
+    constexpr int H = kTcThreads / NOUT;          // row ranges in the epilogue reduction (4 / 2 / 1)
     unsigned char *sAhi = smem_raw;
-    unsigned char *sAlo = sAhi + 2 * kAtomA;
-    unsigned char *sBhi = sAlo + 2 * kAtomA;
-    unsigned char *sBlo = sBhi + 2 * kAtomB;
+    unsigned char *sAlo = sAhi + kAtomA;
+    unsigned char *sBhi = sAlo + kAtomA;
+    unsigned char *sBlo = sBhi + kAtomB;
     float *sStage = reinterpret_cast<float *>(smem_raw);  // epilogue: [128][NOUT+1] floats, aliases the operand buffers
+    float *sPart = sStage + kTcM * LD;                    // [H][NOUT][4] partial reductions
     __shared__ float sScale[256], sShift[256];
     __shared__ float sX[kTcM * 3], sW1[256 * 3], sB1[256];
     __shared__ uint64_t mma_bar;
@@ -176,36 +181,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
     const int nchunks = (c_in + kTcKC - 1) / kTcKC;
     for (int kc = 0; kc < nchunks; kc++) {
         const int k0 = kc * kTcKC;
-        // ---- A operand: 128 rows x 64 k (16 chunks of 4 floats per row); lanes run along k for coalesced reads
-        for (int e = tid; e < kTcM * (kTcKC / 4); e += kTcThreads) {
-            const int row = e >> 4, ch = e & 15;
-            const int k = k0 + ch * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < np && k < c_in) {  // c_in is a multiple of 4 on this path
+        // ---- 1. all global loads of this K chunk go out first (NA + NB independent 16-byte loads per thread) ...
+        float4 av[NA], wv[NB];
+#pragma unroll
+        for (int u = 0; u < NA; u++) {
+            const int e = tid + u * kTcThreads, row = e >> 3, k = k0 + (e & 7) * 4;
+            av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!P.x && row < np && k < c_in) av[u] = __ldg(reinterpret_cast<const float4 *>(in_tile + (size_t)row * c_in + k));
+        }
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int e = tid + u * kTcThreads, row = e >> 3, k = k0 + (e & 7) * 4;
+            wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < c_out && k < c_in) wv[u] = __ldg(reinterpret_cast<const float4 *>(P.weight + (size_t)row * c_in + k));
+        }
+        // ---- 2. ... and fly while the tensor core finishes the previous chunk (its operands live in the same buffers)
+        if (kc > 0) {
+            mbar_wait(&mma_bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+        }
+        // ---- 3. BatchNorm + ReLU of the previous layer, hi/lo split, swizzled store
+#pragma unroll
+        for (int u = 0; u < NA; u++) {
+            const int e = tid + u * kTcThreads, row = e >> 3, ch = e & 7, k = k0 + ch * 4;
+            float4 v = av[u];
+            if (row < np && k < c_in) {
                 if (P.x) {  // layer 1 on the fly: y = (w0*x + w1*y + w2*z) + b
                     const float px = sX[row * 3 + 0], py = sX[row * 3 + 1], pz = sX[row * 3 + 2];
                     v.x = fmaf(sW1[(k + 0) * 3 + 2], pz, fmaf(sW1[(k + 0) * 3 + 1], py, sW1[(k + 0) * 3 + 0] * px)) + sB1[k + 0];
                     v.y = fmaf(sW1[(k + 1) * 3 + 2], pz, fmaf(sW1[(k + 1) * 3 + 1], py, sW1[(k + 1) * 3 + 0] * px)) + sB1[k + 1];
                     v.z = fmaf(sW1[(k + 2) * 3 + 2], pz, fmaf(sW1[(k + 2) * 3 + 1], py, sW1[(k + 2) * 3 + 0] * px)) + sB1[k + 2];
                     v.w = fmaf(sW1[(k + 3) * 3 + 2], pz, fmaf(sW1[(k + 3) * 3 + 1], py, sW1[(k + 3) * 3 + 0] * px)) + sB1[k + 3];
-                } else {
-                    v = __ldg(reinterpret_cast<const float4 *>(in_tile + (size_t)row * c_in + k));
                 }
                 v.x = fmaf(v.x, sScale[k + 0], sShift[k + 0]); v.y = fmaf(v.y, sScale[k + 1], sShift[k + 1]);
                 v.z = fmaf(v.z, sScale[k + 2], sShift[k + 2]); v.w = fmaf(v.w, sScale[k + 3], sShift[k + 3]);
                 if (P.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             }
-            const uint32_t off = (uint32_t)(ch >> 3) * kAtomA + sw128_off(row, ch & 7, P.swizzle);
-            split_store(sAhi, sAlo, off, v);
+            split_store(sAhi, sAlo, sw128_off(row, ch, P.swizzle), v);
         }
-        // ---- B operand: NOUT rows (output channels) x 64 k from W (c_out, c_in) row-major
-        for (int e = tid; e < NOUT * (kTcKC / 4); e += kTcThreads) {
-            const int row = e >> 4, ch = e & 15;
-            const int k = k0 + ch * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < c_out && k < c_in) v = __ldg(reinterpret_cast<const float4 *>(P.weight + (size_t)row * c_in + k));
-            const uint32_t off = (uint32_t)(ch >> 3) * kAtomB + sw128_off(row, ch & 7, P.swizzle);
-            split_store(sBhi, sBlo, off, v);
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int e = tid + u * kTcThreads, row = e >> 3, ch = e & 7;
+            split_store(sBhi, sBlo, sw128_off(row, ch, P.swizzle), wv[u]);
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncthreads();
@@ -214,12 +232,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
             const int ksteps = min(kTcKC, c_in - k0) / 8;
 #pragma unroll 1
             for (int ks = 0; ks < ksteps; ks++) {
-                const uint32_t koff = (uint32_t)(ks >> 2);         // which 32-wide atom
-                const uint32_t kin = (uint32_t)(ks & 3) * P.k_adv16 * 16u;  // byte advance inside the atom (32 B per K=8 step)
-                const uint64_t a_hi = make_sdesc(smem_u32(sAhi) + koff * kAtomA + kin, P.desc_hi);
-                const uint64_t a_lo = make_sdesc(smem_u32(sAlo) + koff * kAtomA + kin, P.desc_hi);
-                const uint64_t b_hi = make_sdesc(smem_u32(sBhi) + koff * kAtomB + kin, P.desc_hi);
-                const uint64_t b_lo = make_sdesc(smem_u32(sBlo) + koff * kAtomB + kin, P.desc_hi);
+                const uint32_t kin = (uint32_t)ks * P.k_adv16 * 16u;  // byte advance inside the atom (32 B per K=8 step)
+                const uint64_t a_hi = make_sdesc(smem_u32(sAhi) + kin, P.desc_hi);
+                const uint64_t a_lo = make_sdesc(smem_u32(sAlo) + kin, P.desc_hi);
+                const uint64_t b_hi = make_sdesc(smem_u32(sBhi) + kin, P.desc_hi);
+                const uint64_t b_lo = make_sdesc(smem_u32(sBlo) + kin, P.desc_hi);
                 const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
                 umma_tf32(tmem_d, a_lo, b_hi, idesc, acc);   // small terms first, the dominant hi*hi last
                 umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
@@ -227,13 +244,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
             }
             umma_commit(&mma_bar);  // arrives when every MMA issued so far has finished reading smem / writing TMEM
         }
-        mbar_wait(&mma_bar, phase);
-        phase ^= 1;
-        tc_fence_after();
     }
+    mbar_wait(&mma_bar, phase);
+    tc_fence_after();
 
     // ---- epilogue: TMEM -> registers (+bias) -> HBM raw store and a padded shared-memory copy of the tile
-    constexpr int LD = NOUT + 1;
     {
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
@@ -263,20 +278,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_layer_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    // ---- per-channel reductions over the tile's valid rows, fixed order
-    for (int c = tid; c < c_out; c += kTcThreads) {
-        float s = 0.f, ss = 0.f, mx = -INFINITY, mn = INFINITY;
-        for (int r = 0; r < np; r++) {
+    // ---- per-channel reductions over the tile's valid rows: H row ranges in parallel, combined in fixed order
+    {
+        const int c = tid % NOUT, h = tid / NOUT;
+        const int r_lo = h * (kTcM / H), r_hi = min(np, (h + 1) * (kTcM / H));
+        float sm = 0.f, ss = 0.f, mx = -INFINITY, mn = INFINITY;
+        for (int r = r_lo; r < r_hi; r++) {
             const float v = sStage[r * LD + c];
-            s += v; ss = fmaf(v, v, ss); mx = fmaxf(mx, v); mn = fminf(mn, v);
+            sm += v; ss = fmaf(v, v, ss); mx = fmaxf(mx, v); mn = fminf(mn, v);
         }
-        if (P.out_stats) {
-            atomicAdd(P.out_stats + c, (double)s);
-            atomicAdd(P.out_stats + c_out + c, (double)ss);
-        }
-        if (P.tile_max) {
-            P.tile_max[(size_t)tile * c_out + c] = mx;
-            P.tile_min[(size_t)tile * c_out + c] = mn;
+        float *pp = sPart + ((size_t)h * NOUT + c) * 4;
+        pp[0] = sm; pp[1] = ss; pp[2] = mx; pp[3] = mn;
+        __syncthreads();
+        if (h == 0 && c < c_out) {
+            for (int g = 1; g < H; g++) {
+                const float *o = sPart + ((size_t)g * NOUT + c) * 4;
+                sm += o[0]; ss += o[1]; mx = fmaxf(mx, o[2]); mn = fminf(mn, o[3]);
+            }
+            if (P.out_stats) {
+                atomicAdd(P.out_stats + c, (double)sm);
+                atomicAdd(P.out_stats + c_out + c, (double)ss);
+            }
+            if (P.tile_max) {
+                P.tile_max[(size_t)tile * c_out + c] = mx;
+                P.tile_min[(size_t)tile * c_out + c] = mn;
+            }
         }
     }
     __syncthreads();
@@ -352,8 +378,8 @@ int launch_x_moments(int b, int n, int layout, const float *x, double *mom, unsi
 
 static size_t tc_smem_bytes(int nout)
 {
-    const size_t operands = 2 * 2 * (size_t)kTcM * 128 + 2 * 2 * (size_t)nout * 128;
-    const size_t stage = (size_t)kTcM * (nout + 1) * sizeof(float);
+    const size_t operands = 2 * (size_t)kTcM * 128 + 2 * (size_t)nout * 128;
+    const size_t stage = (size_t)kTcM * (nout + 1) * sizeof(float) + (size_t)kTcThreads * 4 * sizeof(float);
     return (operands > stage ? operands : stage) + 1024;  // + alignment slack
 }
 

@@ -74,6 +74,8 @@ __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_t
     shift = beta[c] - mean * scale;
 }
 
+// Batched staging helpers: issue up to 4 independent 16-byte loads per thread before touching shared memory, so that the
+// (L2-resident, tiny) operands arrive with one latency instead of one latency per element.
 // RG = number of 32-row groups of the batch (b <= 32*RG)
 template <int RG>
 __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __grid_constant__ HeadParams P)
@@ -82,21 +84,26 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
     const int rank = cluster.block_rank(), csize = cluster.num_blocks();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     extern __shared__ __align__(16) float smem[];
-    // s_in: [c_in_max][33] one row group of the input, transposed; s_w: [c_in_max][16] this CTA's weight slice, transposed
+    // s_in: [c_in_max][33]  one row group of the input, transposed (lane = batch row reads conflict-free)
+    // s_w : [16][c_in_max+4] this CTA's weight slice, row-major like in HBM (warp-uniform float4 reads broadcast)
     int cmax = P.c_feat;
     for (int l = 0; l < P.num_fc; l++) cmax = max(cmax, P.fc[l].c_in);
+    const int ldw = cmax + 4;
     float *s_in = smem;
     float *s_w = smem + (size_t)cmax * 33;
 
-    // ---- phase 0: pooled feature (this CTA's share) + running statistics of the conv stack (rank 0)
+    // ---- phase 0: pooled feature (this CTA's share)
     {
         const int total = P.b * P.c_feat;
         for (int e = rank * kHeadThreads + tid; e < total; e += csize * kHeadThreads) {
             const int bi = e / P.c_feat, c = e % P.c_feat;
             float mx = -INFINITY, mn = INFINITY;
+            const float *tm = P.tile_max + (size_t)bi * P.tiles_per_cloud * P.c_feat + c;
+            const float *tn = P.tile_min + (size_t)bi * P.tiles_per_cloud * P.c_feat + c;
+#pragma unroll 8
             for (int t = 0; t < P.tiles_per_cloud; t++) {
-                mx = fmaxf(mx, __ldg(P.tile_max + ((size_t)bi * P.tiles_per_cloud + t) * P.c_feat + c));
-                mn = fminf(mn, __ldg(P.tile_min + ((size_t)bi * P.tiles_per_cloud + t) * P.c_feat + c));
+                mx = fmaxf(mx, __ldg(tm + (size_t)t * P.c_feat));
+                mn = fminf(mn, __ldg(tn + (size_t)t * P.c_feat));
             }
             float v = mx;
             if (P.last_has_bn) {
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         }
     }
     cluster.sync();
-    if (rank == 0 && P.training) {  // after the barrier: every read of the running buffers (eval mode only) is irrelevant here
+    if (rank == csize - 1 && P.training) {  // running statistics of the conv stack, exactly once
         for (int l = 0; l < P.ru_num; l++)
             for (int c = tid; c < P.ru_c[l]; c += kHeadThreads) {
                 const double m = P.ru_stats[l][c] / P.count;
@@ -129,15 +136,35 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         const HeadLayer &L = P.fc[l];
         const bool last = (l == P.num_fc - 1);
         float *dst = last ? P.out : P.act[l & 1];
+        const int c_in = L.c_in;
         const int per_cta = (L.c_out + csize - 1) / csize;
         const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
+        const bool vec = (c_in & 3) == 0;
         for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels
             const int nch = min(kHeadChPerCta, c_hi - cb);
             __syncthreads();
-            // weight slice, transposed: s_w[k][j] = W[cb+j][k]; lanes along j (conflict-free stores)
-            for (int e = tid; e < L.c_in * kHeadChPerCta; e += kHeadThreads) {
-                const int j = e % kHeadChPerCta, k = e / kHeadChPerCta;
-                s_w[e] = (j < nch) ? __ldg(L.weight + (size_t)(cb + j) * L.c_in + k) : 0.f;
+            // weight slice: rows cb..cb+nch-1 of W (c_out, c_in), copied row-major with coalesced 16-byte loads, 4 in flight
+            if (vec) {
+                const int q = c_in >> 2, total = kHeadChPerCta * q;
+                for (int e0 = tid; e0 < total; e0 += kHeadThreads * 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * kHeadThreads;
+                        const int jr = e / q, kq = e % q;
+                        v[u] = (e < total && jr < nch) ? __ldg(reinterpret_cast<const float4 *>(L.weight + (size_t)(cb + jr) * c_in) + kq) : make_float4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * kHeadThreads;
+                        if (e < total) *reinterpret_cast<float4 *>(s_w + (e / q) * ldw + (e % q) * 4) = v[u];
+                    }
+                }
+            } else {
+                for (int e = tid; e < kHeadChPerCta * c_in; e += kHeadThreads) {
+                    const int jr = e / c_in, k = e % c_in;
+                    s_w[jr * ldw + k] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
+                }
             }
             float acc[RG][4];
 #pragma unroll
@@ -150,19 +177,45 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                 if (r0 < P.b) {   // uniform
                     const int rn = min(32, P.b - r0);
                     __syncthreads();
-                    // input rows r0..r0+rn-1, transposed: s_in[k][r]; lanes along k for coalesced reads
-                    for (int e = tid; e < rn * L.c_in; e += kHeadThreads) {
-                        const int k = e % L.c_in, r = e / L.c_in;
-                        s_in[k * 33 + r] = cur[(size_t)(r0 + r) * L.c_in + k];
+                    // input rows r0..r0+rn-1, transposed into s_in[k][r]; produced by other CTAs of this kernel: plain loads
+                    if (vec) {
+                        const int q = c_in >> 2, total = rn * q;
+                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 4) {
+                            float4 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int e = e0 + u * kHeadThreads;
+                                v[u] = (e < total) ? *(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + e / q) * c_in) + (e % q)) : make_float4(0, 0, 0, 0);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int e = e0 + u * kHeadThreads;
+                                if (e < total) {
+                                    const int r = e / q, k = (e % q) * 4;
+                                    s_in[(k + 0) * 33 + r] = v[u].x; s_in[(k + 1) * 33 + r] = v[u].y;
+                                    s_in[(k + 2) * 33 + r] = v[u].z; s_in[(k + 3) * 33 + r] = v[u].w;
+                                }
+                            }
+                        }
+                    } else {
+                        for (int e = tid; e < rn * c_in; e += kHeadThreads) s_in[(e % c_in) * 33 + e / c_in] = cur[(size_t)(r0 + e / c_in) * c_in + e % c_in];
                     }
                     __syncthreads();
                     const int ldr = min(lane, rn - 1);
-#pragma unroll 4
-                    for (int k = 0; k < L.c_in; k++) {
+                    const float *wrow = s_w + (warp * 4) * ldw;
+                    int k = 0;
+                    for (; k + 4 <= c_in; k += 4) {
+                        const float a0 = s_in[(k + 0) * 33 + ldr], a1 = s_in[(k + 1) * 33 + ldr], a2 = s_in[(k + 2) * 33 + ldr], a3 = s_in[(k + 3) * 33 + ldr];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float4 w = *reinterpret_cast<const float4 *>(wrow + j * ldw + k);
+                            acc[g][j] = fmaf(a3, w.w, fmaf(a2, w.z, fmaf(a1, w.y, fmaf(a0, w.x, acc[g][j]))));
+                        }
+                    }
+                    for (; k < c_in; k++) {
                         const float a = s_in[k * 33 + ldr];
-                        const float4 w = *reinterpret_cast<const float4 *>(s_w + k * kHeadChPerCta + warp * 4);
-                        acc[g][0] = fmaf(a, w.x, acc[g][0]); acc[g][1] = fmaf(a, w.y, acc[g][1]);
-                        acc[g][2] = fmaf(a, w.z, acc[g][2]); acc[g][3] = fmaf(a, w.w, acc[g][3]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[g][j] = fmaf(a, wrow[j * ldw + k], acc[g][j]);
                     }
                 }
             }
@@ -178,11 +231,11 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                 if (L.has_bn && cv) {
                     float mean, var;
                     if (P.training) {
-                        float s = 0.f;
+                        float sm = 0.f;
 #pragma unroll
                         for (int g = 0; g < RG; g++)
-                            if (g * 32 + lane < P.b) s += acc[g][j];
-                        mean = warp_sum(s) / (float)P.b;
+                            if (g * 32 + lane < P.b) sm += acc[g][j];
+                        mean = warp_sum(sm) / (float)P.b;
                         float q = 0.f;
 #pragma unroll
                         for (int g = 0; g < RG; g++)
@@ -353,7 +406,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     // cluster size: enough CTAs that the widest layer is a single 16-channel pass per CTA, capped at 16 (non-portable size)
     int csize = 1;
     while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;
-    const size_t smem = ((size_t)cmax * 33 + (size_t)cmax * kHeadChPerCta) * sizeof(float);
+    const size_t smem = ((size_t)cmax * 33 + (size_t)kHeadChPerCta * (cmax + 4)) * sizeof(float);
     const int rg = (b + 31) / 32;
     if (rg > 8) { set_error("generator: batch %d exceeds the FC head limit of 256 rows", b); return SNB200_EUNSUPPORTED; }
     if (smem > 200 * 1024) { set_error("generator: FC width %d too large for the shared-memory tile", cmax); return SNB200_EUNSUPPORTED; }
