@@ -253,6 +253,29 @@ int launch_chamfer_backward(int b, int n, const float *xyz1, int m, const float 
 // One CTA: per-cloud partials are produced by warps in a fixed order and summed in a fixed order (the reference
 // uses four separate torch reductions; values agree to fp32 rounding).
 // ------------------------------------------------------------------------------------------------------------------
+// all of a lane's loads are issued before the first add (the arrays are a few KB: latency, not bandwidth, is the cost)
+__device__ __forceinline__ void lane_sum_max(const float *__restrict__ p, int n, int lane, float &sum, float &mx)
+{
+    sum = 0.f; mx = -INFINITY;
+    if (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (n & 3) == 0) {
+        const float4 *q = reinterpret_cast<const float4 *>(p);
+        const int n4 = n >> 2;
+        for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (j0 + u * 32 < n4) ? __ldg(q + j0 + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (j0 + u * 32 < n4) {
+                    sum += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+                    mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+                }
+        }
+    } else {
+        for (int j = lane; j < n; j += 32) { const float v = __ldg(p + j); sum += v; mx = fmaxf(mx, v); }
+    }
+}
+
 __global__ void __launch_bounds__(1024) simplification_reduce_kernel(int b, int n, int m, const float *__restrict__ dist1,
                                                                     const float *__restrict__ dist2, float w, float *__restrict__ out4)
 {
@@ -260,13 +283,9 @@ __global__ void __launch_bounds__(1024) simplification_reduce_kernel(int b, int 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float acc1 = 0, accmax = 0, acc2 = 0;  // per-warp accumulators over the clouds this warp owns (lane 0 meaningful)
     for (int bi = warp; bi < b; bi += nwarps) {
-        float s1 = 0, mx = -INFINITY, s2 = 0;
-        for (int j = lane; j < n; j += 32) {
-            const float v = dist1[(size_t)bi * n + j];
-            s1 += v;
-            mx = fmaxf(mx, v);
-        }
-        for (int j = lane; j < m; j += 32) s2 += dist2[(size_t)bi * m + j];
+        float s1, mx, s2, unused;
+        lane_sum_max(dist1 + (size_t)bi * n, n, lane, s1, mx);
+        lane_sum_max(dist2 + (size_t)bi * m, m, lane, s2, unused);
         s1 = warp_sum(s1);
         mx = warp_max(mx);
         s2 = warp_sum(s2);

@@ -19,7 +19,7 @@ namespace cg = cooperative_groups;
 
 namespace snb {
 
-constexpr int kHeadThreads = 128;      // 4 warps x 4 output channels
+constexpr int kHeadThreads = 256;      // 8 warps x 2 output channels
 constexpr int kHeadChPerCta = 16;
 constexpr int kHeadMaxCluster = 16;
 
@@ -74,9 +74,11 @@ __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_t
     shift = beta[c] - mean * scale;
 }
 
-// Batched staging helpers: issue up to 4 independent 16-byte loads per thread before touching shared memory, so that the
-// (L2-resident, tiny) operands arrive with one latency instead of one latency per element.
-// RG = number of 32-row groups of the batch (b <= 32*RG)
+// RG = number of 32-row groups of the batch (b <= 32*RG).  8 warps x 2 output channels = 16 channels per CTA per pass.
+// Everything here is a latency chain (4 dependent layers on 32 rows), so the kernel is organised around taking loads off
+// that chain: the weight slices of ALL layers do not depend on activations and are fetched by TMA bulk copies
+// (cp.async.bulk -> one mbarrier per layer) the moment the kernel starts; the per-layer input tile (32 x c_in) is fetched with
+// all of a thread's 16-byte loads in flight at once.
 template <int RG>
 __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __grid_constant__ HeadParams P)
 {
@@ -84,17 +86,42 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
     const int rank = cluster.block_rank(), csize = cluster.num_blocks();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     extern __shared__ __align__(16) float smem[];
-    // s_in: [c_in_max][33]  one row group of the input, transposed (lane = batch row reads conflict-free)
-    // s_w : [16][c_in_max+4] this CTA's weight slice, row-major like in HBM (warp-uniform float4 reads broadcast)
+    __shared__ uint64_t wbar[SNB200_MAX_FC_LAYERS];
+    // s_in: [c_in_max][33]            one row group of the input, transposed (lane = batch row reads conflict-free)
+    // s_w : per layer [16][c_in+4]    this CTA's first 16-channel weight slice, row-major like in HBM (warp-uniform reads broadcast)
     int cmax = P.c_feat;
     for (int l = 0; l < P.num_fc; l++) cmax = max(cmax, P.fc[l].c_in);
-    const int ldw = cmax + 4;
     float *s_in = smem;
-    float *s_w = smem + (size_t)cmax * 33;
+    float *s_w[SNB200_MAX_FC_LAYERS];
+    {
+        float *p = smem + (size_t)cmax * 33;
+        for (int l = 0; l < P.num_fc; l++) { s_w[l] = p; p += (size_t)kHeadChPerCta * (P.fc[l].c_in + 4); }
+    }
+    // ---- weight prefetch for every layer (pass 0 of this CTA), TMA bulk, one mbarrier per layer
+    if (tid == 0) {
+        for (int l = 0; l < P.num_fc; l++) mbar_init(&wbar[l], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int l = 0; l < P.num_fc; l++) {
+            const HeadLayer &L = P.fc[l];
+            const int per_cta = (L.c_out + csize - 1) / csize;
+            const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
+            const int nch = max(0, min(kHeadChPerCta, c_hi - c_lo));
+            const bool tma_ok = (L.c_in & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+            if (tma_ok && nch > 0) {
+                mbar_expect_tx(&wbar[l], (uint32_t)nch * L.c_in * 4u);
+                for (int j = 0; j < nch; j++)
+                    tma_load_1d(s_w[l] + (size_t)j * (L.c_in + 4), L.weight + (size_t)(c_lo + j) * L.c_in, (uint32_t)L.c_in * 4u, &wbar[l]);
+            }
+        }
+    }
 
-    // ---- phase 0: pooled feature (this CTA's share)
+    // ---- phase 0: pooled feature (this CTA's share) and the conv stack's running statistics (spread over the cluster)
     {
         const int total = P.b * P.c_feat;
+        const double inv = 1.0 / P.count;
         for (int e = rank * kHeadThreads + tid; e < total; e += csize * kHeadThreads) {
             const int bi = e / P.c_feat, c = e % P.c_feat;
             float mx = -INFINITY, mn = INFINITY;
@@ -107,28 +134,41 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
             }
             float v = mx;
             if (P.last_has_bn) {
-                float sc, sh;
-                head_bn_scale_shift(P.last_stats, P.c_feat, c, P.count, P.last_gamma, P.last_beta, P.last_run_mean, P.last_run_var, P.last_eps,
-                                    P.training, sc, sh);
+                float mean, var;
+                if (P.training) {
+                    const double m = P.last_stats[c] * inv;
+                    double vv = P.last_stats[P.c_feat + c] * inv - m * m;
+                    if (vv < 0) vv = 0;
+                    mean = (float)m; var = (float)vv;
+                } else {
+                    mean = P.last_run_mean[c]; var = P.last_run_var[c];
+                }
+                const float sc = P.last_gamma[c] * (1.0f / sqrtf(var + P.last_eps));
+                const float sh = P.last_beta[c] - mean * sc;
                 v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);  // max over points of a monotone map
             }
             if (P.last_relu) v = fmaxf(v, 0.f);
             P.feat[e] = v;
         }
+        if (P.training) {   // training mode never reads the running buffers, so the update can go anywhere in the kernel
+            int base = 0;
+            const int gt = rank * kHeadThreads + tid, gn = csize * kHeadThreads;
+            for (int l = 0; l < P.ru_num; l++) {
+                for (int c = gt - base; c < P.ru_c[l]; c += gn) {
+                    if (c < 0) continue;
+                    const double m = P.ru_stats[l][c] * inv;
+                    double v = P.ru_stats[l][P.ru_c[l] + c] * inv - m * m;
+                    if (v < 0) v = 0;
+                    const double unb = P.count > 1 ? v * (P.count / (P.count - 1)) : v;
+                    const float mom = P.ru_momentum[l];
+                    if (P.ru_mean[l]) P.ru_mean[l][c] = (1.f - mom) * P.ru_mean[l][c] + mom * (float)m;
+                    if (P.ru_var[l]) P.ru_var[l][c] = (1.f - mom) * P.ru_var[l][c] + mom * (float)unb;
+                }
+                base = (base + P.ru_c[l]) % gn;
+            }
+        }
     }
     cluster.sync();
-    if (rank == csize - 1 && P.training) {  // running statistics of the conv stack, exactly once
-        for (int l = 0; l < P.ru_num; l++)
-            for (int c = tid; c < P.ru_c[l]; c += kHeadThreads) {
-                const double m = P.ru_stats[l][c] / P.count;
-                double v = P.ru_stats[l][P.ru_c[l] + c] / P.count - m * m;
-                if (v < 0) v = 0;
-                const double unb = P.count > 1 ? v * P.count / (P.count - 1) : v;
-                const float mom = P.ru_momentum[l];
-                if (P.ru_mean[l]) P.ru_mean[l][c] = (1.f - mom) * P.ru_mean[l][c] + mom * (float)m;
-                if (P.ru_var[l]) P.ru_var[l][c] = (1.f - mom) * P.ru_var[l][c] + mom * (float)unb;
-            }
-    }
 
     // ---- FC layers
     const float *cur = P.feat;
@@ -136,59 +176,44 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         const HeadLayer &L = P.fc[l];
         const bool last = (l == P.num_fc - 1);
         float *dst = last ? P.out : P.act[l & 1];
-        const int c_in = L.c_in;
+        const int c_in = L.c_in, ldw = c_in + 4;
         const int per_cta = (L.c_out + csize - 1) / csize;
         const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
         const bool vec = (c_in & 3) == 0;
-        for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels
+        const bool tma_ok = vec && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+        float *sw = s_w[l];
+        for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels (one pass unless c_out > 16*cluster)
             const int nch = min(kHeadChPerCta, c_hi - cb);
-            __syncthreads();
-            // weight slice: rows cb..cb+nch-1 of W (c_out, c_in), copied row-major with coalesced 16-byte loads, 4 in flight
-            if (vec) {
-                const int q = c_in >> 2, total = kHeadChPerCta * q;
-                for (int e0 = tid; e0 < total; e0 += kHeadThreads * 4) {
-                    float4 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = e0 + u * kHeadThreads;
-                        const int jr = e / q, kq = e % q;
-                        v[u] = (e < total && jr < nch) ? __ldg(reinterpret_cast<const float4 *>(L.weight + (size_t)(cb + jr) * c_in) + kq) : make_float4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = e0 + u * kHeadThreads;
-                        if (e < total) *reinterpret_cast<float4 *>(s_w + (e / q) * ldw + (e % q) * 4) = v[u];
-                    }
-                }
+            if (cb == c_lo && tma_ok) {
+                mbar_wait(&wbar[l], 0);                           // prefetched slice has landed
             } else {
+                __syncthreads();
                 for (int e = tid; e < kHeadChPerCta * c_in; e += kHeadThreads) {
                     const int jr = e / c_in, k = e % c_in;
-                    s_w[jr * ldw + k] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
+                    sw[jr * ldw + k] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
                 }
             }
-            float acc[RG][4];
+            float acc[RG][2];
 #pragma unroll
-            for (int g = 0; g < RG; g++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[g][j] = 0.f;
+            for (int g = 0; g < RG; g++) { acc[g][0] = 0.f; acc[g][1] = 0.f; }
 #pragma unroll
             for (int g = 0; g < RG; g++) {
                 const int r0 = g * 32;
                 if (r0 < P.b) {   // uniform
                     const int rn = min(32, P.b - r0);
                     __syncthreads();
-                    // input rows r0..r0+rn-1, transposed into s_in[k][r]; produced by other CTAs of this kernel: plain loads
+                    // input rows r0..r0+rn-1, transposed into s_in[k][r]; written by other CTAs of this kernel: plain loads.
                     if (vec) {
                         const int q = c_in >> 2, total = rn * q;
-                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 4) {
-                            float4 v[4];
+                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 8) {
+                            float4 v[8];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const int e = e0 + u * kHeadThreads;
                                 v[u] = (e < total) ? *(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + e / q) * c_in) + (e % q)) : make_float4(0, 0, 0, 0);
                             }
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const int e = e0 + u * kHeadThreads;
                                 if (e < total) {
                                     const int r = e / q, k = (e % q) * 4;
@@ -202,28 +227,26 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                     }
                     __syncthreads();
                     const int ldr = min(lane, rn - 1);
-                    const float *wrow = s_w + (warp * 4) * ldw;
+                    const float *w0 = sw + (warp * 2) * ldw, *w1 = w0 + ldw;
                     int k = 0;
                     for (; k + 4 <= c_in; k += 4) {
                         const float a0 = s_in[(k + 0) * 33 + ldr], a1 = s_in[(k + 1) * 33 + ldr], a2 = s_in[(k + 2) * 33 + ldr], a3 = s_in[(k + 3) * 33 + ldr];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float4 w = *reinterpret_cast<const float4 *>(wrow + j * ldw + k);
-                            acc[g][j] = fmaf(a3, w.w, fmaf(a2, w.z, fmaf(a1, w.y, fmaf(a0, w.x, acc[g][j]))));
-                        }
+                        const float4 u0 = *reinterpret_cast<const float4 *>(w0 + k), u1 = *reinterpret_cast<const float4 *>(w1 + k);
+                        acc[g][0] = fmaf(a3, u0.w, fmaf(a2, u0.z, fmaf(a1, u0.y, fmaf(a0, u0.x, acc[g][0]))));
+                        acc[g][1] = fmaf(a3, u1.w, fmaf(a2, u1.z, fmaf(a1, u1.y, fmaf(a0, u1.x, acc[g][1]))));
                     }
                     for (; k < c_in; k++) {
                         const float a = s_in[k * 33 + ldr];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[g][j] = fmaf(a, wrow[j * ldw + k], acc[g][j]);
+                        acc[g][0] = fmaf(a, w0[k], acc[g][0]);
+                        acc[g][1] = fmaf(a, w1[k], acc[g][1]);
                     }
                 }
             }
             // bias, BatchNorm over the batch (rows live in lanes x row groups), activation, store
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int c = cb + warp * 4 + j;
-                const bool cv = (warp * 4 + j) < nch;   // warp-uniform
+            for (int j = 0; j < 2; j++) {
+                const int c = cb + warp * 2 + j;
+                const bool cv = (warp * 2 + j) < nch;   // warp-uniform
                 const float bias = (cv && L.bias) ? L.bias[c] : 0.f;
                 float scale = 1.f, shift = 0.f;
 #pragma unroll
@@ -406,7 +429,9 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     // cluster size: enough CTAs that the widest layer is a single 16-channel pass per CTA, capped at 16 (non-portable size)
     int csize = 1;
     while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;
-    const size_t smem = ((size_t)cmax * 33 + (size_t)kHeadChPerCta * (cmax + 4)) * sizeof(float);
+    size_t wfloats = 0;
+    for (int l = 0; l < nfc; l++) wfloats += (size_t)kHeadChPerCta * (fc[l].c_in + 4);
+    const size_t smem = ((size_t)cmax * 33 + wfloats) * sizeof(float);
     const int rg = (b + 31) / 32;
     if (rg > 8) { set_error("generator: batch %d exceeds the FC head limit of 256 rows", b); return SNB200_EUNSUPPORTED; }
     if (smem > 200 * 1024) { set_error("generator: FC width %d too large for the shared-memory tile", cmax); return SNB200_EUNSUPPORTED; }

@@ -46,6 +46,17 @@ class _GeneratorFunction(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         net = ctx.net
         names = [n for n, _ in net._generator_named_parameters()]
+        # the recompute runs the reference layer stack in true fp32 (torch's cuDNN default would be plain TF32)
+        tf32_c, tf32_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            return _GeneratorFunction._backward(ctx, g, x, params, net, names)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_c, tf32_m
+
+    @staticmethod
+    def _backward(ctx, g, x, params, net, names):
         with torch.enable_grad():
             xs = x.detach().requires_grad_(ctx.needs_input_grad[1])
             ps = {n: p.detach().requires_grad_(p.requires_grad) for n, p in zip(names, params)}
