@@ -366,7 +366,9 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     if (training) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);
     const bool use_tc = !(flags & SNB200_GEN_EXACT_FP32) && tc_stack_supported(nconv, conv);
     int tpc = 0;
-    if (use_tc) {
+    if (flags & SNB200_GEN_PROFILE_SKIP_CONV) {
+        tpc = use_tc ? tc_tiles_per_cloud(n) : (n + (conv[nconv - 1].c_out > 64 ? 128 : 256) - 1) / (conv[nconv - 1].c_out > 64 ? 128 : 256);
+    } else if (use_tc) {
         tpc = tc_tiles_per_cloud(n);
         const snb200_layer &L0 = conv[0];
         if (training && L0.bn_weight) {
@@ -397,6 +399,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
         if (rc) return rc;
     }
 
+    if (flags & SNB200_GEN_PROFILE_SKIP_HEAD) return SNB200_OK;
     // ---- fused pool + FC head
     HeadParams H;
     memset(&H, 0, sizeof(H));
