@@ -19,7 +19,8 @@ namespace cg = cooperative_groups;
 
 namespace snb {
 
-constexpr int kHeadThreads = 256;      // 8 warps x 2 output channels
+constexpr int kHeadThreads = 1024;     // 32 warps: 8 channel pairs x 4 K-quarters
+constexpr int kHeadKSplit = 4;
 constexpr int kHeadChPerCta = 16;
 constexpr int kHeadMaxCluster = 16;
 
@@ -93,9 +94,11 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
     for (int l = 0; l < P.num_fc; l++) cmax = max(cmax, P.fc[l].c_in);
     float *s_in = smem;
     float *s_w[SNB200_MAX_FC_LAYERS];
+    float *s_part;
     {
         float *p = smem + (size_t)cmax * 33;
         for (int l = 0; l < P.num_fc; l++) { s_w[l] = p; p += (size_t)kHeadChPerCta * (P.fc[l].c_in + 4); }
+        s_part = p;   // [kHeadKSplit][16][33] partial dot products
     }
     // ---- weight prefetch for every layer (pass 0 of this CTA), TMA bulk, one mbarrier per layer
     if (tid == 0) {
@@ -205,15 +208,15 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                     // input rows r0..r0+rn-1, transposed into s_in[k][r]; written by other CTAs of this kernel: plain loads.
                     if (vec) {
                         const int q = c_in >> 2, total = rn * q;
-                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 8) {
-                            float4 v[8];
+                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 2) {
+                            float4 v[2];
 #pragma unroll
-                            for (int u = 0; u < 8; u++) {
+                            for (int u = 0; u < 2; u++) {
                                 const int e = e0 + u * kHeadThreads;
                                 v[u] = (e < total) ? *(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + e / q) * c_in) + (e % q)) : make_float4(0, 0, 0, 0);
                             }
 #pragma unroll
-                            for (int u = 0; u < 8; u++) {
+                            for (int u = 0; u < 2; u++) {
                                 const int e = e0 + u * kHeadThreads;
                                 if (e < total) {
                                     const int r = e / q, k = (e % q) * 4;
@@ -227,21 +230,39 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                     }
                     __syncthreads();
                     const int ldr = min(lane, rn - 1);
-                    const float *w0 = sw + (warp * 2) * ldw, *w1 = w0 + ldw;
-                    int k = 0;
-                    for (; k + 4 <= c_in; k += 4) {
+                    const int cp = warp & 7, kq = warp >> 3;                   // channel pair, K quarter
+                    const float *w0 = sw + (cp * 2) * ldw, *w1 = w0 + ldw;
+                    const int kr = ((c_in + 4 * kHeadKSplit - 1) / (4 * kHeadKSplit)) * 4;   // K range per quarter (multiple of 4)
+                    const int k_lo = kq * kr, k_hi = min(c_in, k_lo + kr);
+                    float p0 = 0.f, p1 = 0.f;
+                    int k = k_lo;
+#pragma unroll 4
+                    for (; k + 4 <= k_hi; k += 4) {
                         const float a0 = s_in[(k + 0) * 33 + ldr], a1 = s_in[(k + 1) * 33 + ldr], a2 = s_in[(k + 2) * 33 + ldr], a3 = s_in[(k + 3) * 33 + ldr];
                         const float4 u0 = *reinterpret_cast<const float4 *>(w0 + k), u1 = *reinterpret_cast<const float4 *>(w1 + k);
-                        acc[g][0] = fmaf(a3, u0.w, fmaf(a2, u0.z, fmaf(a1, u0.y, fmaf(a0, u0.x, acc[g][0]))));
-                        acc[g][1] = fmaf(a3, u1.w, fmaf(a2, u1.z, fmaf(a1, u1.y, fmaf(a0, u1.x, acc[g][1]))));
+                        p0 = fmaf(a3, u0.w, fmaf(a2, u0.z, fmaf(a1, u0.y, fmaf(a0, u0.x, p0))));
+                        p1 = fmaf(a3, u1.w, fmaf(a2, u1.z, fmaf(a1, u1.y, fmaf(a0, u1.x, p1))));
                     }
-                    for (; k < c_in; k++) {
+                    for (; k < k_hi; k++) {
                         const float a = s_in[k * 33 + ldr];
-                        acc[g][0] = fmaf(a, w0[k], acc[g][0]);
-                        acc[g][1] = fmaf(a, w1[k], acc[g][1]);
+                        p0 = fmaf(a, w0[k], p0);
+                        p1 = fmaf(a, w1[k], p1);
+                    }
+                    s_part[(kq * 16 + cp * 2 + 0) * 33 + lane] = p0;
+                    s_part[(kq * 16 + cp * 2 + 1) * 33 + lane] = p1;
+                    __syncthreads();
+                    if (warp < 8) {   // fixed-order combination of the K quarters
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int qd = 0; qd < kHeadKSplit; qd++) t += s_part[(qd * 16 + warp * 2 + jj) * 33 + lane];
+                            acc[g][jj] = t;
+                        }
                     }
                 }
             }
+            if (warp >= 8) continue;   // warps 8..31 only contribute partial sums (warp-uniform; no barrier below in this pass)
             // bias, BatchNorm over the batch (rows live in lanes x row groups), activation, store
 #pragma unroll
             for (int j = 0; j < 2; j++) {
@@ -434,7 +455,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;
     size_t wfloats = 0;
     for (int l = 0; l < nfc; l++) wfloats += (size_t)kHeadChPerCta * (fc[l].c_in + 4);
-    const size_t smem = ((size_t)cmax * 33 + wfloats) * sizeof(float);
+    const size_t smem = ((size_t)cmax * 33 + wfloats + (size_t)kHeadKSplit * 16 * 33) * sizeof(float);
     const int rg = (b + 31) / 32;
     if (rg > 8) { set_error("generator: batch %d exceeds the FC head limit of 256 rows", b); return SNB200_EUNSUPPORTED; }
     if (smem > 200 * 1024) { set_error("generator: FC width %d too large for the shared-memory tile", cmax); return SNB200_EUNSUPPORTED; }
