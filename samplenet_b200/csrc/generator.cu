@@ -15,6 +15,7 @@
 #include "encoder_internal.cuh"
 #include <cooperative_groups.h>
 #include <string.h>
+#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 namespace snb {
@@ -56,6 +57,7 @@ struct HeadParams {
     float *act[2];               // (b, max width) scratch
     float *out;                  // (b, c_out_last)
     int out_inner;
+    int dbg;                     // bring-up experiments (env SNB200_HEAD_DEBUG): 1 = stop after pooling, 2 = no TMA weight prefetch
 };
 
 __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_total, int c, double count, const float *gamma, const float *beta,
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !(P.dbg & 2)) {
         for (int l = 0; l < P.num_fc; l++) {
             const HeadLayer &L = P.fc[l];
             const int per_cta = (L.c_out + csize - 1) / csize;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         }
     }
     cluster.sync();
+    if (P.dbg & 1) return;
 
     // ---- FC layers
     const float *cur = P.feat;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         const int per_cta = (L.c_out + csize - 1) / csize;
         const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
         const bool vec = (c_in & 3) == 0;
-        const bool tma_ok = vec && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+        const bool tma_ok = vec && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0 && !(P.dbg & 2);
         float *sw = s_w[l];
         for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels (one pass unless c_out > 16*cluster)
             const int nch = min(kHeadChPerCta, c_hi - cb);
@@ -453,6 +456,12 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     // cluster size: enough CTAs that the widest layer is a single 16-channel pass per CTA, capped at 16 (non-portable size)
     int csize = 1;
     while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;
+    {
+        const char *dbg = getenv("SNB200_HEAD_DEBUG");
+        H.dbg = dbg ? atoi(dbg) : 0;
+        if (H.dbg & 4) csize = min(csize, 8);
+        if (H.dbg & 8) csize = min(csize, 4);
+    }
     size_t wfloats = 0;
     for (int l = 0; l < nfc; l++) wfloats += (size_t)kHeadChPerCta * (fc[l].c_in + 4);
     const size_t smem = ((size_t)cmax * 33 + wfloats + (size_t)kHeadKSplit * 16 * 33) * sizeof(float);
