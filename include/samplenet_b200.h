@@ -150,6 +150,9 @@ int snb200_generator_forward(int b, int n, int layout, const float *x, int num_c
 int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D,
                          unsigned desc_hi, int k_adv16, int swizzle, snb200_stream_t stream);
 
+/* Bring-up instrumentation: 64 SM-clock timestamps written by CTA 0 of the last FC-head launch (synchronous copy). */
+int snb200_debug_head_timestamps(long long *host_out64);
+
 /* Fully connected head on the pooled feature: in (b, c_in0) -> out (b, c_out_last).  BatchNorm over the batch.
  * out_transpose_inner = M > 0: each output row, logically (c_out_last/M, M) -- the reference's y.view(-1, 3, M),
  * samplenet.py:104 -- is stored transposed as (M, c_out_last/M), i.e. directly in BNC order; 0 = stored as is (BCN). */

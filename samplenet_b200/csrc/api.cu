@@ -55,6 +55,8 @@ size_t generator_workspace_bytes(int b, int n, int nconv, const snb200_layer *co
 int launch_generator_forward(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc,
                              int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream);
 
+int debug_head_timestamps(long long *host_out64);
+
 static int check_layers(const char *who, int num_layers, const snb200_layer *layers, int max_layers)
 {
     SNB_REQUIRE(layers != nullptr && num_layers >= 1 && num_layers <= max_layers, "%s: num_layers=%d out of range [1,%d]", who, num_layers, max_layers);
@@ -224,6 +226,8 @@ SNB_API int snb200_generator_forward(int b, int n, int layout, const float *x, i
     return launch_generator_forward(b, n, layout, x, num_conv, conv, num_fc, fc, training, out, out_transpose_inner, feat, flags, workspace,
                                     (cudaStream_t)stream);
 }
+
+SNB_API int snb200_debug_head_timestamps(long long *host_out64) { return debug_head_timestamps(host_out64); }
 
 SNB_API int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D, unsigned desc_hi,
                                  int k_adv16, int swizzle, snb200_stream_t stream)

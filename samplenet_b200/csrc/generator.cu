@@ -77,6 +77,10 @@ __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_t
     shift = beta[c] - mean * scale;
 }
 
+// bring-up instrumentation: SM-clock timestamps of CTA 0 / thread 0 at phase boundaries (read with snb200_debug_head_timestamps)
+__device__ long long g_head_ts[64];
+#define HEAD_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_head_ts[(i)] = clock64(); } while (0)
+
 // RG = number of 32-row groups of the batch (b <= 32*RG).  8 warps x 2 output channels = 16 channels per CTA per pass.
 // Everything here is a latency chain (4 dependent layers on 32 rows), so the kernel is organised around taking loads off
 // that chain: the weight slices of ALL layers do not depend on activations and are fetched by TMA bulk copies
@@ -102,6 +106,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         for (int l = 0; l < P.num_fc; l++) { s_w[l] = p; p += (size_t)kHeadChPerCta * (P.fc[l].c_in + 4); }
         s_part = p;   // [kHeadKSplit][16][33] partial dot products
     }
+    HEAD_TS(0);
     // ---- weight prefetch for every layer (pass 0 of this CTA), TMA bulk, one mbarrier per layer
     if (tid == 0) {
         for (int l = 0; l < P.num_fc; l++) mbar_init(&wbar[l], 1);
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         }
     }
 
+    HEAD_TS(1);
     // ---- phase 0: pooled feature (this CTA's share) and the conv stack's running statistics (spread over the cluster)
     {
         const int total = P.b * P.c_feat;
@@ -173,7 +179,9 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
             }
         }
     }
+    HEAD_TS(2);
     cluster.sync();
+    HEAD_TS(3);
     if (P.dbg & 1) return;
 
     // ---- FC layers
@@ -190,6 +198,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         float *sw = s_w[l];
         for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels (one pass unless c_out > 16*cluster)
             const int nch = min(kHeadChPerCta, c_hi - cb);
+            HEAD_TS(4 + l * 8 + 0);
             if (cb == c_lo && tma_ok) {
                 mbar_wait(&wbar[l], 0);                           // prefetched slice has landed
             } else {
@@ -207,7 +216,9 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                 const int r0 = g * 32;
                 if (r0 < P.b) {   // uniform
                     const int rn = min(32, P.b - r0);
+                    HEAD_TS(4 + l * 8 + 1);
                     __syncthreads();
+                    HEAD_TS(4 + l * 8 + 2);
                     // input rows r0..r0+rn-1, transposed into s_in[k][r]; written by other CTAs of this kernel: plain loads.
                     if (vec) {
                         const int q = c_in >> 2, total = rn * q;
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                         for (int e = tid; e < rn * c_in; e += kHeadThreads) s_in[(e % c_in) * 33 + e / c_in] = cur[(size_t)(r0 + e / c_in) * c_in + e % c_in];
                     }
                     __syncthreads();
+                    HEAD_TS(4 + l * 8 + 3);
                     const int ldr = min(lane, rn - 1);
                     const int cp = warp & 7, kq = warp >> 3;                   // channel pair, K quarter
                     const float *w0 = sw + (cp * 2) * ldw, *w1 = w0 + ldw;
@@ -253,7 +265,9 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                     }
                     s_part[(kq * 16 + cp * 2 + 0) * 33 + lane] = p0;
                     s_part[(kq * 16 + cp * 2 + 1) * 33 + lane] = p1;
+                    HEAD_TS(4 + l * 8 + 4);
                     __syncthreads();
+                    HEAD_TS(4 + l * 8 + 5);
                     if (warp < 8) {   // fixed-order combination of the K quarters
 #pragma unroll
                         for (int jj = 0; jj < 2; jj++) {
@@ -316,7 +330,9 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
             }
         }
         cur = dst;
+        HEAD_TS(4 + l * 8 + 6);
         cluster.sync();   // the next layer reads every CTA's slice
+        HEAD_TS(4 + l * 8 + 7);
     }
 }
 
@@ -367,6 +383,11 @@ static GenWorkspace carve_gen_ws(void *base, int b, int n, int nconv, const snb2
     W.head_act[1] = reinterpret_cast<float *>(p + off); off += hb;
     W.total = off;
     return W;
+}
+
+int debug_head_timestamps(long long *host_out64)
+{
+    return cudaMemcpyFromSymbol(host_out64, g_head_ts, sizeof(long long) * 64) == cudaSuccess ? SNB200_OK : SNB200_ECUDA;
 }
 
 size_t generator_workspace_bytes(int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc)
