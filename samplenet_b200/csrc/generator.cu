@@ -20,8 +20,7 @@ namespace cg = cooperative_groups;
 
 namespace snb {
 
-constexpr int kHeadThreads = 1024;     // 32 warps: 8 channel pairs x 4 K-quarters
-constexpr int kHeadKSplit = 4;
+constexpr int kHeadThreads = 256;      // 8 warps = 8 K slices; lanes = 8 row quads x 4 channel quads
 constexpr int kHeadChPerCta = 16;
 constexpr int kHeadMaxCluster = 16;
 
@@ -81,11 +80,15 @@ __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_t
 __device__ long long g_head_ts[64];
 #define HEAD_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_head_ts[(i)] = clock64(); } while (0)
 
-// RG = number of 32-row groups of the batch (b <= 32*RG).  8 warps x 2 output channels = 16 channels per CTA per pass.
-// Everything here is a latency chain (4 dependent layers on 32 rows), so the kernel is organised around taking loads off
-// that chain: the weight slices of ALL layers do not depend on activations and are fetched by TMA bulk copies
-// (cp.async.bulk -> one mbarrier per layer) the moment the kernel starts; the per-layer input tile (32 x c_in) is fetched with
-// all of a thread's 16-byte loads in flight at once.
+// RG = number of 32-row groups of the batch (b <= 32*RG).  256 threads = 8 warps.
+// Everything here is a latency chain (4 dependent layers on <= 256 rows), so the kernel is organised around keeping loads
+// off that chain and shared-memory wavefronts low:
+//   * the weight slices of ALL layers do not depend on activations: they are fetched by TMA bulk copies (one mbarrier per
+//     layer, one row per issuing thread) the moment the kernel starts;
+//   * per-channel parameters (bias, gamma, beta, running stats) are read into registers before the layer's math;
+//   * the per-CTA product [32 rows x c_in] x [c_in x 16 channels] is register-tiled 4 rows x 4 channels per thread with the
+//     K range split over the 8 warps (2 LDS.128 wavefronts per 16 FMAs), partial sums are combined through shared memory in a
+//     fixed order, and the combine leaves lane = batch row, warp = channel so BatchNorm over the batch is two warp shuffles.
 template <int RG>
 __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __grid_constant__ HeadParams P)
 {
@@ -94,41 +97,49 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t wbar[SNB200_MAX_FC_LAYERS];
-    // s_in: [c_in_max][33]            one row group of the input, transposed (lane = batch row reads conflict-free)
-    // s_w : per layer [16][c_in+4]    this CTA's first 16-channel weight slice, row-major like in HBM (warp-uniform reads broadcast)
+    __shared__ float *s_wptr[SNB200_MAX_FC_LAYERS];
+    // s_in  : [c_in_max][36]          one row group of the input, transposed (k-major), 4-row float4 reads
+    // s_w   : per layer [16][c_in+4]  this CTA's first 16-channel weight slice, row-major like in HBM
+    // s_part: [8 warps][32 rows][17]  partial dot products of the K slices
     int cmax = P.c_feat;
     for (int l = 0; l < P.num_fc; l++) cmax = max(cmax, P.fc[l].c_in);
     float *s_in = smem;
-    float *s_w[SNB200_MAX_FC_LAYERS];
     float *s_part;
-    {
-        float *p = smem + (size_t)cmax * 33;
-        for (int l = 0; l < P.num_fc; l++) { s_w[l] = p; p += (size_t)kHeadChPerCta * (P.fc[l].c_in + 4); }
-        s_part = p;   // [kHeadKSplit][16][33] partial dot products
-    }
     HEAD_TS(0);
-    // ---- weight prefetch for every layer (pass 0 of this CTA), TMA bulk, one mbarrier per layer
     if (tid == 0) {
+        float *p = smem + (size_t)cmax * 36;
+        for (int l = 0; l < P.num_fc; l++) { s_wptr[l] = p; p += (size_t)kHeadChPerCta * (P.fc[l].c_in + 4); }
         for (int l = 0; l < P.num_fc; l++) mbar_init(&wbar[l], 1);
         fence_mbar_init();
+        if (!(P.dbg & 2))
+            for (int l = 0; l < P.num_fc; l++) {   // arm every layer's barrier with the bytes its slice will deliver
+                const HeadLayer &L = P.fc[l];
+                const int per_cta = (L.c_out + csize - 1) / csize;
+                const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
+                const int nch = max(0, min(kHeadChPerCta, c_hi - c_lo));
+                const bool tma_ok = (L.c_in & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+                if (tma_ok && nch > 0) mbar_expect_tx(&wbar[l], (uint32_t)nch * L.c_in * 4u);
+            }
     }
     __syncthreads();
-    if (tid == 0 && !(P.dbg & 2)) {
-        for (int l = 0; l < P.num_fc; l++) {
-            const HeadLayer &L = P.fc[l];
-            const int per_cta = (L.c_out + csize - 1) / csize;
-            const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
-            const int nch = max(0, min(kHeadChPerCta, c_hi - c_lo));
-            const bool tma_ok = (L.c_in & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
-            if (tma_ok && nch > 0) {
-                mbar_expect_tx(&wbar[l], (uint32_t)nch * L.c_in * 4u);
-                for (int j = 0; j < nch; j++)
-                    tma_load_1d(s_w[l] + (size_t)j * (L.c_in + 4), L.weight + (size_t)(c_lo + j) * L.c_in, (uint32_t)L.c_in * 4u, &wbar[l]);
-            }
-        }
+    {
+        float *p = smem + (size_t)cmax * 36;
+        for (int l = 0; l < P.num_fc; l++) p += (size_t)kHeadChPerCta * (P.fc[l].c_in + 4);
+        s_part = p;
     }
-
+    // ---- weight prefetch: thread t issues row (t % 16) of layer (t / 16)
+    if (!(P.dbg & 2) && tid < P.num_fc * kHeadChPerCta) {
+        const int l = tid / kHeadChPerCta, jrow = tid % kHeadChPerCta;
+        const HeadLayer &L = P.fc[l];
+        const int per_cta = (L.c_out + csize - 1) / csize;
+        const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
+        const int nch = max(0, min(kHeadChPerCta, c_hi - c_lo));
+        const bool tma_ok = (L.c_in & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+        if (tma_ok && jrow < nch)
+            tma_load_1d(s_wptr[l] + (size_t)jrow * (L.c_in + 4), L.weight + (size_t)(c_lo + jrow) * L.c_in, (uint32_t)L.c_in * 4u, &wbar[l]);
+    }
     HEAD_TS(1);
+
     // ---- phase 0: pooled feature (this CTA's share) and the conv stack's running statistics (spread over the cluster)
     {
         const int total = P.b * P.c_feat;
@@ -195,10 +206,22 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
         const int c_lo = rank * per_cta, c_hi = min(L.c_out, c_lo + per_cta);
         const bool vec = (c_in & 3) == 0;
         const bool tma_ok = vec && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0 && !(P.dbg & 2);
-        float *sw = s_w[l];
+        float *sw = s_wptr[l];
         for (int cb = c_lo; cb < c_hi; cb += kHeadChPerCta) {      // passes of 16 channels (one pass unless c_out > 16*cluster)
             const int nch = min(kHeadChPerCta, c_hi - cb);
             HEAD_TS(4 + l * 8 + 0);
+            // per-channel parameters of the two channels this warp finishes (warp, warp+8): loads start now
+            float pb[2], pg[2], pbe[2], prm[2], prv[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int c = cb + warp + 8 * j;
+                const bool cv = (warp + 8 * j) < nch;
+                pb[j] = (cv && L.bias) ? __ldg(L.bias + c) : 0.f;
+                pg[j] = (cv && L.has_bn) ? __ldg(L.gamma + c) : 1.f;
+                pbe[j] = (cv && L.has_bn) ? __ldg(L.beta + c) : 0.f;
+                prm[j] = (cv && L.has_bn && L.run_mean) ? L.run_mean[c] : 0.f;
+                prv[j] = (cv && L.has_bn && L.run_var) ? L.run_var[c] : 1.f;
+            }
             if (cb == c_lo && tma_ok) {
                 mbar_wait(&wbar[l], 0);                           // prefetched slice has landed
             } else {
@@ -208,119 +231,133 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                     sw[jr * ldw + k] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
                 }
             }
-            float acc[RG][2];
-#pragma unroll
-            for (int g = 0; g < RG; g++) { acc[g][0] = 0.f; acc[g][1] = 0.f; }
+            float y[RG][2];   // finished pre-activation of (row = g*32 + lane, channel = warp + 8*j)
 #pragma unroll
             for (int g = 0; g < RG; g++) {
+                y[g][0] = 0.f; y[g][1] = 0.f;
                 const int r0 = g * 32;
                 if (r0 < P.b) {   // uniform
                     const int rn = min(32, P.b - r0);
                     HEAD_TS(4 + l * 8 + 1);
                     __syncthreads();
                     HEAD_TS(4 + l * 8 + 2);
-                    // input rows r0..r0+rn-1, transposed into s_in[k][r]; written by other CTAs of this kernel: plain loads.
+                    // input rows r0..r0+rn-1, transposed into s_in[k][r]; written by other CTAs of this kernel: plain loads,
+                    // all of a thread's loads in flight before the first store
                     if (vec) {
                         const int q = c_in >> 2, total = rn * q;
-                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 2) {
-                            float4 v[2];
+                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 8) {
+                            float4 v[8];
 #pragma unroll
-                            for (int u = 0; u < 2; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const int e = e0 + u * kHeadThreads;
                                 v[u] = (e < total) ? *(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + e / q) * c_in) + (e % q)) : make_float4(0, 0, 0, 0);
                             }
 #pragma unroll
-                            for (int u = 0; u < 2; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const int e = e0 + u * kHeadThreads;
                                 if (e < total) {
                                     const int r = e / q, k = (e % q) * 4;
-                                    s_in[(k + 0) * 33 + r] = v[u].x; s_in[(k + 1) * 33 + r] = v[u].y;
-                                    s_in[(k + 2) * 33 + r] = v[u].z; s_in[(k + 3) * 33 + r] = v[u].w;
+                                    s_in[(k + 0) * 36 + r] = v[u].x; s_in[(k + 1) * 36 + r] = v[u].y;
+                                    s_in[(k + 2) * 36 + r] = v[u].z; s_in[(k + 3) * 36 + r] = v[u].w;
                                 }
                             }
                         }
                     } else {
-                        for (int e = tid; e < rn * c_in; e += kHeadThreads) s_in[(e % c_in) * 33 + e / c_in] = cur[(size_t)(r0 + e / c_in) * c_in + e % c_in];
+                        for (int e = tid; e < rn * c_in; e += kHeadThreads) s_in[(e % c_in) * 36 + e / c_in] = cur[(size_t)(r0 + e / c_in) * c_in + e % c_in];
                     }
+                    if (rn < 32)   // rows beyond the batch: keep the tile defined
+                        for (int e = tid; e < (32 - rn) * c_in; e += kHeadThreads) s_in[(e % c_in) * 36 + rn + e / c_in] = 0.f;
                     __syncthreads();
                     HEAD_TS(4 + l * 8 + 3);
-                    const int ldr = min(lane, rn - 1);
-                    const int cp = warp & 7, kq = warp >> 3;                   // channel pair, K quarter
-                    const float *w0 = sw + (cp * 2) * ldw, *w1 = w0 + ldw;
-                    const int kr = ((c_in + 4 * kHeadKSplit - 1) / (4 * kHeadKSplit)) * 4;   // K range per quarter (multiple of 4)
-                    const int k_lo = kq * kr, k_hi = min(c_in, k_lo + kr);
-                    float p0 = 0.f, p1 = 0.f;
+                    // register-tiled partial product: lane -> rows 4*rg..+3, channels 4*cgp..+3; warp -> K slice
+                    const int rg = lane & 7, cgp = lane >> 3;
+                    const int kr = ((c_in + 31) / 32) * 4;                    // K per warp, multiple of 4
+                    const int k_lo = warp * kr, k_hi = min(c_in, k_lo + kr);
+                    float acc[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[r][j] = 0.f;
                     int k = k_lo;
-#pragma unroll 4
                     for (; k + 4 <= k_hi; k += 4) {
-                        const float a0 = s_in[(k + 0) * 33 + ldr], a1 = s_in[(k + 1) * 33 + ldr], a2 = s_in[(k + 2) * 33 + ldr], a3 = s_in[(k + 3) * 33 + ldr];
-                        const float4 u0 = *reinterpret_cast<const float4 *>(w0 + k), u1 = *reinterpret_cast<const float4 *>(w1 + k);
-                        p0 = fmaf(a3, u0.w, fmaf(a2, u0.z, fmaf(a1, u0.y, fmaf(a0, u0.x, p0))));
-                        p1 = fmaf(a3, u1.w, fmaf(a2, u1.z, fmaf(a1, u1.y, fmaf(a0, u1.x, p1))));
+                        float4 a[4], wv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(s_in + (k + i) * 36 + rg * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) wv[j] = *reinterpret_cast<const float4 *>(sw + (cgp * 4 + j) * ldw + k);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            acc[0][j] = fmaf(a[3].x, wv[j].w, fmaf(a[2].x, wv[j].z, fmaf(a[1].x, wv[j].y, fmaf(a[0].x, wv[j].x, acc[0][j]))));
+                            acc[1][j] = fmaf(a[3].y, wv[j].w, fmaf(a[2].y, wv[j].z, fmaf(a[1].y, wv[j].y, fmaf(a[0].y, wv[j].x, acc[1][j]))));
+                            acc[2][j] = fmaf(a[3].z, wv[j].w, fmaf(a[2].z, wv[j].z, fmaf(a[1].z, wv[j].y, fmaf(a[0].z, wv[j].x, acc[2][j]))));
+                            acc[3][j] = fmaf(a[3].w, wv[j].w, fmaf(a[2].w, wv[j].z, fmaf(a[1].w, wv[j].y, fmaf(a[0].w, wv[j].x, acc[3][j]))));
+                        }
                     }
                     for (; k < k_hi; k++) {
-                        const float a = s_in[k * 33 + ldr];
-                        p0 = fmaf(a, w0[k], p0);
-                        p1 = fmaf(a, w1[k], p1);
+                        const float4 a = *reinterpret_cast<const float4 *>(s_in + k * 36 + rg * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float wj = sw[(cgp * 4 + j) * ldw + k];
+                            acc[0][j] = fmaf(a.x, wj, acc[0][j]); acc[1][j] = fmaf(a.y, wj, acc[1][j]);
+                            acc[2][j] = fmaf(a.z, wj, acc[2][j]); acc[3][j] = fmaf(a.w, wj, acc[3][j]);
+                        }
                     }
-                    s_part[(kq * 16 + cp * 2 + 0) * 33 + lane] = p0;
-                    s_part[(kq * 16 + cp * 2 + 1) * 33 + lane] = p1;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) s_part[(warp * 32 + rg * 4 + r) * 17 + cgp * 4 + j] = acc[r][j];
                     HEAD_TS(4 + l * 8 + 4);
                     __syncthreads();
                     HEAD_TS(4 + l * 8 + 5);
-                    if (warp < 8) {   // fixed-order combination of the K quarters
 #pragma unroll
-                        for (int jj = 0; jj < 2; jj++) {
-                            float t = 0.f;
+                    for (int j = 0; j < 2; j++) {   // fixed-order combination of the 8 K slices: lane = row, warp (+8) = channel
+                        float t = 0.f;
 #pragma unroll
-                            for (int qd = 0; qd < kHeadKSplit; qd++) t += s_part[(qd * 16 + warp * 2 + jj) * 33 + lane];
-                            acc[g][jj] = t;
-                        }
+                        for (int w8 = 0; w8 < 8; w8++) t += s_part[(w8 * 32 + lane) * 17 + warp + 8 * j];
+                        y[g][j] = t;
                     }
                 }
             }
-            if (warp >= 8) continue;   // warps 8..31 only contribute partial sums (warp-uniform; no barrier below in this pass)
             // bias, BatchNorm over the batch (rows live in lanes x row groups), activation, store
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                const int c = cb + warp * 2 + j;
-                const bool cv = (warp * 2 + j) < nch;   // warp-uniform
-                const float bias = (cv && L.bias) ? L.bias[c] : 0.f;
+                const int c = cb + warp + 8 * j;
+                const bool cv = (warp + 8 * j) < nch;   // warp-uniform
                 float scale = 1.f, shift = 0.f;
 #pragma unroll
-                for (int g = 0; g < RG; g++) acc[g][j] += bias;
+                for (int g = 0; g < RG; g++) y[g][j] += pb[j];
                 if (L.has_bn && cv) {
                     float mean, var;
                     if (P.training) {
                         float sm = 0.f;
 #pragma unroll
                         for (int g = 0; g < RG; g++)
-                            if (g * 32 + lane < P.b) sm += acc[g][j];
+                            if (g * 32 + lane < P.b) sm += y[g][j];
                         mean = warp_sum(sm) / (float)P.b;
                         float q = 0.f;
 #pragma unroll
                         for (int g = 0; g < RG; g++)
-                            if (g * 32 + lane < P.b) { const float d = acc[g][j] - mean; q = fmaf(d, d, q); }
+                            if (g * 32 + lane < P.b) { const float d = y[g][j] - mean; q = fmaf(d, d, q); }
                         q = warp_sum(q);
                         var = q / (float)P.b;
                         if (lane == 0) {
                             const float unb = P.b > 1 ? q / (float)(P.b - 1) : var;
-                            if (L.run_mean) L.run_mean[c] = (1.f - L.momentum) * L.run_mean[c] + L.momentum * mean;
-                            if (L.run_var) L.run_var[c] = (1.f - L.momentum) * L.run_var[c] + L.momentum * unb;
+                            if (L.run_mean) L.run_mean[c] = (1.f - L.momentum) * prm[j] + L.momentum * mean;
+                            if (L.run_var) L.run_var[c] = (1.f - L.momentum) * prv[j] + L.momentum * unb;
                         }
                     } else {
-                        mean = L.run_mean[c]; var = L.run_var[c];
+                        mean = prm[j]; var = prv[j];
                     }
                     const float invstd = 1.0f / sqrtf(var + L.eps);
-                    scale = L.gamma[c] * invstd;
-                    shift = L.beta[c] - mean * scale;
+                    scale = pg[j] * invstd;
+                    shift = pbe[j] - mean * scale;
                 }
                 if (cv) {
 #pragma unroll
                     for (int g = 0; g < RG; g++) {
                         const int row = g * 32 + lane;
                         if (row < P.b) {
-                            float v = L.has_bn ? fmaf(acc[g][j], scale, shift) : acc[g][j];
+                            float v = L.has_bn ? fmaf(y[g][j], scale, shift) : y[g][j];
                             if (L.relu) v = fmaxf(v, 0.f);
                             const int oc = (last && P.out_inner > 0) ? (c % P.out_inner) * (L.c_out / P.out_inner) + c / P.out_inner : c;
                             dst[(size_t)row * L.c_out + oc] = v;
@@ -485,7 +522,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     }
     size_t wfloats = 0;
     for (int l = 0; l < nfc; l++) wfloats += (size_t)kHeadChPerCta * (fc[l].c_in + 4);
-    const size_t smem = ((size_t)cmax * 33 + wfloats + (size_t)kHeadKSplit * 16 * 33) * sizeof(float);
+    const size_t smem = ((size_t)cmax * 36 + wfloats + (size_t)8 * 32 * 17) * sizeof(float);
     const int rg = (b + 31) / 32;
     if (rg > 8) { set_error("generator: batch %d exceeds the FC head limit of 256 rows", b); return SNB200_EUNSUPPORTED; }
     if (smem > 200 * 1024) { set_error("generator: FC width %d too large for the shared-memory tile", cmax); return SNB200_EUNSUPPORTED; }
