@@ -244,32 +244,37 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                     // input rows r0..r0+rn-1, transposed into s_in[k][r]; written by other CTAs of this kernel: plain loads,
                     // all of a thread's loads in flight before the first store
                     if (vec) {
-                        const int q = c_in >> 2, total = rn * q;
-                        for (int e0 = tid; e0 < total; e0 += kHeadThreads * 8) {
+                        // lane = batch row (conflict-free transposed stores), warps stride over the 16-byte k groups;
+                        // up to 8 loads per thread in flight before the first store
+                        const int q = c_in >> 2;
+                        const float *src = cur + (size_t)(r0 + min(lane, rn - 1)) * c_in;
+                        for (int q0 = warp; q0 < q; q0 += 8 * 8) {
                             float4 v[8];
 #pragma unroll
                             for (int u = 0; u < 8; u++) {
-                                const int e = e0 + u * kHeadThreads;
-                                v[u] = (e < total) ? *(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + e / q) * c_in) + (e % q)) : make_float4(0, 0, 0, 0);
+                                const int kq = q0 + 8 * u;
+                                v[u] = (kq < q) ? *(reinterpret_cast<const float4 *>(src) + kq) : make_float4(0, 0, 0, 0);
                             }
 #pragma unroll
                             for (int u = 0; u < 8; u++) {
-                                const int e = e0 + u * kHeadThreads;
-                                if (e < total) {
-                                    const int r = e / q, k = (e % q) * 4;
-                                    s_in[(k + 0) * 36 + r] = v[u].x; s_in[(k + 1) * 36 + r] = v[u].y;
-                                    s_in[(k + 2) * 36 + r] = v[u].z; s_in[(k + 3) * 36 + r] = v[u].w;
+                                const int kq = q0 + 8 * u;
+                                if (kq < q) {
+                                    const float4 t = (lane < rn) ? v[u] : make_float4(0, 0, 0, 0);
+                                    s_in[(kq * 4 + 0) * 36 + lane] = t.x; s_in[(kq * 4 + 1) * 36 + lane] = t.y;
+                                    s_in[(kq * 4 + 2) * 36 + lane] = t.z; s_in[(kq * 4 + 3) * 36 + lane] = t.w;
                                 }
                             }
                         }
                     } else {
-                        for (int e = tid; e < rn * c_in; e += kHeadThreads) s_in[(e % c_in) * 36 + e / c_in] = cur[(size_t)(r0 + e / c_in) * c_in + e % c_in];
+                        for (int e = tid; e < 32 * c_in; e += kHeadThreads) {
+                            const int r = e & 31, k = e >> 5;
+                            s_in[k * 36 + r] = (r < rn) ? cur[(size_t)(r0 + r) * c_in + k] : 0.f;
+                        }
                     }
-                    if (rn < 32)   // rows beyond the batch: keep the tile defined
-                        for (int e = tid; e < (32 - rn) * c_in; e += kHeadThreads) s_in[(e % c_in) * 36 + rn + e / c_in] = 0.f;
                     __syncthreads();
                     HEAD_TS(4 + l * 8 + 3);
-                    // register-tiled partial product: lane -> rows 4*rg..+3, channels 4*cgp..+3; warp -> K slice
+                    // register-tiled partial product: lane -> rows 4*rg..+3, channels cgp, cgp+4, cgp+8, cgp+12 (bank-conflict-free weight reads);
+                    // warp -> K slice
                     const int rg = lane & 7, cgp = lane >> 3;
                     const int kr = ((c_in + 31) / 32) * 4;                    // K per warp, multiple of 4
                     const int k_lo = warp * kr, k_hi = min(c_in, k_lo + kr);
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
 #pragma unroll
                         for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(s_in + (k + i) * 36 + rg * 4);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) wv[j] = *reinterpret_cast<const float4 *>(sw + (cgp * 4 + j) * ldw + k);
+                        for (int j = 0; j < 4; j++) wv[j] = *reinterpret_cast<const float4 *>(sw + (cgp + 4 * j) * ldw + k);
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             acc[0][j] = fmaf(a[3].x, wv[j].w, fmaf(a[2].x, wv[j].z, fmaf(a[1].x, wv[j].y, fmaf(a[0].x, wv[j].x, acc[0][j]))));
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
                         const float4 a = *reinterpret_cast<const float4 *>(s_in + k * 36 + rg * 4);
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const float wj = sw[(cgp * 4 + j) * ldw + k];
+                            const float wj = sw[(cgp + 4 * j) * ldw + k];
                             acc[0][j] = fmaf(a.x, wj, acc[0][j]); acc[1][j] = fmaf(a.y, wj, acc[1][j]);
                             acc[2][j] = fmaf(a.z, wj, acc[2][j]); acc[3][j] = fmaf(a.w, wj, acc[3][j]);
                         }
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
 #pragma unroll
                     for (int r = 0; r < 4; r++)
 #pragma unroll
-                        for (int j = 0; j < 4; j++) s_part[(warp * 32 + rg * 4 + r) * 17 + cgp * 4 + j] = acc[r][j];
+                        for (int j = 0; j < 4; j++) s_part[(warp * 32 + rg * 4 + r) * 17 + cgp + 4 * j] = acc[r][j];
                     HEAD_TS(4 + l * 8 + 4);
                     __syncthreads();
                     HEAD_TS(4 + l * 8 + 5);
