@@ -1,0 +1,527 @@
+// conv_stack.cu -- the whole per-point MLP (conv layers 1..L, samplenet.py:90-94) as ONE persistent cooperative kernel whose
+// activations never leave the SM.
+//
+// Per-layer kernels (encoder_tc.cu) pay, per layer, a launch, a 8-17 MB activation write + read through L2 and a cold
+// prologue/epilogue; at B=32 that is 65 us for 2.1 GFLOP.  Here every CTA (one per SM) owns up to TWO 128-point tiles for the
+// whole stack:
+//   * the raw (pre-BatchNorm) output of layer l stays in TENSOR MEMORY (128 lanes x c_out columns per tile; two ping-pong
+//     regions per tile slot = 4 x 128 columns = the SM's 512 TMEM columns);
+//   * layer l+1's A operand is produced straight from TMEM: tcgen05.ld (thread = point row) -> BatchNorm + ReLU of layer l ->
+//     exact hi/lo TF32 split -> canonical K-major SWIZZLE_128B shared-memory tile (ring of two 32-wide K chunks), so operand
+//     preparation of chunk k+1 overlaps the tcgen05.mma of chunk k (3 MMAs per K-step: lo*hi, hi*lo, hi*hi);
+//   * the layer's weights are split and staged once per CTA per layer (while the previous layer's MMAs and the grid barrier
+//     are in flight);
+//   * training-mode BatchNorm needs batch statistics of layer l before layer l+1 can start: per-tile column sums are reduced
+//     with a halving shuffle network (31 shuffles per 32x32 block), combined per CTA and added to fp64 global accumulators,
+//     and a grid-wide barrier (cooperative launch, one atomic counter) separates the layers.  Layer 1 (3 -> 64) is evaluated
+//     on the fly from the cloud and its statistics follow analytically from the batch's 9 input moments (phase 0);
+//   * the last layer never materialises: only per-tile column max / min leave the SM (the max-pool commutes with the monotone
+//     BN+ReLU map).
+// Applicable when every CTA's tiles fit its TMEM (tiles <= 2 x CTAs, widths <= 128, K multiples of 32); otherwise the
+// per-layer kernels are used.
+#include "encoder_internal.cuh"
+#include <cooperative_groups.h>
+#include <string.h>
+
+namespace snb {
+
+constexpr int kCsThreads = 256;
+constexpr int kCsM = 128;
+constexpr int kCsMaxLayers = SNB200_MAX_CONV_LAYERS;
+constexpr int kCsSlots = 2;           // tiles per CTA
+constexpr int kCsRegion = 128;        // TMEM columns per (slot, parity) region
+
+struct CsLayer {
+    int c_in, c_out;
+    const float *weight, *bias;
+    // BatchNorm (+ReLU) applied to THIS layer's output when it is consumed by the next layer / the pool
+    const float *gamma, *beta, *run_mean, *run_var;
+    float eps;
+    int has_bn, relu;
+    double *stats;                      // [2][c_out] sum, sumsq (training) -- written here, read by the next layer and the head
+};
+
+struct CsParams {
+    const float *x; int layout;
+    int b, n, tiles, tiles_per_cloud;
+    int num_layers;                     // including layer 1
+    CsLayer L[kCsMaxLayers];
+    int training;
+    double *mom;                        // [9] input moments (zeroed by the caller)
+    unsigned *barrier;                  // grid barrier counter (zeroed by the caller)
+    float *tile_max, *tile_min;         // (tiles, c_last)
+};
+
+// ---- tcgen05 helpers (same encodings as encoder_tc.cu, validated against fp64 in tests/test_gpu_parity.py::test_tc_gemm_3xtf32)
+__device__ __forceinline__ void cs_tmem_alloc(uint32_t *smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cs_tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void cs_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cs_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cs_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void cs_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cs_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void cs_ld32(uint32_t taddr, float *v)
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__host__ __device__ constexpr uint32_t cs_idesc(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr unsigned kCsDescHi = (64u) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t cs_sdesc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)kCsDescHi << 32);
+}
+__device__ __forceinline__ uint32_t cs_sw128(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
+__device__ __forceinline__ void cs_split_store(unsigned char *hi_base, unsigned char *lo_base, uint32_t off, float4 v)
+{
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4 *>(hi_base + off) = h;
+    *reinterpret_cast<float4 *>(lo_base + off) = l;
+}
+
+// bounded waits: a protocol bug must not hang the GPU box -- trap instead (surfaces as a launch failure in the next API call)
+__device__ __forceinline__ void cs_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void cs_grid_barrier(unsigned *counter, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v, spin = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v < target) __nanosleep(32);
+            if (++spin > (1u << 22)) __trap();
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+// Column reduction of a 32x32 block held one row per lane: after the 5 halving steps lane i holds the combined value of
+// column i (31 shuffles instead of 160).  OP: 0 = sum, 1 = max, 2 = min.
+template <int OP>
+__device__ __forceinline__ float cs_colreduce(float *s, int lane)
+{
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+            const float send = up ? s[j] : s[j + half];
+            const float keep = up ? s[j + half] : s[j];
+            const float recv = __shfl_xor_sync(kFullMask, send, half);
+            s[j] = OP == 0 ? keep + recv : (OP == 1 ? fmaxf(keep, recv) : fminf(keep, recv));
+        }
+    }
+    return s[0];
+}
+
+__global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // shared-memory map (dynamic): [A ring: 2 x (hi 16 KB + lo 16 KB)] [W hi | W lo : 2 x c_in x c_out x 4 B]
+    unsigned char *sA[2][2];  // [ring][hi/lo]
+    sA[0][0] = smem_raw;             sA[0][1] = smem_raw + 16384;
+    sA[1][0] = smem_raw + 32768;     sA[1][1] = smem_raw + 49152;
+    unsigned char *sWhi = smem_raw + 65536;
+    __shared__ float sScale[128], sShift[128], sBias[128];
+    __shared__ float sX[kCsSlots][kCsM * 3];
+    __shared__ float sW1[128 * 3], sB1[128];
+    __shared__ float sRedA[4][128], sRedB[4][128];
+    __shared__ uint64_t bar_ring[2], bar_acc[kCsSlots];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ double sMom[9];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hsel = warp >> 2;           // TMEM lane quarter, column half
+    const int row = q * 32 + lane;                      // the point row this thread owns in every tile
+    const int G = gridDim.x;
+    int tile_of[kCsSlots], np_of[kCsSlots];
+    int nslots = 0;
+#pragma unroll
+    for (int s = 0; s < kCsSlots; s++) {
+        const int t = blockIdx.x + s * G;
+        tile_of[s] = t;
+        np_of[s] = 0;
+        if (t < P.tiles) {
+            nslots = s + 1;
+            const int p0 = (t % P.tiles_per_cloud) * kCsM;
+            np_of[s] = min(kCsM, P.n - p0);
+        }
+    }
+
+    if (warp == 0) cs_tmem_alloc(&tmem_base_smem, 512);
+    if (tid == 32) {
+        mbar_init(&bar_ring[0], 1); mbar_init(&bar_ring[1], 1);
+        mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
+        fence_mbar_init();
+    }
+    if (tid < 9) sMom[tid] = 0.0;
+    // the cloud tiles of this CTA and layer 1's weights
+    const CsLayer &L1 = P.L[0];
+    for (int s = 0; s < nslots; s++) {
+        const int t = tile_of[s], cloud = t / P.tiles_per_cloud, p0 = (t % P.tiles_per_cloud) * kCsM;
+        const float *xc = P.x + (size_t)cloud * P.n * 3;
+        for (int e = tid; e < kCsM * 3; e += kCsThreads) {
+            const int r = e / 3, c = e % 3;
+            sX[s][e] = (r < np_of[s]) ? (P.layout == SNB200_BNC ? xc[(size_t)(p0 + r) * 3 + c] : xc[(size_t)c * P.n + p0 + r]) : 0.f;
+        }
+    }
+    for (int e = tid; e < L1.c_out * 3; e += kCsThreads) sW1[e] = L1.weight[e];
+    for (int e = tid; e < L1.c_out; e += kCsThreads) sB1[e] = L1.bias ? L1.bias[e] : 0.f;
+    cs_fence_before();
+    __syncthreads();
+    cs_fence_after();
+    const uint32_t tmem0 = tmem_base_smem;
+    unsigned barrier_epoch = 0;
+    const double cnt = (double)P.b * (double)P.n;
+
+    // ---- phase 0: input moments (training + BN after layer 1): 9 sums over this CTA's points, fp64 atomics, grid barrier
+    const bool need_stats = P.training != 0;
+    if (need_stats && L1.has_bn) {
+        float a9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (tid < kCsM * nslots) {
+            const int s = tid / kCsM, r = tid % kCsM;
+            if (r < np_of[s]) {
+                const float px = sX[s][r * 3 + 0], py = sX[s][r * 3 + 1], pz = sX[s][r * 3 + 2];
+                a9[0] = px; a9[1] = py; a9[2] = pz;
+                a9[3] = px * px; a9[4] = px * py; a9[5] = px * pz; a9[6] = py * py; a9[7] = py * pz; a9[8] = pz * pz;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            float v = a9[j];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+            if (lane == 0) atomicAdd(&sMom[j], (double)v);
+        }
+        __syncthreads();
+        if (tid < 9) atomicAdd(P.mom + tid, sMom[tid]);
+        cs_grid_barrier(P.barrier, ++barrier_epoch * G);
+        if (tid < 9) sMom[tid] = __ldcg(P.mom + tid);
+        __syncthreads();
+    }
+
+    uint32_t ring_phase[2] = {0, 0};
+    uint32_t ring_used[2] = {0, 0};     // has the buffer been handed to the tensor core since its last wait?
+    uint32_t acc_phase[kCsSlots] = {0, 0};
+    int parity = 0;                     // TMEM region parity holding the CURRENT layer's input (previous layer's raw output)
+
+    for (int l = 1; l < P.num_layers; l++) {
+        const CsLayer &Lp = P.L[l - 1];   // producer of this layer's input (its BN+ReLU is applied on load)
+        const CsLayer &Lc = P.L[l];
+        const int K = Lc.c_in, N = Lc.c_out;
+        const int npad = N <= 64 ? 64 : 128;
+        const uint32_t idesc = cs_idesc(kCsM, npad);
+        const uint32_t atomB = (uint32_t)npad * 128u;
+        const int nchunks = K / 32;
+        unsigned char *sWlo = sWhi + (size_t)nchunks * atomB;
+        const bool last = (l == P.num_layers - 1);
+
+        // ---- weights of this layer: split + swizzled store, all K (independent of the barrier: overlaps its latency)
+        {
+            const int q4 = K >> 2, total = npad * q4;   // float4 units
+            for (int e0 = tid; e0 < total; e0 += kCsThreads * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int e = e0 + u * kCsThreads;
+                    const int nrow = e / q4, kq = e % q4;
+                    v[u] = (e < total && nrow < N) ? __ldg(reinterpret_cast<const float4 *>(Lc.weight + (size_t)nrow * K) + kq) : make_float4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int e = e0 + u * kCsThreads;
+                    if (e < total) {
+                        const int nrow = e / q4, kq = e % q4;
+                        cs_split_store(sWhi, sWlo, (uint32_t)(kq >> 3) * atomB + cs_sw128(nrow, kq & 7), v[u]);
+                    }
+                }
+            }
+            for (int c = tid; c < npad; c += kCsThreads) sBias[c] = (c < N && Lc.bias) ? Lc.bias[c] : 0.f;
+        }
+        // ---- BatchNorm (+ReLU) of the producer layer as a per-channel affine map
+        for (int c = tid; c < K; c += kCsThreads) {
+            float sc = 1.f, sh = 0.f;
+            if (Lp.has_bn) {
+                float mean, var;
+                if (P.training) {
+                    double m, v;
+                    if (l == 1) {   // analytic statistics of layer 1 from the input moments
+                        const double mx = sMom[0] / cnt, my = sMom[1] / cnt, mz = sMom[2] / cnt;
+                        const double cxx = sMom[3] / cnt - mx * mx, cxy = sMom[4] / cnt - mx * my, cxz = sMom[5] / cnt - mx * mz;
+                        const double cyy = sMom[6] / cnt - my * my, cyz = sMom[7] / cnt - my * mz, czz = sMom[8] / cnt - mz * mz;
+                        const double a0 = sW1[c * 3 + 0], a1 = sW1[c * 3 + 1], a2 = sW1[c * 3 + 2];
+                        m = a0 * mx + a1 * my + a2 * mz + (double)sB1[c];
+                        v = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
+                        if (v < 0) v = 0;
+                        if (blockIdx.x == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
+                            Lp.stats[c] = cnt * m;
+                            Lp.stats[K + c] = cnt * (v + m * m);
+                        }
+                    } else {
+                        m = __ldcg(Lp.stats + c) / cnt;
+                        v = __ldcg(Lp.stats + K + c) / cnt - m * m;
+                        if (v < 0) v = 0;
+                    }
+                    mean = (float)m; var = (float)v;
+                } else {
+                    mean = Lp.run_mean[c]; var = Lp.run_var[c];
+                }
+                const float invstd = 1.0f / sqrtf(var + Lp.eps);
+                sc = Lp.gamma[c] * invstd;
+                sh = Lp.beta[c] - mean * sc;
+            }
+            sScale[c] = sc;
+            sShift[c] = sh;
+        }
+        __syncthreads();
+
+        // ---- main loop: for each tile slot, K chunks of 32: operand prep (all warps) overlapped with the MMAs of the previous chunk
+        const uint32_t in_region = (uint32_t)(parity * kCsRegion), out_region = (uint32_t)((parity ^ 1) * kCsRegion);
+        int chunk_counter = 0;
+        for (int s = 0; s < nslots; s++) {
+            const int np = np_of[s];
+            const uint32_t t_in = tmem0 + (uint32_t)(s * 2 * kCsRegion) + in_region;
+            const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
+            for (int kc = 0; kc < nchunks; kc++, chunk_counter++) {
+                const int rb = chunk_counter & 1;
+                if (ring_used[rb]) {   // the tensor core must be done reading this ring buffer
+                    cs_mbar_wait(&bar_ring[rb], ring_phase[rb]);
+                    ring_phase[rb] ^= 1;
+                    ring_used[rb] = 0;
+                    cs_fence_after();
+                }
+                // this thread prepares row `row`, k = kc*32 + hsel*16 .. +15 (4 chunks of 16 bytes)
+                float v[16];
+                const int kb = kc * 32 + hsel * 16;
+                if (l == 1) {
+                    const float px = sX[s][row * 3 + 0], py = sX[s][row * 3 + 1], pz = sX[s][row * 3 + 2];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int c = kb + j;
+                        v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
+                    }
+                } else {
+                    cs_ld16(t_in + ((uint32_t)(q * 32) << 16) + (uint32_t)kb, v);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    float t = fmaf(v[j], sScale[kb + j], sShift[kb + j]);
+                    if (Lp.relu) t = fmaxf(t, 0.f);
+                    v[j] = (row < np) ? t : 0.f;
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++)
+                    cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 4 + c4), make_float4(v[c4 * 4 + 0], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]));
+                cs_fence_before();
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    cs_fence_after();
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint32_t kin = (uint32_t)ks * 32u;
+                        const uint64_t a_hi = cs_sdesc(smem_u32(sA[rb][0]) + kin), a_lo = cs_sdesc(smem_u32(sA[rb][1]) + kin);
+                        const uint64_t b_hi = cs_sdesc(smem_u32(sWhi) + (uint32_t)kc * atomB + kin), b_lo = cs_sdesc(smem_u32(sWlo) + (uint32_t)kc * atomB + kin);
+                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                        cs_umma(t_out, a_lo, b_hi, idesc, acc);
+                        cs_umma(t_out, a_hi, b_lo, idesc, 1u);
+                        cs_umma(t_out, a_hi, b_hi, idesc, 1u);
+                    }
+                    cs_commit(&bar_ring[rb]);
+                    if (kc == nchunks - 1) cs_commit(&bar_acc[s]);
+                }
+                ring_used[rb] = 1;
+            }
+        }
+
+        // ---- epilogue per slot: batch statistics (sum, sumsq) or, for the last layer, max / min over the tile's valid rows
+        const bool want_stats = need_stats && Lc.has_bn;
+        for (int s = 0; s < nslots; s++) {   // every MMA of this layer has landed in tensor memory
+            cs_mbar_wait(&bar_acc[s], acc_phase[s]);
+            acc_phase[s] ^= 1;
+        }
+        cs_fence_after();
+        for (int s = 0; s < nslots; s++) {
+            if (!want_stats && !last) break;
+            const int np = np_of[s];
+            const bool pv = row < np;
+            const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
+            // pass A: sums / sums of squares
+            if (want_stats) {
+                for (int cb = hsel * 32; cb < npad; cb += 64) {
+                    float v[32], w[32];
+                    cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float t = pv ? v[j] + sBias[cb + j] : 0.f;
+                        v[j] = t;
+                        w[j] = t * t;
+                    }
+                    sRedA[q][cb + lane] = cs_colreduce<0>(v, lane);
+                    sRedB[q][cb + lane] = cs_colreduce<0>(w, lane);
+                }
+                __syncthreads();
+                if (tid < N) {
+                    const float sm = (sRedA[0][tid] + sRedA[1][tid]) + (sRedA[2][tid] + sRedA[3][tid]);
+                    const float sq = (sRedB[0][tid] + sRedB[1][tid]) + (sRedB[2][tid] + sRedB[3][tid]);
+                    atomicAdd(Lc.stats + tid, (double)sm);
+                    atomicAdd(Lc.stats + N + tid, (double)sq);
+                }
+                __syncthreads();
+            }
+            // pass B: extrema for the max-pool (last layer only)
+            if (last) {
+                for (int cb = hsel * 32; cb < npad; cb += 64) {
+                    float v[32], w[32];
+                    cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float t = v[j] + sBias[cb + j];
+                        v[j] = pv ? t : -INFINITY;
+                        w[j] = pv ? t : INFINITY;
+                    }
+                    sRedA[q][cb + lane] = cs_colreduce<1>(v, lane);
+                    sRedB[q][cb + lane] = cs_colreduce<2>(w, lane);
+                }
+                __syncthreads();
+                if (tid < N) {
+                    P.tile_max[(size_t)tile_of[s] * N + tid] = fmaxf(fmaxf(sRedA[0][tid], sRedA[1][tid]), fmaxf(sRedA[2][tid], sRedA[3][tid]));
+                    P.tile_min[(size_t)tile_of[s] * N + tid] = fminf(fminf(sRedB[0][tid], sRedB[1][tid]), fminf(sRedB[2][tid], sRedB[3][tid]));
+                }
+                __syncthreads();
+            }
+        }
+        parity ^= 1;
+        cs_fence_before();
+        if (want_stats) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // every tile's statistics are in before anyone normalises
+        else __syncthreads();
+        cs_fence_after();
+    }
+
+    // drain the ring barriers so no arrival is pending at exit, then release tensor memory
+    for (int rb = 0; rb < 2; rb++)
+        if (ring_used[rb]) cs_mbar_wait(&bar_ring[rb], ring_phase[rb]);
+    cs_fence_before();
+    __syncthreads();
+    if (warp == 0) cs_tmem_dealloc(tmem0, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
+{
+    if (nconv < 2 || nconv > kCsMaxLayers || conv[0].c_in != 3) return false;
+    if (conv[0].c_out % 32 != 0 || conv[0].c_out > 128) return false;
+    size_t wmax = 0;
+    for (int l = 1; l < nconv; l++) {
+        if (conv[l].c_in % 32 != 0 || conv[l].c_in > 128 || conv[l].c_out > 128 || conv[l].c_out < 8) return false;
+        const size_t npad = conv[l].c_out <= 64 ? 64 : 128;
+        wmax = max(wmax, 2 * (size_t)conv[l].c_in * npad * 4);
+    }
+    if (65536 + wmax > 200 * 1024) return false;
+    const long long tiles = (long long)b * ((n + kCsM - 1) / kCsM);
+    return tiles <= (long long)kCsSlots * kNumSMs;
+}
+
+int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
+                      double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream)
+{
+    CsParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = x; P.layout = layout; P.b = b; P.n = n;
+    P.tiles_per_cloud = (n + kCsM - 1) / kCsM;
+    P.tiles = b * P.tiles_per_cloud;
+    P.num_layers = nconv; P.training = training;
+    P.mom = mom; P.barrier = barrier; P.tile_max = tile_max; P.tile_min = tile_min;
+    size_t wmax = 0;
+    for (int l = 0; l < nconv; l++) {
+        CsLayer &D = P.L[l];
+        D.c_in = conv[l].c_in; D.c_out = conv[l].c_out; D.weight = conv[l].weight; D.bias = conv[l].bias;
+        D.gamma = conv[l].bn_weight; D.beta = conv[l].bn_bias; D.run_mean = conv[l].bn_running_mean; D.run_var = conv[l].bn_running_var;
+        D.eps = conv[l].bn_eps; D.has_bn = conv[l].bn_weight != nullptr; D.relu = conv[l].relu; D.stats = stats[l];
+        if (l >= 1) wmax = max(wmax, 2 * (size_t)conv[l].c_in * (conv[l].c_out <= 64 ? 64 : 128) * 4);
+    }
+    if (tiles_per_cloud_out) *tiles_per_cloud_out = P.tiles_per_cloud;
+    const size_t smem = 65536 + wmax + 1024;
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    int grid = min(P.tiles, kNumSMs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kCsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_stack_kernel, P);
+    if (e != cudaSuccess) { set_error("conv stack: cooperative launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SNB200_ECUDA; }
+    return check_launch("conv stack");
+}
+
+}  // namespace snb

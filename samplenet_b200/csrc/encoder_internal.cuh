@@ -36,4 +36,9 @@ int launch_x_moments(int b, int n, int layout, const float *x, double *mom, unsi
 int launch_simt_conv_stack(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *act0,
                            float *act1, double *const *stats, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream);
 
+// persistent cooperative conv-stack kernel (conv_stack.cu)
+bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv);
+int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
+                      double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream);
+
 }  // namespace snb

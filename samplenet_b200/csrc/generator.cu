@@ -455,6 +455,9 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     int tpc = 0;
     if (flags & SNB200_GEN_PROFILE_SKIP_CONV) {
         tpc = use_tc ? tc_tiles_per_cloud(n) : (n + (conv[nconv - 1].c_out > 64 ? 128 : 256) - 1) / (conv[nconv - 1].c_out > 64 ? 128 : 256);
+    } else if (use_tc && !(flags & SNB200_GEN_PER_LAYER_KERNELS) && conv_stack_supported(b, n, nconv, conv)) {
+        int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc, stream);
+        if (rc) return rc;
     } else if (use_tc) {
         tpc = tc_tiles_per_cloud(n);
         const snb200_layer &L0 = conv[0];

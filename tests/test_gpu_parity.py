@@ -351,6 +351,32 @@ def test_generator_backward_matches_torch_autograd(sb):
     np.testing.assert_allclose(_n(simp), _n(y), rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("b,n", [(32, 1024), (2, 1024), (7, 1000), (37, 1024), (3, 77)])
+def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
+    """The persistent cooperative conv-stack kernel (activations resident in TMEM) == the per-layer tensor-core kernels ==
+    the exact-fp32 CUDA-core path, training and eval mode, full and ragged tiles, one and two tiles per CTA."""
+    torch.manual_seed(b * 1000 + n)
+    net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda()
+    with torch.no_grad():
+        for bn in [net.bn1, net.bn2, net.bn3, net.bn4, net.bn5]:
+            bn.weight.copy_(1 + 0.3 * torch.randn_like(bn.weight)); bn.bias.copy_(0.2 * torch.randn_like(bn.bias))
+            bn.running_mean.copy_(0.1 * torch.randn_like(bn.running_mean)); bn.running_var.copy_(0.5 + torch.rand_like(bn.running_var))
+    x = torch.rand(b, n, 3, device="cuda") - 0.5
+    conv, fc = net._layer_specs()
+    for training in (True, False):
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        outs = []
+        for kw in (dict(), dict(per_layer_kernels=True), dict(exact_fp32=True)):
+            net.load_state_dict(sd)
+            out, feat = sb.ops.generator_forward(x, "bnc", conv, fc, training, 64, **kw)
+            outs.append((out.clone(), feat.clone(), {k: v.clone() for k, v in net.state_dict().items() if "running" in k}))
+        for o, f, st in outs[1:]:
+            np.testing.assert_allclose(_n(outs[0][1]), _n(f), rtol=3e-4, atol=3e-5)
+            np.testing.assert_allclose(_n(outs[0][0]), _n(o), rtol=2e-3, atol=2e-4)
+            for k in st:
+                np.testing.assert_allclose(_n(outs[0][2][k]), _n(st[k]), rtol=1e-4, atol=1e-6, err_msg=k)
+
+
 def test_generator_rec_widths_and_ragged_sizes(sb):
     torch.manual_seed(1)
     import torch.nn.functional as F
