@@ -153,6 +153,7 @@ int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const fl
 
 /* Bring-up instrumentation: 64 SM-clock timestamps written by CTA 0 of the last FC-head launch (synchronous copy). */
 int snb200_debug_head_timestamps(long long *host_out64);
+int snb200_debug_conv_stack_timestamps(long long *host_out64);
 
 /* Fully connected head on the pooled feature: in (b, c_in0) -> out (b, c_out_last).  BatchNorm over the batch.
  * out_transpose_inner = M > 0: each output row, logically (c_out_last/M, M) -- the reference's y.view(-1, 3, M),

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "snb200_generator_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer)]),
     "snb200_generator_forward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _int, _vp, _size, _vp]),
     "snb200_debug_head_timestamps": (_int, [_vp]),
+    "snb200_debug_conv_stack_timestamps": (_int, [_vp]),
     "snb200_debug_tc_gemm": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, ctypes.c_uint, _int, _int, _vp]),
     "snb200_fc_head_workspace_bytes": (_size, [_int, _int, ctypes.POINTER(Layer)]),
     "snb200_fc_head_forward": (_int, [_int, _vp, _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _size, _vp]),

@@ -56,6 +56,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
                              int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream);
 
 int debug_head_timestamps(long long *host_out64);
+int debug_conv_stack_timestamps(long long *host_out64);
 
 static int check_layers(const char *who, int num_layers, const snb200_layer *layers, int max_layers)
 {
@@ -228,6 +229,7 @@ SNB_API int snb200_generator_forward(int b, int n, int layout, const float *x, i
 }
 
 SNB_API int snb200_debug_head_timestamps(long long *host_out64) { return debug_head_timestamps(host_out64); }
+SNB_API int snb200_debug_conv_stack_timestamps(long long *host_out64) { return debug_conv_stack_timestamps(host_out64); }
 
 SNB_API int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D, unsigned desc_hi,
                                  int k_adv16, int swizzle, snb200_stream_t stream)

@@ -182,6 +182,9 @@ __device__ __forceinline__ float cs_colreduce(float *s, int lane)
     return s[0];
 }
 
+__device__ long long g_cs_ts[64];
+#define CS_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_cs_ts[(i)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
         }
     }
 
+    CS_TS(0);
     if (warp == 0) cs_tmem_alloc(&tmem_base_smem, 512);
     if (tid == 32) {
         mbar_init(&bar_ring[0], 1); mbar_init(&bar_ring[1], 1);
@@ -242,6 +246,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
     unsigned barrier_epoch = 0;
     const double cnt = (double)P.b * (double)P.n;
 
+    CS_TS(1);
     // ---- phase 0: input moments (training + BN after layer 1): 9 sums over this CTA's points, fp64 atomics, grid barrier
     const bool need_stats = P.training != 0;
     if (need_stats && L1.has_bn) {
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
         __syncthreads();
     }
 
+    CS_TS(2);
     uint32_t ring_phase[2] = {0, 0};
     uint32_t ring_used[2] = {0, 0};     // has the buffer been handed to the tensor core since its last wait?
     uint32_t acc_phase[kCsSlots] = {0, 0};
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
         unsigned char *sWlo = sWhi + (size_t)nchunks * atomB;
         const bool last = (l == P.num_layers - 1);
 
+        CS_TS(3 + (l - 1) * 8 + 0);
         // ---- weights of this layer: split + swizzled store, all K (independent of the barrier: overlaps its latency)
         {
             const int q4 = K >> 2, total = npad * q4;   // float4 units
@@ -305,6 +312,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
             }
             for (int c = tid; c < npad; c += kCsThreads) sBias[c] = (c < N && Lc.bias) ? Lc.bias[c] : 0.f;
         }
+        CS_TS(3 + (l - 1) * 8 + 1);
         // ---- BatchNorm (+ReLU) of the producer layer as a per-channel affine map
         for (int c = tid; c < K; c += kCsThreads) {
             float sc = 1.f, sh = 0.f;
@@ -337,11 +345,14 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
                 sc = Lp.gamma[c] * invstd;
                 sh = Lp.beta[c] - mean * sc;
             }
+            // tensor memory holds W.a WITHOUT the producer's bias (layer 1 is evaluated with its bias): fold it into the shift
+            if (l >= 2 && Lp.bias) sh = fmaf(Lp.bias[c], sc, sh);
             sScale[c] = sc;
             sShift[c] = sh;
         }
         __syncthreads();
 
+        CS_TS(3 + (l - 1) * 8 + 2);
         // ---- main loop: for each tile slot, K chunks of 32: operand prep (all warps) overlapped with the MMAs of the previous chunk
         const uint32_t in_region = (uint32_t)(parity * kCsRegion), out_region = (uint32_t)((parity ^ 1) * kCsRegion);
         int chunk_counter = 0;
@@ -401,6 +412,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
             }
         }
 
+        CS_TS(3 + (l - 1) * 8 + 3);
         // ---- epilogue per slot: batch statistics (sum, sumsq) or, for the last layer, max / min over the tile's valid rows
         const bool want_stats = need_stats && Lc.has_bn;
         for (int s = 0; s < nslots; s++) {   // every MMA of this layer has landed in tensor memory
@@ -408,6 +420,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
             acc_phase[s] ^= 1;
         }
         cs_fence_after();
+        CS_TS(3 + (l - 1) * 8 + 4);
         for (int s = 0; s < nslots; s++) {
             if (!want_stats && !last) break;
             const int np = np_of[s];
@@ -460,9 +473,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
         }
         parity ^= 1;
         cs_fence_before();
+        CS_TS(3 + (l - 1) * 8 + 5);
         if (want_stats) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // every tile's statistics are in before anyone normalises
         else __syncthreads();
         cs_fence_after();
+        CS_TS(3 + (l - 1) * 8 + 6);
     }
 
     // drain the ring barriers so no arrival is pending at exit, then release tensor memory
@@ -471,6 +486,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
     cs_fence_before();
     __syncthreads();
     if (warp == 0) cs_tmem_dealloc(tmem0, 512);
+}
+
+int debug_conv_stack_timestamps(long long *host_out64)
+{
+    return cudaMemcpyFromSymbol(host_out64, g_cs_ts, sizeof(long long) * 64) == cudaSuccess ? SNB200_OK : SNB200_ECUDA;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
