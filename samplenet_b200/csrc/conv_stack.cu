@@ -156,8 +156,7 @@ __device__ __forceinline__ void cs_grid_barrier(unsigned *counter, unsigned targ
         unsigned v, spin = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (v < target) __nanosleep(32);
-            if (++spin > (1u << 22)) __trap();
+            if (++spin > (1u << 26)) __trap();
         } while (v < target);
     }
     __syncthreads();
@@ -185,7 +184,22 @@ __device__ __forceinline__ float cs_colreduce(float *s, int lane)
 __device__ long long g_cs_ts[64];
 #define CS_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_cs_ts[(i)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
+__device__ __forceinline__ void cs_named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void cs_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Thread roles: warps 0..7 (256 threads) are PRODUCERS (operand preparation, weight staging, epilogues); warp 8 is the MMA
+// ISSUER (lane 0 issues tcgen05.mma / tcgen05.commit, the warp only waits on mbarriers).  Producers and issuer walk the
+// same (layer, slot, chunk) sequence and meet through mbarriers, never through __syncthreads inside the main loop:
+//   bar_full[rb]  producers -> issuer : ring buffer rb holds a prepared 32-wide K chunk   (256 arrivals)
+//   bar_ring[rb]  tensor core -> producers : the MMAs that read ring buffer rb have completed (tcgen05.commit)
+//   bar_acc[s]    tensor core -> producers : every MMA of tile slot s of this layer has completed
+constexpr int kCsProducers = 256;
+constexpr int kCsThreadsAll = kCsProducers + 32;
+
+__global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // shared-memory map (dynamic): [A ring: 2 x (hi 16 KB + lo 16 KB)] [W hi | W lo : 2 x c_in x c_out x 4 B]
@@ -193,17 +207,20 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
     sA[0][0] = smem_raw;             sA[0][1] = smem_raw + 16384;
     sA[1][0] = smem_raw + 32768;     sA[1][1] = smem_raw + 49152;
     unsigned char *sWhi = smem_raw + 65536;
-    __shared__ float sScale[128], sShift[128], sBias[128];
+    __shared__ __align__(16) float sScale[128];
+    __shared__ __align__(16) float sShift[128];
+    __shared__ float sBias[128];
     __shared__ float sX[kCsSlots][kCsM * 3];
     __shared__ float sW1[128 * 3], sB1[128];
     __shared__ float sRedA[4][128], sRedB[4][128];
-    __shared__ uint64_t bar_ring[2], bar_acc[kCsSlots];
+    __shared__ uint64_t bar_full[2], bar_ring[2], bar_acc[kCsSlots];
     __shared__ uint32_t tmem_base_smem;
     __shared__ double sMom[9];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, hsel = warp >> 2;           // TMEM lane quarter, column half
-    const int row = q * 32 + lane;                      // the point row this thread owns in every tile
+    const bool producer = warp < 8;
+    const int q = warp & 3, hsel = (warp >> 2) & 1;     // TMEM lane quarter, column half (producers)
+    const int row = q * 32 + lane;                      // the point row this producer thread owns in every tile
     const int G = gridDim.x;
     int tile_of[kCsSlots], np_of[kCsSlots];
     int nslots = 0;
@@ -220,8 +237,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
     }
 
     CS_TS(0);
-    if (warp == 0) cs_tmem_alloc(&tmem_base_smem, 512);
-    if (tid == 32) {
+    if (warp == 8) cs_tmem_alloc(&tmem_base_smem, 512);
+    if (tid == 0) {
+        mbar_init(&bar_full[0], kCsProducers); mbar_init(&bar_full[1], kCsProducers);
         mbar_init(&bar_ring[0], 1); mbar_init(&bar_ring[1], 1);
         mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
         fence_mbar_init();
@@ -229,41 +247,51 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
     if (tid < 9) sMom[tid] = 0.0;
     // the cloud tiles of this CTA and layer 1's weights
     const CsLayer &L1 = P.L[0];
-    for (int s = 0; s < nslots; s++) {
-        const int t = tile_of[s], cloud = t / P.tiles_per_cloud, p0 = (t % P.tiles_per_cloud) * kCsM;
-        const float *xc = P.x + (size_t)cloud * P.n * 3;
-        for (int e = tid; e < kCsM * 3; e += kCsThreads) {
-            const int r = e / 3, c = e % 3;
-            sX[s][e] = (r < np_of[s]) ? (P.layout == SNB200_BNC ? xc[(size_t)(p0 + r) * 3 + c] : xc[(size_t)c * P.n + p0 + r]) : 0.f;
+    if (producer) {
+        for (int s = 0; s < nslots; s++) {
+            const int t = tile_of[s], cloud = t / P.tiles_per_cloud, p0 = (t % P.tiles_per_cloud) * kCsM;
+            const float *xc = P.x + (size_t)cloud * P.n * 3;
+            if (P.layout == SNB200_BNC) {
+                const float *src = xc + (size_t)p0 * 3;
+                const int nf = np_of[s] * 3;
+                for (int e = tid; e < kCsM * 3; e += kCsProducers) sX[s][e] = (e < nf) ? __ldg(src + e) : 0.f;
+            } else {
+                for (int e = tid; e < kCsM * 3; e += kCsProducers) {
+                    const int c = e / kCsM, r = e % kCsM;    // coalesced along points
+                    sX[s][r * 3 + c] = (r < np_of[s]) ? __ldg(xc + (size_t)c * P.n + p0 + r) : 0.f;
+                }
+            }
         }
+        for (int e = tid; e < L1.c_out * 3; e += kCsProducers) sW1[e] = __ldg(L1.weight + e);
+        for (int e = tid; e < L1.c_out; e += kCsProducers) sB1[e] = L1.bias ? __ldg(L1.bias + e) : 0.f;
     }
-    for (int e = tid; e < L1.c_out * 3; e += kCsThreads) sW1[e] = L1.weight[e];
-    for (int e = tid; e < L1.c_out; e += kCsThreads) sB1[e] = L1.bias ? L1.bias[e] : 0.f;
     cs_fence_before();
     __syncthreads();
     cs_fence_after();
     const uint32_t tmem0 = tmem_base_smem;
     unsigned barrier_epoch = 0;
-    const double cnt = (double)P.b * (double)P.n;
-
+    const double cnt = (double)P.b * (double)P.n, inv_cnt = 1.0 / cnt;
     CS_TS(1);
+
     // ---- phase 0: input moments (training + BN after layer 1): 9 sums over this CTA's points, fp64 atomics, grid barrier
     const bool need_stats = P.training != 0;
     if (need_stats && L1.has_bn) {
-        float a9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (tid < kCsM * nslots) {
-            const int s = tid / kCsM, r = tid % kCsM;
-            if (r < np_of[s]) {
-                const float px = sX[s][r * 3 + 0], py = sX[s][r * 3 + 1], pz = sX[s][r * 3 + 2];
-                a9[0] = px; a9[1] = py; a9[2] = pz;
-                a9[3] = px * px; a9[4] = px * py; a9[5] = px * pz; a9[6] = py * py; a9[7] = py * pz; a9[8] = pz * pz;
+        if (producer) {
+            float a9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (tid < kCsM * nslots) {
+                const int s = tid / kCsM, r = tid % kCsM;
+                if (r < np_of[s]) {
+                    const float px = sX[s][r * 3 + 0], py = sX[s][r * 3 + 1], pz = sX[s][r * 3 + 2];
+                    a9[0] = px; a9[1] = py; a9[2] = pz;
+                    a9[3] = px * px; a9[4] = px * py; a9[5] = px * pz; a9[6] = py * py; a9[7] = py * pz; a9[8] = pz * pz;
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 9; j++) {
-            float v = a9[j];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-            if (lane == 0) atomicAdd(&sMom[j], (double)v);
+            for (int j = 0; j < 9; j++) {
+                float v = a9[j];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+                if (lane == 0) atomicAdd(&sMom[j], (double)v);
+            }
         }
         __syncthreads();
         if (tid < 9) atomicAdd(P.mom + tid, sMom[tid]);
@@ -271,10 +299,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
         if (tid < 9) sMom[tid] = __ldcg(P.mom + tid);
         __syncthreads();
     }
-
     CS_TS(2);
-    uint32_t ring_phase[2] = {0, 0};
-    uint32_t ring_used[2] = {0, 0};     // has the buffer been handed to the tensor core since its last wait?
+
+    uint32_t g = 0;                     // global chunk counter (same sequence in producers and issuer)
     uint32_t acc_phase[kCsSlots] = {0, 0};
     int parity = 0;                     // TMEM region parity holding the CURRENT layer's input (previous layer's raw output)
 
@@ -285,207 +312,220 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stack_kernel(const __grid_
         const int npad = N <= 64 ? 64 : 128;
         const uint32_t idesc = cs_idesc(kCsM, npad);
         const uint32_t atomB = (uint32_t)npad * 128u;
-        const int nchunks = K / 32;
+        const int nchunks = K >> 5;
         unsigned char *sWlo = sWhi + (size_t)nchunks * atomB;
         const bool last = (l == P.num_layers - 1);
+        const bool want_stats = need_stats && Lc.has_bn;
+        const uint32_t in_region = (uint32_t)(parity * kCsRegion), out_region = (uint32_t)((parity ^ 1) * kCsRegion);
 
-        CS_TS(3 + (l - 1) * 8 + 0);
-        // ---- weights of this layer: split + swizzled store, all K (independent of the barrier: overlaps its latency)
-        {
-            const int q4 = K >> 2, total = npad * q4;   // float4 units
-            for (int e0 = tid; e0 < total; e0 += kCsThreads * 8) {
-                float4 v[8];
+        if (!producer) {
+            // =============================== MMA issuer warp ===============================
+            for (int s = 0; s < nslots; s++) {
+                const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
+                for (int kc = 0; kc < nchunks; kc++, g++) {
+                    const int rb = g & 1;
+                    cs_mbar_wait(&bar_full[rb], (g >> 1) & 1);
+                    cs_fence_after();
+                    if (lane == 0) {
+                        const uint64_t a_hi = cs_sdesc(smem_u32(sA[rb][0])), a_lo = cs_sdesc(smem_u32(sA[rb][1]));
+                        const uint64_t b_hi = cs_sdesc(smem_u32(sWhi) + (uint32_t)kc * atomB), b_lo = cs_sdesc(smem_u32(sWlo) + (uint32_t)kc * atomB);
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int e = e0 + u * kCsThreads;
-                    const int nrow = e / q4, kq = e % q4;
-                    v[u] = (e < total && nrow < N) ? __ldg(reinterpret_cast<const float4 *>(Lc.weight + (size_t)nrow * K) + kq) : make_float4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int e = e0 + u * kCsThreads;
-                    if (e < total) {
-                        const int nrow = e / q4, kq = e % q4;
-                        cs_split_store(sWhi, sWlo, (uint32_t)(kq >> 3) * atomB + cs_sw128(nrow, kq & 7), v[u]);
+                        for (int ks = 0; ks < 4; ks++) {   // 32 bytes (K = 8 tf32) per step: +2 in the 16-byte address field
+                            const uint64_t o = (uint64_t)(ks * 2);
+                            cs_umma(t_out, a_lo + o, b_hi + o, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            cs_umma(t_out, a_hi + o, b_lo + o, idesc, 1u);
+                            cs_umma(t_out, a_hi + o, b_hi + o, idesc, 1u);
+                        }
+                        cs_commit(&bar_ring[rb]);
+                        if (kc == nchunks - 1) cs_commit(&bar_acc[s]);
                     }
+                    __syncwarp();
                 }
             }
-            for (int c = tid; c < npad; c += kCsThreads) sBias[c] = (c < N && Lc.bias) ? Lc.bias[c] : 0.f;
-        }
-        CS_TS(3 + (l - 1) * 8 + 1);
-        // ---- BatchNorm (+ReLU) of the producer layer as a per-channel affine map
-        for (int c = tid; c < K; c += kCsThreads) {
-            float sc = 1.f, sh = 0.f;
-            if (Lp.has_bn) {
-                float mean, var;
-                if (P.training) {
-                    double m, v;
-                    if (l == 1) {   // analytic statistics of layer 1 from the input moments
-                        const double mx = sMom[0] / cnt, my = sMom[1] / cnt, mz = sMom[2] / cnt;
-                        const double cxx = sMom[3] / cnt - mx * mx, cxy = sMom[4] / cnt - mx * my, cxz = sMom[5] / cnt - mx * mz;
-                        const double cyy = sMom[6] / cnt - my * my, cyz = sMom[7] / cnt - my * mz, czz = sMom[8] / cnt - mz * mz;
-                        const double a0 = sW1[c * 3 + 0], a1 = sW1[c * 3 + 1], a2 = sW1[c * 3 + 2];
-                        m = a0 * mx + a1 * my + a2 * mz + (double)sB1[c];
-                        v = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
-                        if (v < 0) v = 0;
-                        if (blockIdx.x == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
-                            Lp.stats[c] = cnt * m;
-                            Lp.stats[K + c] = cnt * (v + m * m);
+        } else {
+            // =============================== producer warps ===============================
+            CS_TS(3 + (l - 1) * 8 + 0);
+            // every MMA of the previous layer has completed (bar_acc waited in its epilogue): W may be overwritten
+            {
+                const int sh4 = (K == 32) ? 3 : (K == 64 ? 4 : 5);   // log2(K / 4); K is 32, 64 or 128 on this path
+                const int q4m = (1 << sh4) - 1, total = npad << sh4;
+                for (int e0 = tid; e0 < total; e0 += kCsProducers * 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = e0 + u * kCsProducers;
+                        const int nrow = e >> sh4, kq = e & q4m;
+                        v[u] = (e < total && nrow < N) ? __ldg(reinterpret_cast<const float4 *>(Lc.weight + (size_t)nrow * K) + kq) : make_float4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = e0 + u * kCsProducers;
+                        if (e < total) {
+                            const int nrow = e >> sh4, kq = e & q4m;
+                            cs_split_store(sWhi, sWlo, (uint32_t)(kq >> 3) * atomB + cs_sw128(nrow, kq & 7), v[u]);
+                        }
+                    }
+                }
+                for (int c = tid; c < npad; c += kCsProducers) sBias[c] = (c < N && Lc.bias) ? __ldg(Lc.bias + c) : 0.f;
+            }
+            CS_TS(3 + (l - 1) * 8 + 1);
+            // BatchNorm (+ReLU) of the producer layer as a per-channel affine map
+            for (int c = tid; c < K; c += kCsProducers) {
+                float sc = 1.f, sh = 0.f;
+                if (Lp.has_bn) {
+                    float mean, var;
+                    if (P.training) {
+                        double m, v;
+                        if (l == 1) {   // analytic statistics of layer 1 from the input moments
+                            const double mx = sMom[0] * inv_cnt, my = sMom[1] * inv_cnt, mz = sMom[2] * inv_cnt;
+                            const double cxx = sMom[3] * inv_cnt - mx * mx, cxy = sMom[4] * inv_cnt - mx * my, cxz = sMom[5] * inv_cnt - mx * mz;
+                            const double cyy = sMom[6] * inv_cnt - my * my, cyz = sMom[7] * inv_cnt - my * mz, czz = sMom[8] * inv_cnt - mz * mz;
+                            const double a0 = sW1[c * 3 + 0], a1 = sW1[c * 3 + 1], a2 = sW1[c * 3 + 2];
+                            m = a0 * mx + a1 * my + a2 * mz + (double)sB1[c];
+                            v = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
+                            if (v < 0) v = 0;
+                            if (blockIdx.x == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
+                                Lp.stats[c] = cnt * m;
+                                Lp.stats[K + c] = cnt * (v + m * m);
+                            }
+                        } else {
+                            m = __ldcg(Lp.stats + c) * inv_cnt;
+                            v = __ldcg(Lp.stats + K + c) * inv_cnt - m * m;
+                            if (v < 0) v = 0;
+                        }
+                        mean = (float)m; var = (float)v;
+                    } else {
+                        mean = Lp.run_mean[c]; var = Lp.run_var[c];
+                    }
+                    const float invstd = 1.0f / sqrtf(var + Lp.eps);
+                    sc = Lp.gamma[c] * invstd;
+                    sh = Lp.beta[c] - mean * sc;
+                }
+                // tensor memory holds W.a WITHOUT the producer's bias (layer 1 is evaluated with its bias): fold it into the shift
+                if (l >= 2 && Lp.bias) sh = fmaf(Lp.bias[c], sc, sh);
+                sScale[c] = sc;
+                sShift[c] = sh;
+            }
+            fence_proxy_async();                 // weight tile written by the generic proxy -> visible to the tensor core
+            cs_named_sync(1, kCsProducers);
+            CS_TS(3 + (l - 1) * 8 + 2);
+
+            // ---- operand preparation: chunk g+1 is prepared while the tensor core works on chunk g
+            for (int s = 0; s < nslots; s++) {
+                const int np = np_of[s];
+                const uint32_t t_in = tmem0 + (uint32_t)(s * 2 * kCsRegion) + in_region;
+                for (int kc = 0; kc < nchunks; kc++, g++) {
+                    const int rb = g & 1;
+                    if (g >= 2) {   // the MMAs of chunk g-2 (same ring buffer) must have completed
+                        cs_mbar_wait(&bar_ring[rb], ((g >> 1) - 1) & 1);
+                        cs_fence_after();
+                    }
+                    // this thread prepares row `row`, k = kc*32 + hsel*16 .. +15 (4 chunks of 16 bytes)
+                    float v[16];
+                    const int kb = kc * 32 + hsel * 16;
+                    if (l == 1) {
+                        const float px = sX[s][row * 3 + 0], py = sX[s][row * 3 + 1], pz = sX[s][row * 3 + 2];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int c = kb + j;
+                            v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
                         }
                     } else {
-                        m = __ldcg(Lp.stats + c) / cnt;
-                        v = __ldcg(Lp.stats + K + c) / cnt - m * m;
-                        if (v < 0) v = 0;
+                        cs_ld16(t_in + ((uint32_t)(q * 32) << 16) + (uint32_t)kb, v);
                     }
-                    mean = (float)m; var = (float)v;
-                } else {
-                    mean = Lp.run_mean[c]; var = Lp.run_var[c];
+                    const bool pv = row < np;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(sScale + kb + c4 * 4);
+                        const float4 sh = *reinterpret_cast<const float4 *>(sShift + kb + c4 * 4);
+                        float4 t;
+                        t.x = fmaf(v[c4 * 4 + 0], sc.x, sh.x); t.y = fmaf(v[c4 * 4 + 1], sc.y, sh.y);
+                        t.z = fmaf(v[c4 * 4 + 2], sc.z, sh.z); t.w = fmaf(v[c4 * 4 + 3], sc.w, sh.w);
+                        if (Lp.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                        if (!pv) t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 4 + c4), t);
+                    }
+                    cs_fence_before();
+                    fence_proxy_async();
+                    cs_mbar_arrive(&bar_full[rb]);
                 }
-                const float invstd = 1.0f / sqrtf(var + Lp.eps);
-                sc = Lp.gamma[c] * invstd;
-                sh = Lp.beta[c] - mean * sc;
             }
-            // tensor memory holds W.a WITHOUT the producer's bias (layer 1 is evaluated with its bias): fold it into the shift
-            if (l >= 2 && Lp.bias) sh = fmaf(Lp.bias[c], sc, sh);
-            sScale[c] = sc;
-            sShift[c] = sh;
-        }
-        __syncthreads();
+            CS_TS(3 + (l - 1) * 8 + 3);
 
-        CS_TS(3 + (l - 1) * 8 + 2);
-        // ---- main loop: for each tile slot, K chunks of 32: operand prep (all warps) overlapped with the MMAs of the previous chunk
-        const uint32_t in_region = (uint32_t)(parity * kCsRegion), out_region = (uint32_t)((parity ^ 1) * kCsRegion);
-        int chunk_counter = 0;
-        for (int s = 0; s < nslots; s++) {
-            const int np = np_of[s];
-            const uint32_t t_in = tmem0 + (uint32_t)(s * 2 * kCsRegion) + in_region;
-            const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-            for (int kc = 0; kc < nchunks; kc++, chunk_counter++) {
-                const int rb = chunk_counter & 1;
-                if (ring_used[rb]) {   // the tensor core must be done reading this ring buffer
-                    cs_mbar_wait(&bar_ring[rb], ring_phase[rb]);
-                    ring_phase[rb] ^= 1;
-                    ring_used[rb] = 0;
-                    cs_fence_after();
-                }
-                // this thread prepares row `row`, k = kc*32 + hsel*16 .. +15 (4 chunks of 16 bytes)
-                float v[16];
-                const int kb = kc * 32 + hsel * 16;
-                if (l == 1) {
-                    const float px = sX[s][row * 3 + 0], py = sX[s][row * 3 + 1], pz = sX[s][row * 3 + 2];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int c = kb + j;
-                        v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
-                    }
-                } else {
-                    cs_ld16(t_in + ((uint32_t)(q * 32) << 16) + (uint32_t)kb, v);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    float t = fmaf(v[j], sScale[kb + j], sShift[kb + j]);
-                    if (Lp.relu) t = fmaxf(t, 0.f);
-                    v[j] = (row < np) ? t : 0.f;
-                }
-#pragma unroll
-                for (int c4 = 0; c4 < 4; c4++)
-                    cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 4 + c4), make_float4(v[c4 * 4 + 0], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]));
-                cs_fence_before();
-                fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) {
-                    cs_fence_after();
-#pragma unroll 1
-                    for (int ks = 0; ks < 4; ks++) {
-                        const uint32_t kin = (uint32_t)ks * 32u;
-                        const uint64_t a_hi = cs_sdesc(smem_u32(sA[rb][0]) + kin), a_lo = cs_sdesc(smem_u32(sA[rb][1]) + kin);
-                        const uint64_t b_hi = cs_sdesc(smem_u32(sWhi) + (uint32_t)kc * atomB + kin), b_lo = cs_sdesc(smem_u32(sWlo) + (uint32_t)kc * atomB + kin);
-                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                        cs_umma(t_out, a_lo, b_hi, idesc, acc);
-                        cs_umma(t_out, a_hi, b_lo, idesc, 1u);
-                        cs_umma(t_out, a_hi, b_hi, idesc, 1u);
-                    }
-                    cs_commit(&bar_ring[rb]);
-                    if (kc == nchunks - 1) cs_commit(&bar_acc[s]);
-                }
-                ring_used[rb] = 1;
+            // ---- epilogue: wait for the accumulators, then batch statistics and / or per-tile extrema
+            for (int s = 0; s < nslots; s++) {
+                cs_mbar_wait(&bar_acc[s], acc_phase[s]);
+                acc_phase[s] ^= 1;
             }
-        }
-
-        CS_TS(3 + (l - 1) * 8 + 3);
-        // ---- epilogue per slot: batch statistics (sum, sumsq) or, for the last layer, max / min over the tile's valid rows
-        const bool want_stats = need_stats && Lc.has_bn;
-        for (int s = 0; s < nslots; s++) {   // every MMA of this layer has landed in tensor memory
-            cs_mbar_wait(&bar_acc[s], acc_phase[s]);
-            acc_phase[s] ^= 1;
-        }
-        cs_fence_after();
-        CS_TS(3 + (l - 1) * 8 + 4);
-        for (int s = 0; s < nslots; s++) {
-            if (!want_stats && !last) break;
-            const int np = np_of[s];
-            const bool pv = row < np;
-            const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-            // pass A: sums / sums of squares
-            if (want_stats) {
+            cs_fence_after();
+            CS_TS(3 + (l - 1) * 8 + 4);
+            if (want_stats) {   // sums over BOTH tile slots first (same columns, different rows), one reduction per 32-column block
                 for (int cb = hsel * 32; cb < npad; cb += 64) {
-                    float v[32], w[32];
-                    cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                    float v[32], w[32], t[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float t = pv ? v[j] + sBias[cb + j] : 0.f;
-                        v[j] = t;
-                        w[j] = t * t;
+                    for (int j = 0; j < 32; j++) { v[j] = 0.f; w[j] = 0.f; }
+                    for (int s = 0; s < nslots; s++) {
+                        const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
+                        cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, t);
+                        if (row < np_of[s]) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const float u = t[j] + sBias[cb + j];
+                                v[j] += u;
+                                w[j] = fmaf(u, u, w[j]);
+                            }
+                        }
                     }
                     sRedA[q][cb + lane] = cs_colreduce<0>(v, lane);
                     sRedB[q][cb + lane] = cs_colreduce<0>(w, lane);
                 }
-                __syncthreads();
+                cs_named_sync(1, kCsProducers);
                 if (tid < N) {
                     const float sm = (sRedA[0][tid] + sRedA[1][tid]) + (sRedA[2][tid] + sRedA[3][tid]);
                     const float sq = (sRedB[0][tid] + sRedB[1][tid]) + (sRedB[2][tid] + sRedB[3][tid]);
                     atomicAdd(Lc.stats + tid, (double)sm);
                     atomicAdd(Lc.stats + N + tid, (double)sq);
                 }
-                __syncthreads();
+                cs_named_sync(1, kCsProducers);
             }
-            // pass B: extrema for the max-pool (last layer only)
-            if (last) {
-                for (int cb = hsel * 32; cb < npad; cb += 64) {
-                    float v[32], w[32];
-                    cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+            if (last) {   // extrema for the max-pool, per tile
+                for (int s = 0; s < nslots; s++) {
+                    const bool pv = row < np_of[s];
+                    const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
+                    for (int cb = hsel * 32; cb < npad; cb += 64) {
+                        float v[32], w[32];
+                        cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float t = v[j] + sBias[cb + j];
-                        v[j] = pv ? t : -INFINITY;
-                        w[j] = pv ? t : INFINITY;
+                        for (int j = 0; j < 32; j++) {
+                            const float u = v[j] + sBias[cb + j];
+                            v[j] = pv ? u : -INFINITY;
+                            w[j] = pv ? u : INFINITY;
+                        }
+                        sRedA[q][cb + lane] = cs_colreduce<1>(v, lane);
+                        sRedB[q][cb + lane] = cs_colreduce<2>(w, lane);
                     }
-                    sRedA[q][cb + lane] = cs_colreduce<1>(v, lane);
-                    sRedB[q][cb + lane] = cs_colreduce<2>(w, lane);
+                    cs_named_sync(1, kCsProducers);
+                    if (tid < N) {
+                        P.tile_max[(size_t)tile_of[s] * N + tid] = fmaxf(fmaxf(sRedA[0][tid], sRedA[1][tid]), fmaxf(sRedA[2][tid], sRedA[3][tid]));
+                        P.tile_min[(size_t)tile_of[s] * N + tid] = fminf(fminf(sRedB[0][tid], sRedB[1][tid]), fminf(sRedB[2][tid], sRedB[3][tid]));
+                    }
+                    cs_named_sync(1, kCsProducers);
                 }
-                __syncthreads();
-                if (tid < N) {
-                    P.tile_max[(size_t)tile_of[s] * N + tid] = fmaxf(fmaxf(sRedA[0][tid], sRedA[1][tid]), fmaxf(sRedA[2][tid], sRedA[3][tid]));
-                    P.tile_min[(size_t)tile_of[s] * N + tid] = fminf(fminf(sRedB[0][tid], sRedB[1][tid]), fminf(sRedB[2][tid], sRedB[3][tid]));
-                }
-                __syncthreads();
             }
+            CS_TS(3 + (l - 1) * 8 + 5);
         }
         parity ^= 1;
         cs_fence_before();
-        CS_TS(3 + (l - 1) * 8 + 5);
         if (want_stats) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // every tile's statistics are in before anyone normalises
         else __syncthreads();
         cs_fence_after();
         CS_TS(3 + (l - 1) * 8 + 6);
     }
 
-    // drain the ring barriers so no arrival is pending at exit, then release tensor memory
-    for (int rb = 0; rb < 2; rb++)
-        if (ring_used[rb]) cs_mbar_wait(&bar_ring[rb], ring_phase[rb]);
+    // every commit has been observed through bar_acc; release tensor memory
     cs_fence_before();
     __syncthreads();
-    if (warp == 0) cs_tmem_dealloc(tmem0, 512);
+    if (warp == 8) cs_tmem_dealloc(tmem0, 512);
 }
 
 int debug_conv_stack_timestamps(long long *host_out64)
@@ -500,7 +540,7 @@ bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
     if (conv[0].c_out % 32 != 0 || conv[0].c_out > 128) return false;
     size_t wmax = 0;
     for (int l = 1; l < nconv; l++) {
-        if (conv[l].c_in % 32 != 0 || conv[l].c_in > 128 || conv[l].c_out > 128 || conv[l].c_out < 8) return false;
+        if ((conv[l].c_in != 32 && conv[l].c_in != 64 && conv[l].c_in != 128) || conv[l].c_out > 128 || conv[l].c_out < 8) return false;
         const size_t npad = conv[l].c_out <= 64 ? 64 : 128;
         wmax = max(wmax, 2 * (size_t)conv[l].c_in * npad * 4);
     }
@@ -534,7 +574,7 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     int grid = min(P.tiles, kNumSMs);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kCsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kCsThreadsAll); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
