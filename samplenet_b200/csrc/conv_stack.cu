@@ -30,6 +30,8 @@ constexpr int kCsM = 128;
 constexpr int kCsMaxLayers = SNB200_MAX_CONV_LAYERS;
 constexpr int kCsSlots = 2;           // tiles per CTA
 constexpr int kCsRegion = 128;        // TMEM columns per (slot, parity) region
+constexpr int kCsProducers = 256;
+constexpr int kCsThreadsAll = kCsProducers + 32;
 
 struct CsLayer {
     int c_in, c_out;
@@ -92,6 +94,16 @@ __device__ __forceinline__ void cs_ld16(uint32_t taddr, float *v)
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void cs_ld16_issue(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void cs_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cs_ld32(uint32_t taddr, float *v)
 {
     uint32_t r[32];
@@ -147,6 +159,19 @@ __device__ __forceinline__ void cs_mbar_wait(uint64_t *bar, uint32_t parity)
         if (spin > (1u << 24)) __trap();
     }
 }
+__device__ __forceinline__ void cs_grid_arrive(unsigned *counter)
+{
+    __threadfence();
+    atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void cs_grid_wait(unsigned *counter, unsigned target)
+{
+    unsigned v, spin = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (++spin > (1u << 26)) __trap();
+    } while (v < target);
+}
 __device__ __forceinline__ void cs_grid_barrier(unsigned *counter, unsigned target)
 {
     __syncthreads();
@@ -181,6 +206,37 @@ __device__ __forceinline__ float cs_colreduce(float *s, int lane)
     return s[0];
 }
 
+// Split + swizzled staging of one layer's whole weight matrix (all K) into shared memory, by the 256 producer threads.
+// Only legal once every MMA that reads the previous layer's weights has completed.
+__device__ __forceinline__ void cs_stage_weights(const CsLayer &Lc, unsigned char *sWhi, float *sBias, int tid)
+{
+    const int K = Lc.c_in, N = Lc.c_out;
+    const int npad = N <= 64 ? 64 : 128;
+    const uint32_t atomB = (uint32_t)npad * 128u;
+    unsigned char *sWlo = sWhi + (size_t)(K >> 5) * atomB;
+    const int sh4 = (K == 32) ? 3 : (K == 64 ? 4 : 5);   // log2(K / 4); K is 32, 64 or 128 on this path
+    const int q4m = (1 << sh4) - 1, total = npad << sh4;
+    for (int e0 = tid; e0 < total; e0 += kCsProducers * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * kCsProducers;
+            const int nrow = e >> sh4, kq = e & q4m;
+            v[u] = (e < total && nrow < N) ? __ldg(reinterpret_cast<const float4 *>(Lc.weight + (size_t)nrow * K) + kq) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * kCsProducers;
+            if (e < total) {
+                const int nrow = e >> sh4, kq = e & q4m;
+                cs_split_store(sWhi, sWlo, (uint32_t)(kq >> 3) * atomB + cs_sw128(nrow, kq & 7), v[u]);
+            }
+        }
+    }
+    for (int c = tid; c < npad; c += kCsProducers) sBias[c] = (c < N && Lc.bias) ? __ldg(Lc.bias + c) : 0.f;
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
+}
+
 __device__ long long g_cs_ts[64];
 #define CS_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_cs_ts[(i)] = clock64(); } while (0)
 
@@ -196,8 +252,6 @@ __device__ __forceinline__ void cs_mbar_arrive(uint64_t *bar)
 //   bar_full[rb]  producers -> issuer : ring buffer rb holds a prepared 32-wide K chunk   (256 arrivals)
 //   bar_ring[rb]  tensor core -> producers : the MMAs that read ring buffer rb have completed (tcgen05.commit)
 //   bar_acc[s]    tensor core -> producers : every MMA of tile slot s of this layer has completed
-constexpr int kCsProducers = 256;
-constexpr int kCsThreadsAll = kCsProducers + 32;
 
 __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
 {
@@ -295,8 +349,15 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         }
         __syncthreads();
         if (tid < 9) atomicAdd(P.mom + tid, sMom[tid]);
-        cs_grid_barrier(P.barrier, ++barrier_epoch * G);
+        __syncthreads();
+        if (tid == 0) cs_grid_arrive(P.barrier);
+        if (producer) cs_stage_weights(P.L[1], sWhi, sBias, tid);     // overlaps the barrier latency
+        if (tid == 0) cs_grid_wait(P.barrier, ++barrier_epoch * G);
+        __syncthreads();
         if (tid < 9) sMom[tid] = __ldcg(P.mom + tid);
+        __syncthreads();
+    } else {
+        if (producer) cs_stage_weights(P.L[1], sWhi, sBias, tid);
         __syncthreads();
     }
     CS_TS(2);
@@ -345,29 +406,6 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         } else {
             // =============================== producer warps ===============================
             CS_TS(3 + (l - 1) * 8 + 0);
-            // every MMA of the previous layer has completed (bar_acc waited in its epilogue): W may be overwritten
-            {
-                const int sh4 = (K == 32) ? 3 : (K == 64 ? 4 : 5);   // log2(K / 4); K is 32, 64 or 128 on this path
-                const int q4m = (1 << sh4) - 1, total = npad << sh4;
-                for (int e0 = tid; e0 < total; e0 += kCsProducers * 8) {
-                    float4 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int e = e0 + u * kCsProducers;
-                        const int nrow = e >> sh4, kq = e & q4m;
-                        v[u] = (e < total && nrow < N) ? __ldg(reinterpret_cast<const float4 *>(Lc.weight + (size_t)nrow * K) + kq) : make_float4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int e = e0 + u * kCsProducers;
-                        if (e < total) {
-                            const int nrow = e >> sh4, kq = e & q4m;
-                            cs_split_store(sWhi, sWlo, (uint32_t)(kq >> 3) * atomB + cs_sw128(nrow, kq & 7), v[u]);
-                        }
-                    }
-                }
-                for (int c = tid; c < npad; c += kCsProducers) sBias[c] = (c < N && Lc.bias) ? __ldg(Lc.bias + c) : 0.f;
-            }
             CS_TS(3 + (l - 1) * 8 + 1);
             // BatchNorm (+ReLU) of the producer layer as a per-channel affine map
             for (int c = tid; c < K; c += kCsProducers) {
@@ -406,23 +444,22 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 sScale[c] = sc;
                 sShift[c] = sh;
             }
-            fence_proxy_async();                 // weight tile written by the generic proxy -> visible to the tensor core
             cs_named_sync(1, kCsProducers);
             CS_TS(3 + (l - 1) * 8 + 2);
 
-            // ---- operand preparation: chunk g+1 is prepared while the tensor core works on chunk g
-            for (int s = 0; s < nslots; s++) {
-                const int np = np_of[s];
-                const uint32_t t_in = tmem0 + (uint32_t)(s * 2 * kCsRegion) + in_region;
-                for (int kc = 0; kc < nchunks; kc++, g++) {
+            // ---- operand preparation: chunk g+1 is prepared while the tensor core works on chunk g; inside a thread the
+            //      tensor-memory load of the NEXT chunk is in flight while the current chunk is normalised, split and stored
+            {
+                const int total_chunks = nslots * nchunks;
+                uint32_t rnext[16];
+                if (l >= 2 && total_chunks > 0)
+                    cs_ld16_issue(tmem0 + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * 16), rnext);
+                for (int ci = 0; ci < total_chunks; ci++, g++) {
+                    const int s = ci / nchunks, kc = ci - s * nchunks;
+                    const int np = np_of[s];
                     const int rb = g & 1;
-                    if (g >= 2) {   // the MMAs of chunk g-2 (same ring buffer) must have completed
-                        cs_mbar_wait(&bar_ring[rb], ((g >> 1) - 1) & 1);
-                        cs_fence_after();
-                    }
-                    // this thread prepares row `row`, k = kc*32 + hsel*16 .. +15 (4 chunks of 16 bytes)
-                    float v[16];
                     const int kb = kc * 32 + hsel * 16;
+                    float v[16];
                     if (l == 1) {
                         const float px = sX[s][row * 3 + 0], py = sX[s][row * 3 + 1], pz = sX[s][row * 3 + 2];
 #pragma unroll
@@ -431,9 +468,16 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
                         }
                     } else {
-                        cs_ld16(t_in + ((uint32_t)(q * 32) << 16) + (uint32_t)kb, v);
+                        cs_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rnext[j]);
+                        if (ci + 1 < total_chunks) {   // next chunk's raw activations: issue now, consume next iteration
+                            const int s2 = (ci + 1) / nchunks, kc2 = (ci + 1) - s2 * nchunks;
+                            cs_ld16_issue(tmem0 + (uint32_t)(s2 * 2 * kCsRegion) + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(kc2 * 32 + hsel * 16), rnext);
+                        }
                     }
                     const bool pv = row < np;
+                    float4 tq[4];
 #pragma unroll
                     for (int c4 = 0; c4 < 4; c4++) {
                         const float4 sc = *reinterpret_cast<const float4 *>(sScale + kb + c4 * 4);
@@ -443,8 +487,14 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         t.z = fmaf(v[c4 * 4 + 2], sc.z, sh.z); t.w = fmaf(v[c4 * 4 + 3], sc.w, sh.w);
                         if (Lp.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                         if (!pv) t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 4 + c4), t);
+                        tq[c4] = t;
                     }
+                    if (g >= 2) {   // the MMAs of chunk g-2 (same ring buffer) must have completed before its operands are overwritten
+                        cs_mbar_wait(&bar_ring[rb], ((g >> 1) - 1) & 1);
+                        cs_fence_after();
+                    }
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 4 + c4), tq[c4]);
                     cs_fence_before();
                     fence_proxy_async();
                     cs_mbar_arrive(&bar_full[rb]);
@@ -516,8 +566,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         }
         parity ^= 1;
         cs_fence_before();
-        if (want_stats) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // every tile's statistics are in before anyone normalises
-        else __syncthreads();
+        __syncthreads();                                         // this CTA's statistics atomics are issued, its MMAs are done
+        if (want_stats && tid == 0) cs_grid_arrive(P.barrier);
+        if (producer && l + 1 < P.num_layers) cs_stage_weights(P.L[l + 1], sWhi, sBias, tid);   // overlaps the barrier latency
+        if (want_stats && tid == 0) cs_grid_wait(P.barrier, (barrier_epoch + 1) * G);   // every tile's statistics are in
+        if (want_stats) barrier_epoch++;
+        __syncthreads();
         cs_fence_after();
         CS_TS(3 + (l - 1) * 8 + 6);
     }

