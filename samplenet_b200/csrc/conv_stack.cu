@@ -30,7 +30,7 @@ constexpr int kCsM = 128;
 constexpr int kCsMaxLayers = SNB200_MAX_CONV_LAYERS;
 constexpr int kCsSlots = 2;           // tiles per CTA
 constexpr int kCsRegion = 128;        // TMEM columns per (slot, parity) region
-constexpr int kCsProducers = 256;
+constexpr int kCsProducers = 512;     // 16 producer warps: TMEM lane quarter = warp & 3, column group = (warp >> 2) & 3
 constexpr int kCsThreadsAll = kCsProducers + 32;
 
 struct CsLayer {
@@ -102,6 +102,13 @@ __device__ __forceinline__ void cs_ld16_issue(uint32_t taddr, uint32_t *r)
           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void cs_ld8_issue(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void cs_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cs_ld32(uint32_t taddr, float *v)
@@ -237,6 +244,25 @@ __device__ __forceinline__ void cs_stage_weights(const CsLayer &Lc, unsigned cha
     fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
 }
 
+// 32 rows x 16 columns held one row per lane: after the five steps lanes 2c and 2c+1 both hold the combined value of column c.
+template <int OP>
+__device__ __forceinline__ float cs_colreduce16(float *s, int lane)
+{
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool up = (lane & (half * 2)) != 0;
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+            const float send = up ? s[j] : s[j + half];
+            const float keep = up ? s[j + half] : s[j];
+            const float recv = __shfl_xor_sync(kFullMask, send, half * 2);
+            s[j] = OP == 0 ? keep + recv : (OP == 1 ? fmaxf(keep, recv) : fminf(keep, recv));
+        }
+    }
+    const float o = __shfl_xor_sync(kFullMask, s[0], 1);
+    return OP == 0 ? s[0] + o : (OP == 1 ? fmaxf(s[0], o) : fminf(s[0], o));
+}
+
 __device__ long long g_cs_ts[64];
 #define CS_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_cs_ts[(i)] = clock64(); } while (0)
 
@@ -272,8 +298,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     __shared__ double sMom[9];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool producer = warp < 8;
-    const int q = warp & 3, hsel = (warp >> 2) & 1;     // TMEM lane quarter, column half (producers)
+    const bool producer = warp < 16;
+    const int q = warp & 3, hsel = (warp >> 2) & 3;     // TMEM lane quarter, column group (producers)
     const int row = q * 32 + lane;                      // the point row this producer thread owns in every tile
     const int G = gridDim.x;
     int tile_of[kCsSlots], np_of[kCsSlots];
@@ -291,7 +317,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     }
 
     CS_TS(0);
-    if (warp == 8) cs_tmem_alloc(&tmem_base_smem, 512);
+    if (warp == 16) cs_tmem_alloc(&tmem_base_smem, 512);
     if (tid == 0) {
         mbar_init(&bar_full[0], kCsProducers); mbar_init(&bar_full[1], kCsProducers);
         mbar_init(&bar_ring[0], 1); mbar_init(&bar_ring[1], 1);
@@ -451,35 +477,37 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             //      tensor-memory load of the NEXT chunk is in flight while the current chunk is normalised, split and stored
             {
                 const int total_chunks = nslots * nchunks;
-                uint32_t rnext[16];
+                uint32_t rnext[8];
                 if (l >= 2 && total_chunks > 0)
-                    cs_ld16_issue(tmem0 + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * 16), rnext);
+                    cs_ld8_issue(tmem0 + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * 8), rnext);
+                int s = 0, kc = 0;
                 for (int ci = 0; ci < total_chunks; ci++, g++) {
-                    const int s = ci / nchunks, kc = ci - s * nchunks;
-                    const int np = np_of[s];
+                    const int np = (s == 0) ? np_of[0] : np_of[1];
                     const int rb = g & 1;
-                    const int kb = kc * 32 + hsel * 16;
-                    float v[16];
+                    const int kb = kc * 32 + hsel * 8;
+                    float v[8];
                     if (l == 1) {
-                        const float px = sX[s][row * 3 + 0], py = sX[s][row * 3 + 1], pz = sX[s][row * 3 + 2];
+                        const float *xr = (s == 0 ? sX[0] : sX[1]) + row * 3;
+                        const float px = xr[0], py = xr[1], pz = xr[2];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
+                        for (int j = 0; j < 8; j++) {
                             const int c = kb + j;
                             v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
                         }
                     } else {
                         cs_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(rnext[j]);
-                        if (ci + 1 < total_chunks) {   // next chunk's raw activations: issue now, consume next iteration
-                            const int s2 = (ci + 1) / nchunks, kc2 = (ci + 1) - s2 * nchunks;
-                            cs_ld16_issue(tmem0 + (uint32_t)(s2 * 2 * kCsRegion) + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(kc2 * 32 + hsel * 16), rnext);
-                        }
+                        for (int j = 0; j < 8; j++) v[j] = __uint_as_float(rnext[j]);
                     }
+                    // advance (slot, chunk) and put the next chunk's raw activations in flight
+                    int s2 = s, kc2 = kc + 1;
+                    if (kc2 == nchunks) { kc2 = 0; s2 = s + 1; }
+                    if (l >= 2 && ci + 1 < total_chunks)
+                        cs_ld8_issue(tmem0 + (uint32_t)(s2 * 2 * kCsRegion) + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(kc2 * 32 + hsel * 8), rnext);
                     const bool pv = row < np;
-                    float4 tq[4];
+                    float4 tq[2];
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
+                    for (int c4 = 0; c4 < 2; c4++) {
                         const float4 sc = *reinterpret_cast<const float4 *>(sScale + kb + c4 * 4);
                         const float4 sh = *reinterpret_cast<const float4 *>(sShift + kb + c4 * 4);
                         float4 t;
@@ -494,10 +522,11 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         cs_fence_after();
                     }
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 4 + c4), tq[c4]);
+                    for (int c4 = 0; c4 < 2; c4++) cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 2 + c4), tq[c4]);
                     cs_fence_before();
                     fence_proxy_async();
                     cs_mbar_arrive(&bar_full[rb]);
+                    s = s2; kc = kc2;
                 }
             }
             CS_TS(3 + (l - 1) * 8 + 3);
@@ -509,25 +538,26 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             }
             cs_fence_after();
             CS_TS(3 + (l - 1) * 8 + 4);
-            if (want_stats) {   // sums over BOTH tile slots first (same columns, different rows), one reduction per 32-column block
-                for (int cb = hsel * 32; cb < npad; cb += 64) {
-                    float v[32], w[32], t[32];
+            if (want_stats) {   // sums over BOTH tile slots first (same columns, different rows), one reduction per 16-column block
+                for (int cb = hsel * 16; cb < npad; cb += 64) {
+                    float v[16], w[16], t[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) { v[j] = 0.f; w[j] = 0.f; }
+                    for (int j = 0; j < 16; j++) { v[j] = 0.f; w[j] = 0.f; }
                     for (int s = 0; s < nslots; s++) {
                         const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-                        cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, t);
-                        if (row < np_of[s]) {
+                        cs_ld16(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, t);
+                        if (row < (s == 0 ? np_of[0] : np_of[1])) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
+                            for (int j = 0; j < 16; j++) {
                                 const float u = t[j] + sBias[cb + j];
                                 v[j] += u;
                                 w[j] = fmaf(u, u, w[j]);
                             }
                         }
                     }
-                    sRedA[q][cb + lane] = cs_colreduce<0>(v, lane);
-                    sRedB[q][cb + lane] = cs_colreduce<0>(w, lane);
+                    const float sm = cs_colreduce16<0>(v, lane);
+                    const float sq = cs_colreduce16<0>(w, lane);
+                    if (!(lane & 1)) { sRedA[q][cb + (lane >> 1)] = sm; sRedB[q][cb + (lane >> 1)] = sq; }
                 }
                 cs_named_sync(1, kCsProducers);
                 if (tid < N) {
@@ -540,24 +570,26 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             }
             if (last) {   // extrema for the max-pool, per tile
                 for (int s = 0; s < nslots; s++) {
-                    const bool pv = row < np_of[s];
+                    const bool pv = row < (s == 0 ? np_of[0] : np_of[1]);
                     const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-                    for (int cb = hsel * 32; cb < npad; cb += 64) {
-                        float v[32], w[32];
-                        cs_ld32(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                    for (int cb = hsel * 16; cb < npad; cb += 64) {
+                        float v[16], w[16];
+                        cs_ld16(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
+                        for (int j = 0; j < 16; j++) {
                             const float u = v[j] + sBias[cb + j];
                             v[j] = pv ? u : -INFINITY;
                             w[j] = pv ? u : INFINITY;
                         }
-                        sRedA[q][cb + lane] = cs_colreduce<1>(v, lane);
-                        sRedB[q][cb + lane] = cs_colreduce<2>(w, lane);
+                        const float mx = cs_colreduce16<1>(v, lane);
+                        const float mn = cs_colreduce16<2>(w, lane);
+                        if (!(lane & 1)) { sRedA[q][cb + (lane >> 1)] = mx; sRedB[q][cb + (lane >> 1)] = mn; }
                     }
                     cs_named_sync(1, kCsProducers);
                     if (tid < N) {
-                        P.tile_max[(size_t)tile_of[s] * N + tid] = fmaxf(fmaxf(sRedA[0][tid], sRedA[1][tid]), fmaxf(sRedA[2][tid], sRedA[3][tid]));
-                        P.tile_min[(size_t)tile_of[s] * N + tid] = fminf(fminf(sRedB[0][tid], sRedB[1][tid]), fminf(sRedB[2][tid], sRedB[3][tid]));
+                        const int tile = (s == 0) ? tile_of[0] : tile_of[1];
+                        P.tile_max[(size_t)tile * N + tid] = fmaxf(fmaxf(sRedA[0][tid], sRedA[1][tid]), fmaxf(sRedA[2][tid], sRedA[3][tid]));
+                        P.tile_min[(size_t)tile * N + tid] = fminf(fminf(sRedB[0][tid], sRedB[1][tid]), fminf(sRedB[2][tid], sRedB[3][tid]));
                     }
                     cs_named_sync(1, kCsProducers);
                 }
@@ -579,7 +611,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // every commit has been observed through bar_acc; release tensor memory
     cs_fence_before();
     __syncthreads();
-    if (warp == 8) cs_tmem_dealloc(tmem0, 512);
+    if (warp == 16) cs_tmem_dealloc(tmem0, 512);
 }
 
 int debug_conv_stack_timestamps(long long *host_out64)
