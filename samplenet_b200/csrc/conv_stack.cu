@@ -30,7 +30,8 @@ constexpr int kCsM = 128;
 constexpr int kCsMaxLayers = SNB200_MAX_CONV_LAYERS;
 constexpr int kCsSlots = 2;           // tiles per CTA
 constexpr int kCsRegion = 128;        // TMEM columns per (slot, parity) region
-constexpr int kCsProducers = 512;     // 16 producer warps: TMEM lane quarter = warp & 3, column group = (warp >> 2) & 3
+constexpr int kCsProducers = 512;     // 16 producer warps = 2 groups of 8; group (warp >> 3) prepares the K chunks of its parity
+constexpr int kCsGroup = 256;
 constexpr int kCsThreadsAll = kCsProducers + 32;
 
 struct CsLayer {
@@ -168,8 +169,8 @@ __device__ __forceinline__ void cs_mbar_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void cs_grid_arrive(unsigned *counter)
 {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release is cumulative over everything ordered before it by the preceding CTA barrier (the other threads' statistics atomics)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
 }
 __device__ __forceinline__ void cs_grid_wait(unsigned *counter, unsigned target)
 {
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool producer = warp < 16;
-    const int q = warp & 3, hsel = (warp >> 2) & 3;     // TMEM lane quarter, column group (producers)
+    const int q = warp & 3, hsel = (warp >> 2) & 3;     // TMEM lane quarter, column group (epilogue: 4 groups of 16 columns)
+    const int grp = (warp >> 3) & 1, hs2 = (warp >> 2) & 1; // main loop: producer group, column half inside the chunk
     const int row = q * 32 + lane;                      // the point row this producer thread owns in every tile
     const int G = gridDim.x;
     int tile_of[kCsSlots], np_of[kCsSlots];
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     CS_TS(0);
     if (warp == 16) cs_tmem_alloc(&tmem_base_smem, 512);
     if (tid == 0) {
-        mbar_init(&bar_full[0], kCsProducers); mbar_init(&bar_full[1], kCsProducers);
+        mbar_init(&bar_full[0], kCsGroup); mbar_init(&bar_full[1], kCsGroup);
         mbar_init(&bar_ring[0], 1); mbar_init(&bar_ring[1], 1);
         mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
         fence_mbar_init();
@@ -476,38 +478,32 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             // ---- operand preparation: chunk g+1 is prepared while the tensor core works on chunk g; inside a thread the
             //      tensor-memory load of the NEXT chunk is in flight while the current chunk is normalised, split and stored
             {
+                // Producer group `grp` prepares the chunks whose global index has its parity (= ring buffer grp): while one group
+                // is inside its fence / arrive latency chain the other one is already normalising the next chunk.
                 const int total_chunks = nslots * nchunks;
-                uint32_t rnext[8];
-                if (l >= 2 && total_chunks > 0)
-                    cs_ld8_issue(tmem0 + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * 8), rnext);
-                int s = 0, kc = 0;
-                for (int ci = 0; ci < total_chunks; ci++, g++) {
+                const uint32_t g0 = g;
+                for (int ci = 0; ci < total_chunks; ci++) {
+                    const uint32_t gg = g0 + (uint32_t)ci;
+                    if ((int)(gg & 1) != grp) continue;
+                    const int s = ci / nchunks, kc = ci - s * nchunks;
                     const int np = (s == 0) ? np_of[0] : np_of[1];
-                    const int rb = g & 1;
-                    const int kb = kc * 32 + hsel * 8;
-                    float v[8];
+                    const int kb = kc * 32 + hs2 * 16;
+                    float v[16];
                     if (l == 1) {
                         const float *xr = (s == 0 ? sX[0] : sX[1]) + row * 3;
                         const float px = xr[0], py = xr[1], pz = xr[2];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
+                        for (int j = 0; j < 16; j++) {
                             const int c = kb + j;
                             v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
                         }
                     } else {
-                        cs_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; j++) v[j] = __uint_as_float(rnext[j]);
+                        cs_ld16(tmem0 + (uint32_t)(s * 2 * kCsRegion) + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)kb, v);
                     }
-                    // advance (slot, chunk) and put the next chunk's raw activations in flight
-                    int s2 = s, kc2 = kc + 1;
-                    if (kc2 == nchunks) { kc2 = 0; s2 = s + 1; }
-                    if (l >= 2 && ci + 1 < total_chunks)
-                        cs_ld8_issue(tmem0 + (uint32_t)(s2 * 2 * kCsRegion) + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)(kc2 * 32 + hsel * 8), rnext);
                     const bool pv = row < np;
-                    float4 tq[2];
+                    float4 tq[4];
 #pragma unroll
-                    for (int c4 = 0; c4 < 2; c4++) {
+                    for (int c4 = 0; c4 < 4; c4++) {
                         const float4 sc = *reinterpret_cast<const float4 *>(sScale + kb + c4 * 4);
                         const float4 sh = *reinterpret_cast<const float4 *>(sShift + kb + c4 * 4);
                         float4 t;
@@ -517,17 +513,17 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         if (!pv) t = make_float4(0.f, 0.f, 0.f, 0.f);
                         tq[c4] = t;
                     }
-                    if (g >= 2) {   // the MMAs of chunk g-2 (same ring buffer) must have completed before its operands are overwritten
-                        cs_mbar_wait(&bar_ring[rb], ((g >> 1) - 1) & 1);
+                    if (gg >= 2) {   // the MMAs of chunk gg-2 (same ring buffer) must have completed before its operands are overwritten
+                        cs_mbar_wait(&bar_ring[grp], ((gg >> 1) - 1) & 1);
                         cs_fence_after();
                     }
 #pragma unroll
-                    for (int c4 = 0; c4 < 2; c4++) cs_split_store(sA[rb][0], sA[rb][1], cs_sw128(row, hsel * 2 + c4), tq[c4]);
+                    for (int c4 = 0; c4 < 4; c4++) cs_split_store(sA[grp][0], sA[grp][1], cs_sw128(row, hs2 * 4 + c4), tq[c4]);
                     cs_fence_before();
                     fence_proxy_async();
-                    cs_mbar_arrive(&bar_full[rb]);
-                    s = s2; kc = kc2;
+                    cs_mbar_arrive(&bar_full[grp]);
                 }
+                g = g0 + (uint32_t)total_chunks;
             }
             CS_TS(3 + (l - 1) * 8 + 3);
 
