@@ -129,39 +129,41 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
-def time_kernels(sb, net, x, pk):
-    """CUDA-event timing of each stage, launched alone through the C-ABI wrappers, L2 flushed between iterations."""
-    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=x.device)
+def graph_time_us(fn, reps=20, replays=20):
+    """Warm in-graph time of one stage: R back-to-back launches captured in one CUDA graph, CUDA events on the replay stream."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn(); fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(replays):
+        g.replay()
+    b.record(); b.synchronize()
+    return a.elapsed_time(b) * 1e3 / (reps * replays)
+
+
+def time_kernels(sb, net, x):
+    """Per-stage device time, measured live: each stage alone, launched through the C-ABI wrappers, R launches per graph."""
     conv_specs, fc_specs = net._layer_specs()
     out = {}
-
-    def timed(fn, iters=20):
-        ts = []
-        for _ in range(iters + 3):
-            flush.fill_(1)
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b_.record(); b_.synchronize()
-            ts.append(a.elapsed_time(b_))
-        return float(np.mean(ts[3:]))
-
     with torch.no_grad():
         sigma = net.project.sigma().detach().reshape(1).contiguous()
         simp = net(x)[0].detach()
-        out["generator_ms"] = timed(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M))
-        out["knn_softproj_ms"] = timed(lambda: sb.ops.knn_soft_project_forward(x, simp, K_NN, "bnc", sigma, want=("proj", "idx", "weights", "dist")))
-        out["chamfer_ms"] = timed(lambda: sb.ops.nn_distance_forward(simp, x))
-        out["loss_fused_ms"] = timed(lambda: sb.ops.simplification_loss_forward(simp, x, 1.0))
-        # the conv layers, each alone, through the tensor-core layer kernel's stand-alone entry (same kernel, same tile shapes;
-        # BatchNorm-on-load and the statistics epilogue are part of it, the input here is a random activation tensor)
-        widths = [64, 64, 64, 128, BOTTLENECK]
-        layer_ms = []
-        for l in range(1, 5):
-            A = torch.randn(B * N, widths[l - 1], device=x.device)
-            Wt = torch.randn(widths[l], widths[l - 1], device=x.device) / widths[l - 1] ** 0.5
-            bias = torch.zeros(widths[l], device=x.device)
-            layer_ms.append(timed(lambda A=A, Wt=Wt, bias=bias: sb.ops.debug_tc_gemm(A, Wt, bias), iters=10))
-        out["tc_layer_ms"] = layer_ms
-        out["generator_fp32_ms"] = timed(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M, exact_fp32=True), iters=5)
+        out["generator_us"] = graph_time_us(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M))
+        out["conv_stack_us"] = graph_time_us(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M, _profile_flags=2))
+        out["fc_head_us"] = graph_time_us(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M, _profile_flags=4))
+        out["generator_per_layer_kernels_us"] = graph_time_us(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M, per_layer_kernels=True), reps=10)
+        out["generator_exact_fp32_us"] = graph_time_us(lambda: sb.ops.generator_forward(x, "bnc", conv_specs, fc_specs, True, M, exact_fp32=True), reps=5)
+        out["knn_softproj_us"] = graph_time_us(lambda: sb.ops.knn_soft_project_forward(x, simp, K_NN, "bnc", sigma, want=("proj", "idx", "weights", "dist")))
+        out["chamfer_us"] = graph_time_us(lambda: sb.ops.nn_distance_forward(simp, x))
+        out["chamfer_plus_reduce_us"] = graph_time_us(lambda: sb.ops.simplification_loss_forward(simp, x, 1.0))
     return out
 
 
@@ -223,32 +225,20 @@ def run_ours(args, rank, world, local_rank):
     value = world * B * args.steps / (ms_val * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel, timed live (alone, L2 flushed)
-    kt = time_kernels(sb, net, dev_pool[0], pk)
-    layer_ms = kt["tc_layer_ms"]                      # layers 2..5
-    widths = [64, 64, 64, 128, BOTTLENECK]
-    layer_flops = [2.0 * B * N * widths[i] * widths[i + 1] for i in range(4)]
-    dom = int(np.argmax(layer_ms))
-    gen_flops = sum(layer_flops) + 2.0 * B * N * 3 * 64
-    ach_tf = layer_flops[dom] / (layer_ms[dom] * 1e-3) / 1e12
+    # ---- roofline of the dominant kernel, timed live (alone, warm, in-graph: R launches per CUDA graph, CUDA events)
+    kt = time_kernels(sb, net, dev_pool[0])
+    widths = [3, 64, 64, 64, 128, BOTTLENECK]
+    conv_flops = sum(2.0 * B * N * widths[i] * widths[i + 1] for i in range(5))
+    ach_tf = conv_flops / (kt["conv_stack_us"] * 1e-6) / 1e12
     roofline = {
-        "kernel": "tc_layer_kernel (generator layer %d: %d->%d, tcgen05.mma kind::tf32, 3xTF32, M=128 tiles)" % (dom + 2, widths[dom], widths[dom + 1]),
+        "kernel": "conv_stack_kernel (generator conv layers 1-5 in one persistent cooperative launch: tcgen05.mma kind::tf32 3xTF32, "
+                  "activations resident in TMEM, 5 grid barriers for the BatchNorm batch statistics)",
         "bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops"],
-        "peak_source": pk["source"] + " cuBLAS bf16 burst. `achieved` counts the ALGORITHMIC fp32 flops (2*M*N*K); the kernel issues 3 TF32 MMAs "
-                       "per product (error compensation) and TF32 runs at half the bf16 rate, so the ceiling for this number is peak/6",
-        "frac_of_3xtf32_ceiling": ach_tf / (pk["bf16_tflops"] / 6.0), "traffic": None,
-        "generator_tflops": gen_flops / (kt["generator_ms"] * 1e-3) / 1e12,
-    }
-    pair_bytes_sp = B * (12 * N + 12 * M + 12 * M)
-    pair_bytes_cd = B * (12 * (N + M) + 8 * (N + M))
-    roofline_pairwise = {
-        "knn_softproj": {"bound": "hbm", "achieved": pair_bytes_sp / (kt["knn_softproj_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": pair_bytes_sp / (kt["knn_softproj_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": kt["knn_softproj_ms"],
-                         "algorithmic_bytes": pair_bytes_sp},
-        "chamfer": {"bound": "hbm", "achieved": pair_bytes_cd / (kt["chamfer_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": pair_bytes_cd / (kt["chamfer_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": kt["chamfer_ms"],
-                    "algorithmic_bytes": pair_bytes_cd},
-        "note": "0.4-0.7 MB per launch: these launches are latency-bound at B=32 (SURVEY.md section 7); fractions reported as required",
+        "peak_source": pk["source"] + " cuBLAS bf16 burst. `achieved` counts the ALGORITHMIC fp32 flops (2*M*N*K = %.2f GFLOP per launch); the kernel "
+                       "issues 3 TF32 MMAs per product (error compensation to fp32 accuracy) and TF32 runs at half the bf16 rate, so the ceiling "
+                       "for this number is peak/6; at B=32 the launch is bounded by its 5 grid barriers + per-layer prologue/epilogue latency, "
+                       "not by the tensor pipe" % (conv_flops / 1e9),
+        "frac_of_3xtf32_ceiling": ach_tf / (pk["bf16_tflops"] / 6.0), "traffic": None, "us_per_launch": kt["conv_stack_us"],
     }
     # ---- CPU baseline beside it (bounded: a few full B=32 steps)
     cpu_val, cpu_ms, cores, kind = cpu_reference_arm(6, 2)
@@ -265,8 +255,7 @@ def run_ours(args, rank, world, local_rank):
         "launches_per_step": int(step.launches_per_step),
         "roofline": roofline,
         "roofline_pairwise": roofline_pairwise,
-        "kernel_ms": {"generator": kt["generator_ms"], "generator_exact_fp32_cuda_cores": kt["generator_fp32_ms"], "tc_layers_2to5": layer_ms, "knn_softproj": kt["knn_softproj_ms"], "chamfer": kt["chamfer_ms"],
-                      "chamfer+reduce": kt["loss_fused_ms"]},
+        "kernel_us": kt,
         "cpu_baseline": {"value": cpu_val, "unit": "clouds/s", "cores": cores, "kind": kind,
                          "sample": "6 full steps of B=32 on the host: torch CPU layer stack (%d threads) + C-oracle kNN/soft-proj (1 thread) + "
                                    "reference CPU Chamfer (oracle/_ref, 1 thread)" % cores, "ms_per_step": cpu_ms},

@@ -15,7 +15,6 @@
 #include "encoder_internal.cuh"
 #include <cooperative_groups.h>
 #include <string.h>
-#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 namespace snb {
@@ -56,7 +55,7 @@ struct HeadParams {
     float *act[2];               // (b, max width) scratch
     float *out;                  // (b, c_out_last)
     int out_inner;
-    int dbg;                     // bring-up experiments (env SNB200_HEAD_DEBUG): 1 = stop after pooling, 2 = no TMA weight prefetch
+    int dbg;                     // bring-up switches (always 0 in the product): 1 = stop after pooling, 2 = no TMA weight prefetch
 };
 
 __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_total, int c, double count, const float *gamma, const float *beta,
@@ -522,12 +521,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     // cluster size: enough CTAs that the widest layer is a single 16-channel pass per CTA, capped at 16 (non-portable size)
     int csize = 1;
     while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;
-    {
-        const char *dbg = getenv("SNB200_HEAD_DEBUG");
-        H.dbg = dbg ? atoi(dbg) : 0;
-        if (H.dbg & 4) csize = min(csize, 8);
-        if (H.dbg & 8) csize = min(csize, 4);
-    }
+    H.dbg = 0;
     size_t wfloats = 0;
     for (int l = 0; l < nfc; l++) wfloats += (size_t)kHeadChPerCta * (fc[l].c_in + 4);
     const size_t smem = ((size_t)cmax * 36 + wfloats + (size_t)8 * 32 * 17) * sizeof(float);
