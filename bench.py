@@ -240,6 +240,17 @@ def run_ours(args, rank, world, local_rank):
                        "not by the tensor pipe" % (conv_flops / 1e9),
         "frac_of_3xtf32_ceiling": ach_tf / (pk["bf16_tflops"] / 6.0), "traffic": None, "us_per_launch": kt["conv_stack_us"],
     }
+    pair_bytes_sp = B * (12 * N + 12 * M + 12 * M)
+    pair_bytes_cd = B * (12 * (N + M) + 8 * (N + M))
+    roofline_pairwise = {
+        "knn_softproj": {"bound": "hbm", "achieved": pair_bytes_sp / (kt["knn_softproj_us"] * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": pair_bytes_sp / (kt["knn_softproj_us"] * 1e-6) / 1e9 / pk["hbm_gbs"], "us": kt["knn_softproj_us"],
+                         "algorithmic_bytes": pair_bytes_sp},
+        "chamfer": {"bound": "hbm", "achieved": pair_bytes_cd / (kt["chamfer_us"] * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": pair_bytes_cd / (kt["chamfer_us"] * 1e-6) / 1e9 / pk["hbm_gbs"], "us": kt["chamfer_us"],
+                    "algorithmic_bytes": pair_bytes_cd},
+        "note": "0.4-0.7 MB per launch: these launches are latency-bound at B=32 (SURVEY.md section 7); fractions reported as required",
+    }
     # ---- CPU baseline beside it (bounded: a few full B=32 steps)
     cpu_val, cpu_ms, cores, kind = cpu_reference_arm(6, 2)
     line = {
