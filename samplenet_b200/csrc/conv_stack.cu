@@ -53,6 +53,8 @@ struct CsParams {
     double *mom;                        // [9] input moments (zeroed by the caller)
     unsigned *barrier;                  // grid barrier counter (zeroed by the caller)
     float *tile_max, *tile_min;         // (tiles, c_last)
+    int fuse_head;                      // run the pool + FC head as the tail of this launch
+    HeadParams H;
 };
 
 // ---- tcgen05 helpers (same encodings as encoder_tc.cu, validated against fp64 in tests/test_gpu_parity.py::test_tc_gemm_3xtf32)
@@ -608,6 +610,207 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     cs_fence_before();
     __syncthreads();
     if (warp == 16) cs_tmem_dealloc(tmem0, 512);
+
+    // ================================================================================================================
+    // Fused tail: max-pool finalise + FC head (samplenet.py:97-104) on ALL CTAs of the grid.  Each FC layer's output
+    // channels are spread over the CTAs (BatchNorm over the batch stays inside one warp: lane = batch row), activations go
+    // through a few-KB global scratch that lives in L2, and the layers are separated by the same grid barrier.  Versus the
+    // 16-CTA cluster kernel this removes a launch and spreads each layer's latency chain over 9x more SMs.
+    // ================================================================================================================
+    if (!P.fuse_head) return;
+    const HeadParams &H = P.H;
+    float *s_in = reinterpret_cast<float *>(smem_raw);                 // [c_in][33] one 32-row group of the input, transposed
+    float *s_part = reinterpret_cast<float *>(smem_raw) + 256 * 33;    // [16 warps][2 channels][32 rows]
+    const double inv_cnt_h = 1.0 / H.count;
+    // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
+    // no grid barrier has been crossed yet.
+    if (!(need_stats && P.L[P.num_layers - 1].has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);
+    // ---- phase P: pooled feature, spread over the grid; running statistics of the conv stack, spread over the grid
+    {
+        const int total = H.b * H.c_feat;
+        const int gt = blockIdx.x * kCsThreadsAll + tid, gn = G * kCsThreadsAll;
+        for (int e = gt; e < total; e += gn) {
+            const int bi = e / H.c_feat, c = e % H.c_feat;
+            float mx = -INFINITY, mn = INFINITY;
+            const float *tm = H.tile_max + (size_t)bi * H.tiles_per_cloud * H.c_feat + c;
+            const float *tn = H.tile_min + (size_t)bi * H.tiles_per_cloud * H.c_feat + c;
+#pragma unroll 8
+            for (int t = 0; t < H.tiles_per_cloud; t++) {
+                mx = fmaxf(mx, __ldcg(tm + (size_t)t * H.c_feat));
+                mn = fminf(mn, __ldcg(tn + (size_t)t * H.c_feat));
+            }
+            float v = mx;
+            if (H.last_has_bn) {
+                float mean, var;
+                if (H.training) {
+                    const double m = __ldcg(H.last_stats + c) * inv_cnt_h;
+                    double vv = __ldcg(H.last_stats + H.c_feat + c) * inv_cnt_h - m * m;
+                    if (vv < 0) vv = 0;
+                    mean = (float)m; var = (float)vv;
+                } else {
+                    mean = H.last_run_mean[c]; var = H.last_run_var[c];
+                }
+                const float sc = H.last_gamma[c] * (1.0f / sqrtf(var + H.last_eps));
+                const float sh = H.last_beta[c] - mean * sc;
+                v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);
+            }
+            if (H.last_relu) v = fmaxf(v, 0.f);
+            H.feat[e] = v;
+        }
+        if (H.training) {
+            int base = 0;
+            for (int l = 0; l < H.ru_num; l++) {
+                for (int c = gt - base; c < H.ru_c[l]; c += gn) {
+                    if (c < 0) continue;
+                    const double m = __ldcg(H.ru_stats[l] + c) * inv_cnt_h;
+                    double v = __ldcg(H.ru_stats[l] + H.ru_c[l] + c) * inv_cnt_h - m * m;
+                    if (v < 0) v = 0;
+                    const double unb = H.count > 1 ? v * (H.count / (H.count - 1)) : v;
+                    const float mom = H.ru_momentum[l];
+                    if (H.ru_mean[l]) H.ru_mean[l][c] = (1.f - mom) * H.ru_mean[l][c] + mom * (float)m;
+                    if (H.ru_var[l]) H.ru_var[l][c] = (1.f - mom) * H.ru_var[l][c] + mom * (float)unb;
+                }
+                base = (base + H.ru_c[l]) % gn;
+            }
+        }
+    }
+    cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the pooled feature of every cloud is in place
+
+    const float *cur = H.feat;
+    for (int l = 0; l < H.num_fc; l++) {
+        const HeadLayer &L = H.fc[l];
+        const bool lastfc = (l == H.num_fc - 1);
+        float *dst = lastfc ? H.out : H.act[l & 1];
+        const int c_in = L.c_in;
+        const int cpc = ((L.c_out + G - 1) / G + 1) & ~1;             // channels per CTA, even (pairs)
+        const int c_lo = blockIdx.x * cpc, c_hi = min(L.c_out, c_lo + cpc);
+        const int nrg = (H.b + 31) >> 5;
+        for (int cb = c_lo; cb < c_hi; cb += 2) {                     // one channel pair at a time
+            const int c0 = cb, c1 = cb + 1;
+            const bool has1 = c1 < c_hi;
+            float y0[8], y1[8];                                       // finished pre-activations, row group g -> lane = row (warps 0 / 1)
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) { y0[gq] = 0.f; y1[gq] = 0.f; }
+            // this warp's K slice of the two weight rows (uniform addresses: one request per warp)
+            const int kr = ((c_in + 63) / 64) * 4;                    // K per warp (16 warps), multiple of 4
+            const int k_lo = min(c_in, warp * kr), k_hi = min(c_in, k_lo + kr);
+            float w0r[16], w1r[16];                                    // register copy when the slice is <= 16 wide (c_in <= 256)
+            const bool wreg = kr <= 16;
+            if (wreg && producer) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int k = k_lo + j;
+                    w0r[j] = (k < k_hi) ? __ldg(L.weight + (size_t)c0 * c_in + k) : 0.f;
+                    w1r[j] = (k < k_hi && has1) ? __ldg(L.weight + (size_t)c1 * c_in + k) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) {
+                if (gq < nrg) {
+                    const int r0 = gq * 32, rn = min(32, H.b - r0);
+                    __syncthreads();
+                    if (producer) {   // stage rows r0..r0+rn-1 transposed: lane = row, warps stride over 16-byte k groups
+                        const int q4 = c_in >> 2;
+                        const float *src = cur + (size_t)(r0 + min(lane, rn - 1)) * c_in;
+                        if ((c_in & 3) == 0) {
+                            for (int kq0 = warp; kq0 < q4; kq0 += 16 * 4) {
+                                float4 v[4];
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const int kq = kq0 + 16 * u;
+                                    v[u] = (kq < q4) ? __ldcg(reinterpret_cast<const float4 *>(src) + kq) : make_float4(0, 0, 0, 0);
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const int kq = kq0 + 16 * u;
+                                    if (kq < q4) {
+                                        const float4 t = (lane < rn) ? v[u] : make_float4(0, 0, 0, 0);
+                                        s_in[(kq * 4 + 0) * 33 + lane] = t.x; s_in[(kq * 4 + 1) * 33 + lane] = t.y;
+                                        s_in[(kq * 4 + 2) * 33 + lane] = t.z; s_in[(kq * 4 + 3) * 33 + lane] = t.w;
+                                    }
+                                }
+                            }
+                        } else {
+                            for (int k = warp; k < c_in; k += 16) s_in[k * 33 + lane] = (lane < rn) ? __ldcg(src + k) : 0.f;
+                        }
+                    }
+                    __syncthreads();
+                    if (producer) {
+                        float a0 = 0.f, a1 = 0.f;
+                        if (wreg) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const float a = (k_lo + j < k_hi) ? s_in[(k_lo + j) * 33 + lane] : 0.f;
+                                a0 = fmaf(a, w0r[j], a0);
+                                a1 = fmaf(a, w1r[j], a1);
+                            }
+                        } else {
+                            for (int k = k_lo; k < k_hi; k++) {
+                                const float a = s_in[k * 33 + lane];
+                                a0 = fmaf(a, __ldg(L.weight + (size_t)c0 * c_in + k), a0);
+                                if (has1) a1 = fmaf(a, __ldg(L.weight + (size_t)c1 * c_in + k), a1);
+                            }
+                        }
+                        s_part[(warp * 2 + 0) * 32 + lane] = a0;
+                        s_part[(warp * 2 + 1) * 32 + lane] = a1;
+                    }
+                    __syncthreads();
+                    if (warp < 2) {   // fixed-order combination of the 16 K slices: warp 0 -> channel c0, warp 1 -> channel c1
+                        float t = 0.f;
+#pragma unroll
+                        for (int w16 = 0; w16 < 16; w16++) t += s_part[(w16 * 2 + warp) * 32 + lane];
+                        if (warp == 0) y0[gq] = t; else y1[gq] = t;
+                    }
+                }
+            }
+            if (warp < 2 && (warp == 0 || has1)) {
+                const int c = (warp == 0) ? c0 : c1;
+                float *y = (warp == 0) ? y0 : y1;
+                const float bias = L.bias ? __ldg(L.bias + c) : 0.f;
+                float scale = 1.f, shift = 0.f;
+#pragma unroll
+                for (int gq = 0; gq < 8; gq++) y[gq] += bias;
+                if (L.has_bn) {
+                    float mean, var;
+                    if (H.training) {
+                        float sm = 0.f;
+#pragma unroll
+                        for (int gq = 0; gq < 8; gq++)
+                            if (gq * 32 + lane < H.b) sm += y[gq];
+                        mean = warp_sum(sm) / (float)H.b;
+                        float qq = 0.f;
+#pragma unroll
+                        for (int gq = 0; gq < 8; gq++)
+                            if (gq * 32 + lane < H.b) { const float d = y[gq] - mean; qq = fmaf(d, d, qq); }
+                        qq = warp_sum(qq);
+                        var = qq / (float)H.b;
+                        if (lane == 0) {
+                            const float unb = H.b > 1 ? qq / (float)(H.b - 1) : var;
+                            if (L.run_mean) L.run_mean[c] = (1.f - L.momentum) * L.run_mean[c] + L.momentum * mean;
+                            if (L.run_var) L.run_var[c] = (1.f - L.momentum) * L.run_var[c] + L.momentum * unb;
+                        }
+                    } else {
+                        mean = L.run_mean[c]; var = L.run_var[c];
+                    }
+                    const float invstd = 1.0f / sqrtf(var + L.eps);
+                    scale = __ldg(L.gamma + c) * invstd;
+                    shift = __ldg(L.beta + c) - mean * scale;
+                }
+#pragma unroll
+                for (int gq = 0; gq < 8; gq++) {
+                    const int r = gq * 32 + lane;
+                    if (r < H.b) {
+                        float v = L.has_bn ? fmaf(y[gq], scale, shift) : y[gq];
+                        if (L.relu) v = fmaxf(v, 0.f);
+                        const int oc = (lastfc && H.out_inner > 0) ? (c % H.out_inner) * (L.c_out / H.out_inner) + c / H.out_inner : c;
+                        dst[(size_t)r * L.c_out + oc] = v;
+                    }
+                }
+            }
+        }
+        cur = dst;
+        if (!lastfc) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the next layer reads every CTA's channels
+    }
 }
 
 int debug_conv_stack_timestamps(long long *host_out64)
@@ -632,10 +835,12 @@ bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
 }
 
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
-                      double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream)
+                      double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, const HeadParams *head,
+                      cudaStream_t stream)
 {
     CsParams P;
     memset(&P, 0, sizeof(P));
+    if (head) { P.fuse_head = 1; P.H = *head; }
     P.x = x; P.layout = layout; P.b = b; P.n = n;
     P.tiles_per_cloud = (n + kCsM - 1) / kCsM;
     P.tiles = b * P.tiles_per_cloud;

@@ -36,9 +36,46 @@ int launch_x_moments(int b, int n, int layout, const float *x, double *mom, unsi
 int launch_simt_conv_stack(int b, int n, int layout, const float *x, int num_layers, const snb200_layer *layers, int training, float *act0,
                            float *act1, double *const *stats, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream);
 
-// persistent cooperative conv-stack kernel (conv_stack.cu)
+// pool + FC head description (generator.cu builds it; the cluster kernel and the fused tail of the conv-stack kernel consume it)
+struct HeadLayer {
+    int c_in, c_out;
+    const float *weight, *bias, *gamma, *beta;
+    float *run_mean, *run_var;
+    float eps, momentum;
+    int has_bn, relu;
+};
+
+struct HeadParams {
+    int b, training;
+    // pooling of the last conv layer
+    int c_feat, tiles_per_cloud;
+    const float *tile_max, *tile_min;
+    const double *last_stats;
+    const float *last_gamma, *last_beta, *last_run_mean, *last_run_var;
+    float last_eps;
+    int last_has_bn, last_relu;
+    double count;
+    float *feat;                 // (b, c_feat) global: pooled feature (also an API output)
+    // running-statistics updates of the conv layers
+    int ru_num;
+    const double *ru_stats[SNB200_MAX_CONV_LAYERS];
+    float *ru_mean[SNB200_MAX_CONV_LAYERS];
+    float *ru_var[SNB200_MAX_CONV_LAYERS];
+    float ru_momentum[SNB200_MAX_CONV_LAYERS];
+    int ru_c[SNB200_MAX_CONV_LAYERS];
+    // FC layers
+    int num_fc;
+    HeadLayer fc[SNB200_MAX_FC_LAYERS];
+    float *act[2];               // (b, max width) scratch
+    float *out;                  // (b, c_out_last)
+    int out_inner;
+    int dbg;                     // bring-up switches (always 0 in the product): 1 = stop after pooling, 2 = no TMA weight prefetch
+};
+
+// persistent cooperative conv-stack kernel (conv_stack.cu); head != nullptr fuses the pool + FC head into the same launch
 bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv);
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
-                      double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, cudaStream_t stream);
+                      double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, const HeadParams *head,
+                      cudaStream_t stream);
 
 }  // namespace snb

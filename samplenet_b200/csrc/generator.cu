@@ -23,41 +23,6 @@ constexpr int kHeadThreads = 256;      // 8 warps = 8 K slices; lanes = 8 row qu
 constexpr int kHeadChPerCta = 16;
 constexpr int kHeadMaxCluster = 16;
 
-struct HeadLayer {
-    int c_in, c_out;
-    const float *weight, *bias, *gamma, *beta;
-    float *run_mean, *run_var;
-    float eps, momentum;
-    int has_bn, relu;
-};
-
-struct HeadParams {
-    int b, training;
-    // pooling of the last conv layer
-    int c_feat, tiles_per_cloud;
-    const float *tile_max, *tile_min;
-    const double *last_stats;
-    const float *last_gamma, *last_beta, *last_run_mean, *last_run_var;
-    float last_eps;
-    int last_has_bn, last_relu;
-    double count;
-    float *feat;                 // (b, c_feat) global: pooled feature (also an API output)
-    // running-statistics updates of the conv layers
-    int ru_num;
-    const double *ru_stats[SNB200_MAX_CONV_LAYERS];
-    float *ru_mean[SNB200_MAX_CONV_LAYERS];
-    float *ru_var[SNB200_MAX_CONV_LAYERS];
-    float ru_momentum[SNB200_MAX_CONV_LAYERS];
-    int ru_c[SNB200_MAX_CONV_LAYERS];
-    // FC layers
-    int num_fc;
-    HeadLayer fc[SNB200_MAX_FC_LAYERS];
-    float *act[2];               // (b, max width) scratch
-    float *out;                  // (b, c_out_last)
-    int out_inner;
-    int dbg;                     // bring-up switches (always 0 in the product): 1 = stop after pooling, 2 = no TMA weight prefetch
-};
-
 __device__ __forceinline__ void head_bn_scale_shift(const double *stats, int c_total, int c, double count, const float *gamma, const float *beta,
                                                     const float *run_mean, const float *run_var, float eps, int training, float &scale, float &shift)
 {
@@ -436,6 +401,36 @@ size_t generator_workspace_bytes(int b, int n, int nconv, const snb200_layer *co
     return carve_gen_ws(nullptr, b, n, nconv, conv, nfc, fc).total;
 }
 
+static void fill_head_params(HeadParams &H, int b, int n, int tpc, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc, int training,
+                             float *out, int out_transpose_inner, float *feat_out, const GenWorkspace &W)
+{
+    memset(&H, 0, sizeof(H));
+    const snb200_layer &LL = conv[nconv - 1];
+    H.b = b; H.training = training; H.c_feat = LL.c_out; H.tiles_per_cloud = tpc;
+    H.tile_max = W.tile_max; H.tile_min = W.tile_min; H.last_stats = W.stats[nconv - 1];
+    H.last_gamma = LL.bn_weight; H.last_beta = LL.bn_bias; H.last_run_mean = LL.bn_running_mean; H.last_run_var = LL.bn_running_var;
+    H.last_eps = LL.bn_eps; H.last_has_bn = LL.bn_weight != nullptr; H.last_relu = LL.relu;
+    H.count = (double)b * (double)n;
+    H.feat = feat_out ? feat_out : W.feat;
+    if (training)
+        for (int l = 0; l < nconv; l++) {
+            if (!conv[l].bn_weight || (!conv[l].bn_running_mean && !conv[l].bn_running_var)) continue;
+            const int i = H.ru_num++;
+            H.ru_stats[i] = W.stats[l]; H.ru_mean[i] = conv[l].bn_running_mean; H.ru_var[i] = conv[l].bn_running_var;
+            H.ru_momentum[i] = conv[l].bn_momentum; H.ru_c[i] = conv[l].c_out;
+        }
+    H.num_fc = nfc;
+    for (int l = 0; l < nfc; l++) {
+        HeadLayer &D = H.fc[l];
+        D.c_in = fc[l].c_in; D.c_out = fc[l].c_out; D.weight = fc[l].weight; D.bias = fc[l].bias; D.gamma = fc[l].bn_weight; D.beta = fc[l].bn_bias;
+        D.run_mean = fc[l].bn_running_mean; D.run_var = fc[l].bn_running_var; D.eps = fc[l].bn_eps; D.momentum = fc[l].bn_momentum;
+        D.has_bn = fc[l].bn_weight != nullptr; D.relu = fc[l].relu;
+    }
+    H.act[0] = W.head_act[0]; H.act[1] = W.head_act[1];
+    H.out = out; H.out_inner = out_transpose_inner;
+    H.dbg = 0;
+}
+
 static bool tc_stack_supported(int nconv, const snb200_layer *conv)
 {
     if (nconv < 2 || conv[0].c_in != 3) return false;
@@ -449,14 +444,22 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
                              int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream)
 {
     GenWorkspace W = carve_gen_ws(workspace, b, n, nconv, conv, nfc, fc);
-    if (training) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);
+    const bool coop = !(flags & (SNB200_GEN_EXACT_FP32 | SNB200_GEN_PER_LAYER_KERNELS | SNB200_GEN_PROFILE_SKIP_CONV)) && tc_stack_supported(nconv, conv) &&
+                      conv_stack_supported(b, n, nconv, conv);
+    if (training || coop) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);   // statistics, moments, grid-barrier counter
     const bool use_tc = !(flags & SNB200_GEN_EXACT_FP32) && tc_stack_supported(nconv, conv);
     int tpc = 0;
     if (flags & SNB200_GEN_PROFILE_SKIP_CONV) {
         tpc = use_tc ? tc_tiles_per_cloud(n) : (n + (conv[nconv - 1].c_out > 64 ? 128 : 256) - 1) / (conv[nconv - 1].c_out > 64 ? 128 : 256);
     } else if (use_tc && !(flags & SNB200_GEN_PER_LAYER_KERNELS) && conv_stack_supported(b, n, nconv, conv)) {
-        int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc, stream);
+        // one persistent cooperative launch for the conv stack AND (unless profiling flags split them) the pool + FC head
+        HeadParams H;
+        const bool fuse_head = !(flags & (SNB200_GEN_PROFILE_SKIP_HEAD | SNB200_GEN_SEPARATE_HEAD)) && b <= 256;
+        if (fuse_head) fill_head_params(H, b, n, (n + 127) / 128, nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
+        int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc,
+                                   fuse_head ? &H : nullptr, stream);
         if (rc) return rc;
+        if (fuse_head) return SNB200_OK;
     } else if (use_tc) {
         tpc = tc_tiles_per_cloud(n);
         const snb200_layer &L0 = conv[0];
@@ -489,35 +492,11 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     }
 
     if (flags & SNB200_GEN_PROFILE_SKIP_HEAD) return SNB200_OK;
-    // ---- fused pool + FC head
+    // ---- pool + FC head as its own cluster launch
     HeadParams H;
-    memset(&H, 0, sizeof(H));
-    const snb200_layer &LL = conv[nconv - 1];
-    H.b = b; H.training = training; H.c_feat = LL.c_out; H.tiles_per_cloud = tpc;
-    H.tile_max = W.tile_max; H.tile_min = W.tile_min; H.last_stats = W.stats[nconv - 1];
-    H.last_gamma = LL.bn_weight; H.last_beta = LL.bn_bias; H.last_run_mean = LL.bn_running_mean; H.last_run_var = LL.bn_running_var;
-    H.last_eps = LL.bn_eps; H.last_has_bn = LL.bn_weight != nullptr; H.last_relu = LL.relu;
-    H.count = (double)b * (double)n;
-    H.feat = feat_out ? feat_out : W.feat;
-    if (training)
-        for (int l = 0; l < nconv; l++) {
-            if (!conv[l].bn_weight || (!conv[l].bn_running_mean && !conv[l].bn_running_var)) continue;
-            const int i = H.ru_num++;
-            H.ru_stats[i] = W.stats[l]; H.ru_mean[i] = conv[l].bn_running_mean; H.ru_var[i] = conv[l].bn_running_var;
-            H.ru_momentum[i] = conv[l].bn_momentum; H.ru_c[i] = conv[l].c_out;
-        }
-    H.num_fc = nfc;
-    int cmax = LL.c_out, max_out = 0;
-    for (int l = 0; l < nfc; l++) {
-        HeadLayer &D = H.fc[l];
-        D.c_in = fc[l].c_in; D.c_out = fc[l].c_out; D.weight = fc[l].weight; D.bias = fc[l].bias; D.gamma = fc[l].bn_weight; D.beta = fc[l].bn_bias;
-        D.run_mean = fc[l].bn_running_mean; D.run_var = fc[l].bn_running_var; D.eps = fc[l].bn_eps; D.momentum = fc[l].bn_momentum;
-        D.has_bn = fc[l].bn_weight != nullptr; D.relu = fc[l].relu;
-        cmax = max(cmax, D.c_in);
-        max_out = max(max_out, D.c_out);
-    }
-    H.act[0] = W.head_act[0]; H.act[1] = W.head_act[1];
-    H.out = out; H.out_inner = out_transpose_inner;
+    fill_head_params(H, b, n, tpc, nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
+    int cmax = conv[nconv - 1].c_out, max_out = 0;
+    for (int l = 0; l < nfc; l++) { cmax = max(cmax, fc[l].c_in); max_out = max(max_out, fc[l].c_out); }
     // cluster size: enough CTAs that the widest layer is a single 16-channel pass per CTA, capped at 16 (non-portable size)
     int csize = 1;
     while (csize < kHeadMaxCluster && csize * kHeadChPerCta < max_out) csize *= 2;

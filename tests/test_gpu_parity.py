@@ -351,7 +351,7 @@ def test_generator_backward_matches_torch_autograd(sb):
     np.testing.assert_allclose(_n(simp), _n(y), rtol=2e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("b,n", [(32, 1024), (2, 1024), (7, 1000), (37, 1024), (3, 77)])
+@pytest.mark.parametrize("b,n", [(32, 1024), (2, 1024), (7, 1000), (37, 1024), (3, 77), (70, 500)])
 def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
     """The persistent cooperative conv-stack kernel (activations resident in TMEM) == the per-layer tensor-core kernels ==
     the exact-fp32 CUDA-core path, training and eval mode, full and ragged tiles, one and two tiles per CTA."""
@@ -366,7 +366,7 @@ def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
     for training in (True, False):
         sd = {k: v.clone() for k, v in net.state_dict().items()}
         outs = []
-        for kw in (dict(), dict(per_layer_kernels=True), dict(exact_fp32=True)):
+        for kw in (dict(), dict(separate_head=True), dict(per_layer_kernels=True), dict(exact_fp32=True)):
             net.load_state_dict(sd)
             out, feat = sb.ops.generator_forward(x, "bnc", conv, fc, training, 64, **kw)
             outs.append((out.clone(), feat.clone(), {k: v.clone() for k, v in net.state_dict().items() if "running" in k}))

@@ -52,7 +52,8 @@ def main():
         sigma = net.project.sigma().detach().reshape(1).contiguous()
         out["generator_total"] = graph_time(lambda: sb.ops.generator_forward(x, "bnc", conv, fc, True, M))
         out["generator_conv_only"] = graph_time(lambda: sb.ops.generator_forward(x, "bnc", conv, fc, True, M, _profile_flags=2))
-        out["generator_head_only"] = graph_time(lambda: sb.ops.generator_forward(x, "bnc", conv, fc, True, M, _profile_flags=4))
+        out["generator_head_only_cluster_kernel"] = graph_time(lambda: sb.ops.generator_forward(x, "bnc", conv, fc, True, M, _profile_flags=4))
+        out["generator_total_separate_head"] = graph_time(lambda: sb.ops.generator_forward(x, "bnc", conv, fc, True, M, separate_head=True))
         out["generator_exact_fp32_total"] = graph_time(lambda: sb.ops.generator_forward(x, "bnc", conv, fc, True, M, exact_fp32=True), reps=5)
         widths = [64, 64, 64, 128, 128]
         for l in range(1, 5):
