@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     float *s_in = reinterpret_cast<float *>(smem_raw);                 // [c_in][33] one 32-row group of the input, transposed
     float *s_part = reinterpret_cast<float *>(smem_raw) + 256 * 33;    // [16 warps][2 channels][32 rows]
     const double inv_cnt_h = 1.0 / H.count;
+    CS_TS(36);
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
     // no grid barrier has been crossed yet.
     if (!(need_stats && P.L[P.num_layers - 1].has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);
@@ -674,7 +675,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             }
         }
     }
+    CS_TS(37);
     cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the pooled feature of every cloud is in place
+    CS_TS(38);
 
     const float *cur = H.feat;
     for (int l = 0; l < H.num_fc; l++) {
@@ -685,6 +688,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         const int cpc = ((L.c_out + G - 1) / G + 1) & ~1;             // channels per CTA, even (pairs)
         const int c_lo = blockIdx.x * cpc, c_hi = min(L.c_out, c_lo + cpc);
         const int nrg = (H.b + 31) >> 5;
+        CS_TS(39 + l * 6 + 0);
         for (int cb = c_lo; cb < c_hi; cb += 2) {                     // one channel pair at a time
             const int c0 = cb, c1 = cb + 1;
             const bool has1 = c1 < c_hi;
@@ -735,6 +739,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         }
                     }
                     __syncthreads();
+                    CS_TS(39 + l * 6 + 1);
                     if (producer) {
                         float a0 = 0.f, a1 = 0.f;
                         if (wreg) {
@@ -755,6 +760,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         s_part[(warp * 2 + 1) * 32 + lane] = a1;
                     }
                     __syncthreads();
+                    CS_TS(39 + l * 6 + 2);
                     if (warp < 2) {   // fixed-order combination of the 16 K slices: warp 0 -> channel c0, warp 1 -> channel c1
                         float t = 0.f;
 #pragma unroll
@@ -809,7 +815,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             }
         }
         cur = dst;
+        CS_TS(39 + l * 6 + 3);
         if (!lastfc) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the next layer reads every CTA's channels
+        CS_TS(39 + l * 6 + 4);
     }
 }
 

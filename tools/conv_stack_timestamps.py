@@ -17,6 +17,10 @@ names = {0: "start", 1: "setup done", 2: "moments + barrier done"}
 for l in range(4):
     for i, n in enumerate(["layer start", "W staged", "scale/shift", "main loop issued", "acc ready", "epilogue done", "grid barrier done"]):
         names[3 + l * 8 + i] = "L%d %s" % (l + 2, n)
+names[36] = "head: start"; names[37] = "head: pooled"; names[38] = "head: barrier P done"
+for l in range(4):
+    for i, n in enumerate(["start", "input staged", "partials done", "stored", "barrier done"]):
+        names[39 + l * 6 + i] = "FC%d %s" % (l + 1, n)
 prev = t0
 for i in sorted(names):
     print("%-28s %8d cycles  (+%d)" % (names[i], ts[i] - t0, ts[i] - prev)); prev = ts[i]
