@@ -620,7 +620,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     if (!P.fuse_head) return;
     const HeadParams &H = P.H;
     float *s_in = reinterpret_cast<float *>(smem_raw);                 // [c_in][33] one 32-row group of the input, transposed
-    float *s_part = reinterpret_cast<float *>(smem_raw) + 256 * 33;    // [16 warps][2 channels][32 rows]
+    int hcmax = H.c_feat;
+    for (int l = 0; l < H.num_fc; l++) hcmax = max(hcmax, H.fc[l].c_in);
+    float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33;   // [4 K quarters][8 channels][32 rows]
     const double inv_cnt_h = 1.0 / H.count;
     CS_TS(36);
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
@@ -635,6 +637,10 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             float mx = -INFINITY, mn = INFINITY;
             const float *tm = H.tile_max + (size_t)bi * H.tiles_per_cloud * H.c_feat + c;
             const float *tn = H.tile_min + (size_t)bi * H.tiles_per_cloud * H.c_feat + c;
+            // every load of this element is issued before the first use
+            const double st0 = (H.last_has_bn && H.training) ? __ldcg(H.last_stats + c) : 0.0;
+            const double st1 = (H.last_has_bn && H.training) ? __ldcg(H.last_stats + H.c_feat + c) : 0.0;
+            const float lg = H.last_has_bn ? __ldg(H.last_gamma + c) : 1.f, lb = H.last_has_bn ? __ldg(H.last_beta + c) : 0.f;
 #pragma unroll 8
             for (int t = 0; t < H.tiles_per_cloud; t++) {
                 mx = fmaxf(mx, __ldcg(tm + (size_t)t * H.c_feat));
@@ -644,15 +650,15 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             if (H.last_has_bn) {
                 float mean, var;
                 if (H.training) {
-                    const double m = __ldcg(H.last_stats + c) * inv_cnt_h;
-                    double vv = __ldcg(H.last_stats + H.c_feat + c) * inv_cnt_h - m * m;
+                    const double m = st0 * inv_cnt_h;
+                    double vv = st1 * inv_cnt_h - m * m;
                     if (vv < 0) vv = 0;
                     mean = (float)m; var = (float)vv;
                 } else {
                     mean = H.last_run_mean[c]; var = H.last_run_var[c];
                 }
-                const float sc = H.last_gamma[c] * (1.0f / sqrtf(var + H.last_eps));
-                const float sh = H.last_beta[c] - mean * sc;
+                const float sc = lg * (1.0f / sqrtf(var + H.last_eps));
+                const float sh = lb - mean * sc;
                 v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);
             }
             if (H.last_relu) v = fmaxf(v, 0.f);
@@ -680,39 +686,52 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     CS_TS(38);
 
     const float *cur = H.feat;
+    float *s_wh = s_part + 4 * 8 * 32;                                  // [8 channels][c_in] this CTA's weight rows
     for (int l = 0; l < H.num_fc; l++) {
         const HeadLayer &L = H.fc[l];
         const bool lastfc = (l == H.num_fc - 1);
         float *dst = lastfc ? H.out : H.act[l & 1];
         const int c_in = L.c_in;
-        const int cpc = ((L.c_out + G - 1) / G + 1) & ~1;             // channels per CTA, even (pairs)
+        // 8 output channels per pass and per CTA: few enough CTAs read the (shared) input that L2 does not serialise on it
+        const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
         const int c_lo = blockIdx.x * cpc, c_hi = min(L.c_out, c_lo + cpc);
         const int nrg = (H.b + 31) >> 5;
         CS_TS(39 + l * 6 + 0);
-        for (int cb = c_lo; cb < c_hi; cb += 2) {                     // one channel pair at a time
-            const int c0 = cb, c1 = cb + 1;
-            const bool has1 = c1 < c_hi;
-            float y0[8], y1[8];                                       // finished pre-activations, row group g -> lane = row (warps 0 / 1)
-#pragma unroll
-            for (int gq = 0; gq < 8; gq++) { y0[gq] = 0.f; y1[gq] = 0.f; }
-            // this warp's K slice of the two weight rows (uniform addresses: one request per warp)
-            const int kr = ((c_in + 63) / 64) * 4;                    // K per warp (16 warps), multiple of 4
-            const int k_lo = min(c_in, warp * kr), k_hi = min(c_in, k_lo + kr);
-            float w0r[16], w1r[16];                                    // register copy when the slice is <= 16 wide (c_in <= 256)
-            const bool wreg = kr <= 16;
-            if (wreg && producer) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int k = k_lo + j;
-                    w0r[j] = (k < k_hi) ? __ldg(L.weight + (size_t)c0 * c_in + k) : 0.f;
-                    w1r[j] = (k < k_hi && has1) ? __ldg(L.weight + (size_t)c1 * c_in + k) : 0.f;
+        for (int cb = c_lo; cb < c_hi; cb += 8) {                     // one group of 8 channels at a time
+            const int nch = min(8, c_hi - cb);
+            // per-channel parameters of the channel this warp will finish (warps 0..7): loads start now
+            const int cw = cb + (warp & 7);
+            const bool cvw = warp < 8 && (warp & 7) < nch;
+            const float pbias = (cvw && L.bias) ? __ldg(L.bias + cw) : 0.f;
+            const float pgam = (cvw && L.has_bn) ? __ldg(L.gamma + cw) : 1.f;
+            const float pbet = (cvw && L.has_bn) ? __ldg(L.beta + cw) : 0.f;
+            const float prm = (cvw && L.has_bn && L.run_mean) ? L.run_mean[cw] : 0.f;
+            const float prv = (cvw && L.has_bn && L.run_var) ? L.run_var[cw] : 1.f;
+            __syncthreads();
+            // weight rows cb..cb+nch-1, row-major as in HBM (coalesced float4 / scalar copy)
+            if (producer) {
+                if ((c_in & 3) == 0) {
+                    const int q4 = c_in >> 2, total = 8 * q4;
+                    for (int e = tid; e < total; e += kCsProducers) {
+                        const int jr = e / q4, kq = e - jr * q4;
+                        const float4 v = (jr < nch) ? __ldg(reinterpret_cast<const float4 *>(L.weight + (size_t)(cb + jr) * c_in) + kq) : make_float4(0, 0, 0, 0);
+                        *reinterpret_cast<float4 *>(s_wh + jr * c_in + kq * 4) = v;
+                    }
+                } else {
+                    for (int e = tid; e < 8 * c_in; e += kCsProducers) {
+                        const int jr = e / c_in, k = e - jr * c_in;
+                        s_wh[e] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
+                    }
                 }
             }
+            float yv[8];                                              // finished pre-activation: row group g, lane = row, warp = channel
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) yv[gq] = 0.f;
 #pragma unroll
             for (int gq = 0; gq < 8; gq++) {
                 if (gq < nrg) {
                     const int r0 = gq * 32, rn = min(32, H.b - r0);
-                    __syncthreads();
+                    if (gq > 0) __syncthreads();
                     if (producer) {   // stage rows r0..r0+rn-1 transposed: lane = row, warps stride over 16-byte k groups
                         const int q4 = c_in >> 2;
                         const float *src = cur + (size_t)(r0 + min(lane, rn - 1)) * c_in;
@@ -740,75 +759,65 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     }
                     __syncthreads();
                     CS_TS(39 + l * 6 + 1);
-                    if (producer) {
+                    if (producer) {   // warp -> (channel pair = warp & 3, K quarter = warp >> 2); lane = row
+                        const int cp2 = (warp & 3) * 2, kq4 = warp >> 2;
+                        const int kr = ((c_in + 15) / 16) * 4;            // K per quarter, multiple of 4
+                        const int k_lo = min(c_in, kq4 * kr), k_hi = min(c_in, k_lo + kr);
+                        const float *w0 = s_wh + cp2 * c_in, *w1 = w0 + c_in;
                         float a0 = 0.f, a1 = 0.f;
-                        if (wreg) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const float a = (k_lo + j < k_hi) ? s_in[(k_lo + j) * 33 + lane] : 0.f;
-                                a0 = fmaf(a, w0r[j], a0);
-                                a1 = fmaf(a, w1r[j], a1);
-                            }
-                        } else {
-                            for (int k = k_lo; k < k_hi; k++) {
-                                const float a = s_in[k * 33 + lane];
-                                a0 = fmaf(a, __ldg(L.weight + (size_t)c0 * c_in + k), a0);
-                                if (has1) a1 = fmaf(a, __ldg(L.weight + (size_t)c1 * c_in + k), a1);
-                            }
+#pragma unroll 4
+                        for (int k = k_lo; k < k_hi; k++) {
+                            const float a = s_in[k * 33 + lane];
+                            a0 = fmaf(a, w0[k], a0);
+                            a1 = fmaf(a, w1[k], a1);
                         }
-                        s_part[(warp * 2 + 0) * 32 + lane] = a0;
-                        s_part[(warp * 2 + 1) * 32 + lane] = a1;
+                        s_part[(kq4 * 8 + cp2 + 0) * 32 + lane] = a0;
+                        s_part[(kq4 * 8 + cp2 + 1) * 32 + lane] = a1;
                     }
                     __syncthreads();
                     CS_TS(39 + l * 6 + 2);
-                    if (warp < 2) {   // fixed-order combination of the 16 K slices: warp 0 -> channel c0, warp 1 -> channel c1
-                        float t = 0.f;
-#pragma unroll
-                        for (int w16 = 0; w16 < 16; w16++) t += s_part[(w16 * 2 + warp) * 32 + lane];
-                        if (warp == 0) y0[gq] = t; else y1[gq] = t;
-                    }
+                    if (warp < 8)   // fixed-order combination of the 4 K quarters: warp = channel, lane = row
+                        yv[gq] = (s_part[(0 * 8 + warp) * 32 + lane] + s_part[(1 * 8 + warp) * 32 + lane]) +
+                                 (s_part[(2 * 8 + warp) * 32 + lane] + s_part[(3 * 8 + warp) * 32 + lane]);
                 }
             }
-            if (warp < 2 && (warp == 0 || has1)) {
-                const int c = (warp == 0) ? c0 : c1;
-                float *y = (warp == 0) ? y0 : y1;
-                const float bias = L.bias ? __ldg(L.bias + c) : 0.f;
+            if (cvw) {
                 float scale = 1.f, shift = 0.f;
 #pragma unroll
-                for (int gq = 0; gq < 8; gq++) y[gq] += bias;
+                for (int gq = 0; gq < 8; gq++) yv[gq] += pbias;
                 if (L.has_bn) {
                     float mean, var;
                     if (H.training) {
                         float sm = 0.f;
 #pragma unroll
                         for (int gq = 0; gq < 8; gq++)
-                            if (gq * 32 + lane < H.b) sm += y[gq];
+                            if (gq * 32 + lane < H.b) sm += yv[gq];
                         mean = warp_sum(sm) / (float)H.b;
                         float qq = 0.f;
 #pragma unroll
                         for (int gq = 0; gq < 8; gq++)
-                            if (gq * 32 + lane < H.b) { const float d = y[gq] - mean; qq = fmaf(d, d, qq); }
+                            if (gq * 32 + lane < H.b) { const float d = yv[gq] - mean; qq = fmaf(d, d, qq); }
                         qq = warp_sum(qq);
                         var = qq / (float)H.b;
                         if (lane == 0) {
                             const float unb = H.b > 1 ? qq / (float)(H.b - 1) : var;
-                            if (L.run_mean) L.run_mean[c] = (1.f - L.momentum) * L.run_mean[c] + L.momentum * mean;
-                            if (L.run_var) L.run_var[c] = (1.f - L.momentum) * L.run_var[c] + L.momentum * unb;
+                            if (L.run_mean) L.run_mean[cw] = (1.f - L.momentum) * prm + L.momentum * mean;
+                            if (L.run_var) L.run_var[cw] = (1.f - L.momentum) * prv + L.momentum * unb;
                         }
                     } else {
-                        mean = L.run_mean[c]; var = L.run_var[c];
+                        mean = prm; var = prv;
                     }
                     const float invstd = 1.0f / sqrtf(var + L.eps);
-                    scale = __ldg(L.gamma + c) * invstd;
-                    shift = __ldg(L.beta + c) - mean * scale;
+                    scale = pgam * invstd;
+                    shift = pbet - mean * scale;
                 }
 #pragma unroll
                 for (int gq = 0; gq < 8; gq++) {
                     const int r = gq * 32 + lane;
                     if (r < H.b) {
-                        float v = L.has_bn ? fmaf(y[gq], scale, shift) : y[gq];
+                        float v = L.has_bn ? fmaf(yv[gq], scale, shift) : yv[gq];
                         if (L.relu) v = fmaxf(v, 0.f);
-                        const int oc = (lastfc && H.out_inner > 0) ? (c % H.out_inner) * (L.c_out / H.out_inner) + c / H.out_inner : c;
+                        const int oc = (lastfc && H.out_inner > 0) ? (cw % H.out_inner) * (L.c_out / H.out_inner) + cw / H.out_inner : cw;
                         dst[(size_t)r * L.c_out + oc] = v;
                     }
                 }
@@ -863,7 +872,14 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
         if (l >= 1) wmax = max(wmax, 2 * (size_t)conv[l].c_in * (conv[l].c_out <= 64 ? 64 : 128) * 4);
     }
     if (tiles_per_cloud_out) *tiles_per_cloud_out = P.tiles_per_cloud;
-    const size_t smem = 65536 + wmax + 1024;
+    size_t smem = 65536 + wmax + 1024;
+    if (head) {   // the fused tail reuses the same dynamic shared memory: input tile + partial sums + 8 weight rows
+        int hcmax = head->c_feat;
+        for (int l = 0; l < head->num_fc; l++) hcmax = max(hcmax, head->fc[l].c_in);
+        const size_t hs = ((size_t)hcmax * 33 + 1024 + (size_t)8 * hcmax) * sizeof(float) + 1024;
+        if (hs > 200 * 1024) { set_error("conv stack: FC width %d too large for the fused head", hcmax); return SNB200_EUNSUPPORTED; }
+        smem = max(smem, hs);
+    }
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
     int grid = min(P.tiles, kNumSMs);

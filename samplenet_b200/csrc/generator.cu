@@ -454,7 +454,8 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     } else if (use_tc && !(flags & SNB200_GEN_PER_LAYER_KERNELS) && conv_stack_supported(b, n, nconv, conv)) {
         // one persistent cooperative launch for the conv stack AND (unless profiling flags split them) the pool + FC head
         HeadParams H;
-        const bool fuse_head = !(flags & (SNB200_GEN_PROFILE_SKIP_HEAD | SNB200_GEN_SEPARATE_HEAD)) && b <= 256;
+        bool fuse_head = !(flags & (SNB200_GEN_PROFILE_SKIP_HEAD | SNB200_GEN_SEPARATE_HEAD)) && b <= 256;
+        for (int l = 0; l < nfc; l++) fuse_head = fuse_head && fc[l].c_in <= 1024;
         if (fuse_head) fill_head_params(H, b, n, (n + 127) / 128, nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
         int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc,
                                    fuse_head ? &H : nullptr, stream);
