@@ -266,6 +266,35 @@ __device__ __forceinline__ float cs_colreduce16(float *s, int lane)
     return OP == 0 ? s[0] + o : (OP == 1 ? fmaxf(s[0], o) : fminf(s[0], o));
 }
 
+// 8 weight rows (output channels cb..cb+nch-1) of an FC layer into shared memory, row-major as in HBM
+__device__ __forceinline__ void cs_head_stage_weights(const HeadLayer &L, int cb, int nch, float *s_wh, int tid, bool producer)
+{
+    if (!producer) return;
+    const int c_in = L.c_in;
+    if ((c_in & 3) == 0) {
+        const int q4 = c_in >> 2, total = 8 * q4;
+        for (int e0 = tid; e0 < total; e0 += kCsProducers * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * kCsProducers;
+                const int jr = e / q4, kq = e - jr * q4;
+                v[u] = (e < total && jr < nch) ? __ldg(reinterpret_cast<const float4 *>(L.weight + (size_t)(cb + jr) * c_in) + kq) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * kCsProducers;
+                if (e < total) *reinterpret_cast<float4 *>(s_wh + (size_t)e * 4) = v[u];
+            }
+        }
+    } else {
+        for (int e = tid; e < 8 * c_in; e += kCsProducers) {
+            const int jr = e / c_in, k = e - jr * c_in;
+            s_wh[e] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
+        }
+    }
+}
+
 __device__ long long g_cs_ts[64];
 #define CS_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_cs_ts[(i)] = clock64(); } while (0)
 
@@ -622,7 +651,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     float *s_in = reinterpret_cast<float *>(smem_raw);                 // [c_in][33] one 32-row group of the input, transposed
     int hcmax = H.c_feat;
     for (int l = 0; l < H.num_fc; l++) hcmax = max(hcmax, H.fc[l].c_in);
-    float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33;   // [4 K quarters][8 channels][32 rows]
+    float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33;   // [8 K slices][8 channels][32 rows]
     const double inv_cnt_h = 1.0 / H.count;
     CS_TS(36);
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
@@ -664,29 +693,19 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             if (H.last_relu) v = fmaxf(v, 0.f);
             H.feat[e] = v;
         }
-        if (H.training) {
-            int base = 0;
-            for (int l = 0; l < H.ru_num; l++) {
-                for (int c = gt - base; c < H.ru_c[l]; c += gn) {
-                    if (c < 0) continue;
-                    const double m = __ldcg(H.ru_stats[l] + c) * inv_cnt_h;
-                    double v = __ldcg(H.ru_stats[l] + H.ru_c[l] + c) * inv_cnt_h - m * m;
-                    if (v < 0) v = 0;
-                    const double unb = H.count > 1 ? v * (H.count / (H.count - 1)) : v;
-                    const float mom = H.ru_momentum[l];
-                    if (H.ru_mean[l]) H.ru_mean[l][c] = (1.f - mom) * H.ru_mean[l][c] + mom * (float)m;
-                    if (H.ru_var[l]) H.ru_var[l][c] = (1.f - mom) * H.ru_var[l][c] + mom * (float)unb;
-                }
-                base = (base + H.ru_c[l]) % gn;
-            }
-        }
     }
     CS_TS(37);
+    float *s_wh = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33 + 8 * 8 * 32;   // [8 channels][c_in] weight rows
+    if (H.num_fc > 0) {   // weights do not depend on activations: stage layer 1's rows while the barrier completes
+        const HeadLayer &L0 = H.fc[0];
+        const int cpc0 = max(8, (((L0.c_out + G - 1) / G + 7) / 8) * 8);
+        const int lo0 = blockIdx.x * cpc0, hi0 = min(L0.c_out, lo0 + cpc0);
+        if (lo0 < hi0) cs_head_stage_weights(L0, lo0, min(8, hi0 - lo0), s_wh, tid, producer);
+    }
     cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the pooled feature of every cloud is in place
     CS_TS(38);
 
     const float *cur = H.feat;
-    float *s_wh = s_part + 4 * 8 * 32;                                  // [8 channels][c_in] this CTA's weight rows
     for (int l = 0; l < H.num_fc; l++) {
         const HeadLayer &L = H.fc[l];
         const bool lastfc = (l == H.num_fc - 1);
@@ -707,22 +726,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             const float pbet = (cvw && L.has_bn) ? __ldg(L.beta + cw) : 0.f;
             const float prm = (cvw && L.has_bn && L.run_mean) ? L.run_mean[cw] : 0.f;
             const float prv = (cvw && L.has_bn && L.run_var) ? L.run_var[cw] : 1.f;
-            __syncthreads();
-            // weight rows cb..cb+nch-1, row-major as in HBM (coalesced float4 / scalar copy)
-            if (producer) {
-                if ((c_in & 3) == 0) {
-                    const int q4 = c_in >> 2, total = 8 * q4;
-                    for (int e = tid; e < total; e += kCsProducers) {
-                        const int jr = e / q4, kq = e - jr * q4;
-                        const float4 v = (jr < nch) ? __ldg(reinterpret_cast<const float4 *>(L.weight + (size_t)(cb + jr) * c_in) + kq) : make_float4(0, 0, 0, 0);
-                        *reinterpret_cast<float4 *>(s_wh + jr * c_in + kq * 4) = v;
-                    }
-                } else {
-                    for (int e = tid; e < 8 * c_in; e += kCsProducers) {
-                        const int jr = e / c_in, k = e - jr * c_in;
-                        s_wh[e] = (jr < nch) ? __ldg(L.weight + (size_t)(cb + jr) * c_in + k) : 0.f;
-                    }
-                }
+            if (cb != c_lo) {   // (the first group of every layer was staged before the preceding grid barrier)
+                __syncthreads();
+                cs_head_stage_weights(L, cb, nch, s_wh, tid, producer);
             }
             float yv[8];                                              // finished pre-activation: row group g, lane = row, warp = channel
 #pragma unroll
@@ -759,26 +765,40 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     }
                     __syncthreads();
                     CS_TS(39 + l * 6 + 1);
-                    if (producer) {   // warp -> (channel pair = warp & 3, K quarter = warp >> 2); lane = row
-                        const int cp2 = (warp & 3) * 2, kq4 = warp >> 2;
-                        const int kr = ((c_in + 15) / 16) * 4;            // K per quarter, multiple of 4
-                        const int k_lo = min(c_in, kq4 * kr), k_hi = min(c_in, k_lo + kr);
-                        const float *w0 = s_wh + cp2 * c_in, *w1 = w0 + c_in;
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-                        for (int k = k_lo; k < k_hi; k++) {
-                            const float a = s_in[k * 33 + lane];
-                            a0 = fmaf(a, w0[k], a0);
-                            a1 = fmaf(a, w1[k], a1);
+                    if (producer) {   // warp -> (channel quad = warp & 1, K eighth = warp >> 1); lane = row
+                        const int cq = (warp & 1) * 4, k8 = warp >> 1;
+                        const int kr = ((c_in + 31) / 32) * 4;            // K per eighth, multiple of 4
+                        const int k_lo = min(c_in, k8 * kr), k_hi = min(c_in, k_lo + kr);
+                        const float *wq = s_wh + cq * c_in;
+                        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+                        int k = k_lo;
+                        if ((c_in & 3) == 0) {
+                            for (; k + 4 <= k_hi; k += 4) {
+                                const float x0 = s_in[(k + 0) * 33 + lane], x1 = s_in[(k + 1) * 33 + lane], x2 = s_in[(k + 2) * 33 + lane], x3 = s_in[(k + 3) * 33 + lane];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const float4 wv = *reinterpret_cast<const float4 *>(wq + j * c_in + k);
+                                    a4[j] = fmaf(x3, wv.w, fmaf(x2, wv.z, fmaf(x1, wv.y, fmaf(x0, wv.x, a4[j]))));
+                                }
+                            }
                         }
-                        s_part[(kq4 * 8 + cp2 + 0) * 32 + lane] = a0;
-                        s_part[(kq4 * 8 + cp2 + 1) * 32 + lane] = a1;
+                        for (; k < k_hi; k++) {
+                            const float xv = s_in[k * 33 + lane];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) a4[j] = fmaf(xv, wq[j * c_in + k], a4[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) s_part[(k8 * 8 + cq + j) * 32 + lane] = a4[j];
                     }
                     __syncthreads();
                     CS_TS(39 + l * 6 + 2);
                     if (warp < 8)   // fixed-order combination of the 4 K quarters: warp = channel, lane = row
-                        yv[gq] = (s_part[(0 * 8 + warp) * 32 + lane] + s_part[(1 * 8 + warp) * 32 + lane]) +
-                                 (s_part[(2 * 8 + warp) * 32 + lane] + s_part[(3 * 8 + warp) * 32 + lane]);
+                    {
+                        float t = 0.f;
+#pragma unroll
+                        for (int e8 = 0; e8 < 8; e8++) t += s_part[(e8 * 8 + warp) * 32 + lane];
+                        yv[gq] = t;
+                    }
                 }
             }
             if (cvw) {
@@ -825,8 +845,34 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         }
         cur = dst;
         CS_TS(39 + l * 6 + 3);
-        if (!lastfc) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the next layer reads every CTA's channels
+        if (!lastfc) {
+            __syncthreads();                                           // everyone is done with this layer's weight rows
+            const HeadLayer &Ln = H.fc[l + 1];
+            const int cpcn = max(8, (((Ln.c_out + G - 1) / G + 7) / 8) * 8);
+            const int lon = blockIdx.x * cpcn, hin = min(Ln.c_out, lon + cpcn);
+            if (lon < hin) cs_head_stage_weights(Ln, lon, min(8, hin - lon), s_wh, tid, producer);
+            cs_grid_barrier(P.barrier, ++barrier_epoch * G);           // the next layer reads every CTA's channels
+        }
         CS_TS(39 + l * 6 + 4);
+    }
+    // ---- running statistics of the conv stack: off the critical path, taken by the CTAs from the top of the grid (idle in the
+    //      last FC layer); training mode never reads these buffers inside the kernel
+    if (H.training) {
+        const int gt = (G - 1 - (int)blockIdx.x) * kCsThreadsAll + tid, gn = G * kCsThreadsAll;
+        int base = 0;
+        for (int l = 0; l < H.ru_num; l++) {
+            for (int c = gt - base; c < H.ru_c[l]; c += gn) {
+                if (c < 0) continue;
+                const double m = __ldcg(H.ru_stats[l] + c) * inv_cnt_h;
+                double v = __ldcg(H.ru_stats[l] + H.ru_c[l] + c) * inv_cnt_h - m * m;
+                if (v < 0) v = 0;
+                const double unb = H.count > 1 ? v * (H.count / (H.count - 1)) : v;
+                const float mom = H.ru_momentum[l];
+                if (H.ru_mean[l]) H.ru_mean[l][c] = (1.f - mom) * H.ru_mean[l][c] + mom * (float)m;
+                if (H.ru_var[l]) H.ru_var[l][c] = (1.f - mom) * H.ru_var[l][c] + mom * (float)unb;
+            }
+            base = (base + H.ru_c[l]) % gn;
+        }
     }
 }
 
@@ -876,7 +922,7 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     if (head) {   // the fused tail reuses the same dynamic shared memory: input tile + partial sums + 8 weight rows
         int hcmax = head->c_feat;
         for (int l = 0; l < head->num_fc; l++) hcmax = max(hcmax, head->fc[l].c_in);
-        const size_t hs = ((size_t)hcmax * 33 + 1024 + (size_t)8 * hcmax) * sizeof(float) + 1024;
+        const size_t hs = ((size_t)hcmax * 33 + 2048 + (size_t)8 * hcmax) * sizeof(float) + 1024;
         if (hs > 200 * 1024) { set_error("conv stack: FC width %d too large for the fused head", hcmax); return SNB200_EUNSUPPORTED; }
         smem = max(smem, hs);
     }
