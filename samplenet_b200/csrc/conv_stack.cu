@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // ================================================================================================================
     if (!P.fuse_head) return;
     const HeadParams &H = P.H;
-    float *s_in = reinterpret_cast<float *>(smem_raw);                 // [c_in][33] one 32-row group of the input, transposed
+    float *s_in = reinterpret_cast<float *>(smem_raw);                 // [32 rows][c_in + 1] one row group of the input
     int hcmax = H.c_feat;
     for (int l = 0; l < H.num_fc; l++) hcmax = max(hcmax, H.fc[l].c_in);
     float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33;   // [8 K slices][8 channels][32 rows]
@@ -738,29 +738,34 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 if (gq < nrg) {
                     const int r0 = gq * 32, rn = min(32, H.b - r0);
                     if (gq > 0) __syncthreads();
-                    if (producer) {   // stage rows r0..r0+rn-1 transposed: lane = row, warps stride over 16-byte k groups
-                        const int q4 = c_in >> 2;
-                        const float *src = cur + (size_t)(r0 + min(lane, rn - 1)) * c_in;
+                    if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride: coalesced 16-byte loads (lanes along k),
+                                      // conflict-free scalar stores, conflict-free lane = row reads
+                        const int ldi = c_in + 1;
                         if ((c_in & 3) == 0) {
-                            for (int kq0 = warp; kq0 < q4; kq0 += 16 * 4) {
+                            const int q4 = c_in >> 2, total = 32 * q4;
+                            for (int e0 = tid; e0 < total; e0 += kCsProducers * 4) {
                                 float4 v[4];
 #pragma unroll
                                 for (int u = 0; u < 4; u++) {
-                                    const int kq = kq0 + 16 * u;
-                                    v[u] = (kq < q4) ? __ldcg(reinterpret_cast<const float4 *>(src) + kq) : make_float4(0, 0, 0, 0);
+                                    const int e = e0 + u * kCsProducers;
+                                    const int r = e / q4, kq = e - r * q4;
+                                    v[u] = (e < total && r < rn) ? __ldcg(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + r) * c_in) + kq) : make_float4(0, 0, 0, 0);
                                 }
 #pragma unroll
                                 for (int u = 0; u < 4; u++) {
-                                    const int kq = kq0 + 16 * u;
-                                    if (kq < q4) {
-                                        const float4 t = (lane < rn) ? v[u] : make_float4(0, 0, 0, 0);
-                                        s_in[(kq * 4 + 0) * 33 + lane] = t.x; s_in[(kq * 4 + 1) * 33 + lane] = t.y;
-                                        s_in[(kq * 4 + 2) * 33 + lane] = t.z; s_in[(kq * 4 + 3) * 33 + lane] = t.w;
+                                    const int e = e0 + u * kCsProducers;
+                                    if (e < total) {
+                                        const int r = e / q4, kq = e - r * q4;
+                                        float *d = s_in + r * ldi + kq * 4;
+                                        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
                                     }
                                 }
                             }
                         } else {
-                            for (int k = warp; k < c_in; k += 16) s_in[k * 33 + lane] = (lane < rn) ? __ldcg(src + k) : 0.f;
+                            for (int e = tid; e < 32 * c_in; e += kCsProducers) {
+                                const int r = e / c_in, k = e - r * c_in;
+                                s_in[r * ldi + k] = (r < rn) ? __ldcg(cur + (size_t)(r0 + r) * c_in + k) : 0.f;
+                            }
                         }
                     }
                     __syncthreads();
@@ -774,7 +779,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         int k = k_lo;
                         if ((c_in & 3) == 0) {
                             for (; k + 4 <= k_hi; k += 4) {
-                                const float x0 = s_in[(k + 0) * 33 + lane], x1 = s_in[(k + 1) * 33 + lane], x2 = s_in[(k + 2) * 33 + lane], x3 = s_in[(k + 3) * 33 + lane];
+                                const float *xr = s_in + lane * (c_in + 1) + k;
+                                const float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
                                     const float4 wv = *reinterpret_cast<const float4 *>(wq + j * c_in + k);
@@ -783,7 +789,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             }
                         }
                         for (; k < k_hi; k++) {
-                            const float xv = s_in[k * 33 + lane];
+                            const float xv = s_in[lane * (c_in + 1) + k];
 #pragma unroll
                             for (int j = 0; j < 4; j++) a4[j] = fmaf(xv, wq[j * c_in + k], a4[j]);
                         }
