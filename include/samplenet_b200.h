@@ -37,6 +37,17 @@ extern "C" {
 #define SNB200_DIST_FMA 0      /* d = fma(dz,dz,fma(dy,dy,dx*dx)): the arithmetic nvcc gives the reference CUDA kernels */
 #define SNB200_DIST_UNFUSED 1  /* d = (dx*dx+dy*dy)+dz*dz, three roundings: the arithmetic of the reference CPU code */
 
+/* how the `sigma` device scalar of the projection entry points is interpreted (sigma_mode); `sigma_floor` is the clamp:
+ *   SIGMA_VALUE       *sigma is sigma itself
+ *   SIGMA_FROM_T_REG  *sigma is the temperature T, sigma = max(T*T, floor)      registration/src/soft_projection.py:97-99
+ *   SIGMA_FROM_T_CLS  *sigma is T, sigma = T*T                                   classification/soft_projection.py:41
+ *   SIGMA_FROM_T_REC  *sigma is T, sigma = max(T, floor)^2                       reconstruction/src/soft_projection.py:51-54
+ * (evaluating sigma inside the kernel removes two elementwise launches from every forward) */
+#define SNB200_SIGMA_VALUE 0
+#define SNB200_SIGMA_FROM_T_REG 1
+#define SNB200_SIGMA_FROM_T_CLS 2
+#define SNB200_SIGMA_FROM_T_REC 3
+
 typedef void *snb200_stream_t; /* a cudaStream_t */
 
 const char *snb200_last_error(void);
@@ -85,18 +96,19 @@ int snb200_simplification_loss_forward(int b, int n, const float *samp, int m, c
  * 1 <= k <= 32, k <= n.
  * --------------------------------------------------------------------------------------------------------- */
 int snb200_knn_soft_project_forward(int b, int n, int m, int k, int layout, const float *points, const float *query,
-                                    const float *sigma, int hard, const float *feats, int f, float *proj, float *prop,
+                                    const float *sigma, int sigma_mode, float sigma_floor, int hard, const float *feats, int f, float *proj, float *prop,
                                     int *knn_idx, float *knn_val, float *weights, float *dist_over_sigma, int flags,
                                     snb200_stream_t stream);
 
 /* Backward of the soft projection given the saved knn_idx and weights.  grad_proj in `layout` (may be NULL),
  * grad_prop like prop (may be NULL).  Outputs (each may be NULL): grad_points, grad_query in `layout` (overwritten),
- * grad_feats like feats (overwritten), grad_sigma: DEVICE pointer to one float (overwritten).
+ * grad_feats like feats (overwritten), grad_sigma: DEVICE pointer to one float (overwritten), the gradient with respect to
+ * SIGMA (for the FROM_T modes the caller applies d sigma / d T).
  * Replaces the autograd graph of registration/src/soft_projection.py:92-152 and groupPointGradLauncher
  * (tf_grouping.cpp:173).  workspace: see query. */
 size_t snb200_soft_project_backward_workspace_bytes(int b, int n, int m, int k, int f);
 int snb200_soft_project_backward(int b, int n, int m, int k, int layout, const float *points, const float *query,
-                                 const float *sigma, const float *feats, int f, const int *knn_idx,
+                                 const float *sigma, int sigma_mode, float sigma_floor, const float *feats, int f, const int *knn_idx,
                                  const float *weights, const float *grad_proj, const float *grad_prop,
                                  float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
                                  void *workspace, size_t workspace_bytes, snb200_stream_t stream);
@@ -121,6 +133,7 @@ typedef struct snb200_layer {
     const float *bias;    /* (c_out) */
     const float *bn_weight, *bn_bias;   /* (c_out) gamma/beta, NULL => no BatchNorm after this layer */
     float *bn_running_mean, *bn_running_var; /* (c_out) updated in training mode when non-NULL */
+    long long *bn_num_batches_tracked;  /* int64 device scalar, +1 per training forward when non-NULL (torch BatchNorm bookkeeping) */
     float bn_eps, bn_momentum;
     int relu;             /* apply ReLU after (BatchNorm of) this layer */
 } snb200_layer;

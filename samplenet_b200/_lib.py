@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsamplenet_b200.so")
 BNC, BCN = 0, 1
 DIST_FMA, DIST_UNFUSED = 0, 1
 GEN_EXACT_FP32 = 1
+SIGMA_VALUE, SIGMA_FROM_T_REG, SIGMA_FROM_T_CLS, SIGMA_FROM_T_REC = 0, 1, 2, 3
 
 _c_float_p = ctypes.c_void_p  # raw device pointers travel as integers
 _vp = ctypes.c_void_p
@@ -26,7 +27,7 @@ class Layer(ctypes.Structure):
     _fields_ = [
         ("c_in", _int), ("c_out", _int),
         ("weight", _vp), ("bias", _vp), ("bn_weight", _vp), ("bn_bias", _vp),
-        ("bn_running_mean", _vp), ("bn_running_var", _vp),
+        ("bn_running_mean", _vp), ("bn_running_var", _vp), ("bn_num_batches_tracked", _vp),
         ("bn_eps", _float), ("bn_momentum", _float), ("relu", _int),
     ]
 
@@ -40,9 +41,9 @@ _SIGNATURES = {
     "snb200_nn_distance_backward": (_int, [_int, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb200_simplification_loss_workspace_bytes": (_size, [_int, _int, _int]),
     "snb200_simplification_loss_forward": (_int, [_int, _int, _vp, _int, _vp, _float, _vp, _vp, _vp, _vp, _vp, _vp, _size, _int, _vp]),
-    "snb200_knn_soft_project_forward": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "snb200_knn_soft_project_forward": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp, _int, _float, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "snb200_soft_project_backward_workspace_bytes": (_size, [_int, _int, _int, _int, _int]),
-    "snb200_soft_project_backward": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _size, _vp]),
+    "snb200_soft_project_backward": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp, _int, _float, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _size, _vp]),
     "snb200_group_point": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "snb200_group_point_grad": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "snb200_encoder_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer)]),

@@ -23,12 +23,13 @@ int launch_chamfer_forward(int b, int n, const float *xyz1, int m, const float *
 int launch_chamfer_backward(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1, const int *idx1,
                             const float *grad_dist2, const int *idx2, float *grad_xyz1, float *grad_xyz2, cudaStream_t stream);
 int launch_simplification_reduce(int b, int n, int m, const float *dist1, const float *dist2, float w, float *out4, cudaStream_t stream);
-int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma, int hard,
+int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma, int sigma_mode,
+                        float sigma_floor, int hard,
                         const float *feats, int f, float *proj, float *prop, int *knn_idx, float *knn_val, float *weights,
                         float *dist_over_sigma, int flags, cudaStream_t stream);
 size_t softproj_bwd_workspace(int b, int n, int m, int k, int f);
 int launch_softproj_backward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
-                             const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
+                             int sigma_mode, float sigma_floor, const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
                              const float *grad_prop, float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
                              void *workspace, cudaStream_t stream);
 int launch_group_point(int b, int n, int c, int m, int ns, int layout, const float *points, const int *idx, float *out, cudaStream_t stream);
@@ -113,7 +114,7 @@ SNB_API int snb200_simplification_loss_forward(int b, int n, const float *samp, 
 }
 
 SNB_API int snb200_knn_soft_project_forward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
-                                            int hard, const float *feats, int f, float *proj, float *prop, int *knn_idx, float *knn_val,
+                                            int sigma_mode, float sigma_floor, int hard, const float *feats, int f, float *proj, float *prop, int *knn_idx, float *knn_val,
                                             float *weights, float *dist_over_sigma, int flags, snb200_stream_t stream)
 {
     SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "knn_soft_project_forward: bad sizes b=%d n=%d m=%d", b, n, m);
@@ -124,15 +125,16 @@ SNB_API int snb200_knn_soft_project_forward(int b, int n, int m, int k, int layo
     SNB_REQUIRE(points && query, "knn_soft_project_forward: null input");
     const bool needs_sigma = proj || prop || weights || dist_over_sigma;
     SNB_REQUIRE(!needs_sigma || sigma, "knn_soft_project_forward: sigma is required for projection outputs");
+    SNB_REQUIRE(sigma_mode >= 0 && sigma_mode <= 3, "knn_soft_project_forward: unknown sigma_mode %d", sigma_mode);
     SNB_REQUIRE(!prop || (feats && f >= 1), "knn_soft_project_forward: prop requested without features");
-    return launch_knn_softproj(b, n, m, k, layout, points, query, sigma, hard, feats, f, proj, prop, knn_idx, knn_val, weights, dist_over_sigma,
+    return launch_knn_softproj(b, n, m, k, layout, points, query, sigma, sigma_mode, sigma_floor, hard, feats, f, proj, prop, knn_idx, knn_val, weights, dist_over_sigma,
                                flags, (cudaStream_t)stream);
 }
 
 SNB_API size_t snb200_soft_project_backward_workspace_bytes(int b, int n, int m, int k, int f) { return softproj_bwd_workspace(b, n, m, k, f); }
 
 SNB_API int snb200_soft_project_backward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
-                                         const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
+                                         int sigma_mode, float sigma_floor, const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
                                          const float *grad_prop, float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
                                          void *workspace, size_t workspace_bytes, snb200_stream_t stream)
 {
@@ -145,7 +147,7 @@ SNB_API int snb200_soft_project_backward(int b, int n, int m, int k, int layout,
         set_error("soft_project_backward: workspace %zu < %zu bytes", workspace_bytes, softproj_bwd_workspace(b, n, m, k, f));
         return SNB200_EWORKSPACE;
     }
-    return launch_softproj_backward(b, n, m, k, layout, points, query, sigma, feats, f, knn_idx, weights, grad_proj, grad_prop, grad_points,
+    return launch_softproj_backward(b, n, m, k, layout, points, query, sigma, sigma_mode, sigma_floor, feats, f, knn_idx, weights, grad_proj, grad_prop, grad_points,
                                     grad_query, grad_feats, grad_sigma, workspace, (cudaStream_t)stream);
 }
 

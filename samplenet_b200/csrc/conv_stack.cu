@@ -861,6 +861,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         }
         CS_TS(39 + l * 6 + 4);
     }
+    if (blockIdx.x == G - 1 && tid < H.num_counters) *H.counters[tid] += 1;
     // ---- running statistics of the conv stack: off the critical path, taken by the CTAs from the top of the grid (idle in the
     //      last FC layer); training mode never reads these buffers inside the kernel
     if (H.training) {

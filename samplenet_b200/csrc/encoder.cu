@@ -234,6 +234,8 @@ struct RunUpdateParams {
     float momentum[SNB200_MAX_CONV_LAYERS];
     int c[SNB200_MAX_CONV_LAYERS];
     double count;
+    int num_counters;
+    long long *counters[SNB200_MAX_CONV_LAYERS];
 };
 
 struct PoolParams {
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(256) pool_finalize_kernel(const __grid_constan
         P.feat[e] = v;
     }
     if (blockIdx.x == gridDim.x - 1) {
+        if ((int)threadIdx.x < P.ru.num_counters) *P.ru.counters[threadIdx.x] += 1;
         // the last block applies the running-stat updates after every read of run_mean/run_var that other blocks
         // of THIS kernel could make is irrelevant: in training mode bn_scale_shift never reads the running buffers.
         for (int l = 0; l < P.ru.num; l++)
@@ -293,6 +296,7 @@ struct FcParams {
     int has_bn, relu, training;
     int out_inner;  // > 0: store row (c_out/out_inner, out_inner) transposed
     float *out;
+    long long *counter;  // BatchNorm num_batches_tracked of this layer (training) or nullptr
 };
 
 __global__ void __launch_bounds__(kFcWarps * 32) fc_layer_kernel(const __grid_constant__ FcParams P)
@@ -301,6 +305,7 @@ __global__ void __launch_bounds__(kFcWarps * 32) fc_layer_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int co = blockIdx.x * kFcWarps + warp;
     const bool active = co < P.c_out;  // warp-uniform
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.counter) *P.counter += 1;
     const float *w = P.weight + (size_t)(active ? co : 0) * P.c_in;
     float y[kFcMaxRowsPerLane];  // lane holds rows lane, lane+32, ...
 #pragma unroll
@@ -488,6 +493,8 @@ int launch_encoder_forward(int b, int n, int layout, const float *x, int num_lay
             Q.ru.stats[i] = W.stats[l]; Q.ru.run_mean[i] = layers[l].bn_running_mean; Q.ru.run_var[i] = layers[l].bn_running_var;
             Q.ru.momentum[i] = layers[l].bn_momentum; Q.ru.c[i] = layers[l].c_out;
         }
+        for (int l = 0; l < num_layers; l++)
+            if (layers[l].bn_weight && layers[l].bn_num_batches_tracked) Q.ru.counters[Q.ru.num_counters++] = layers[l].bn_num_batches_tracked;
     }
     pool_finalize_kernel<<<(b * LL.c_out + 255) / 256, 256, 0, stream>>>(Q);
     return check_launch("encoder pool finalize");
@@ -518,6 +525,7 @@ int launch_fc_head_forward(int b, const float *in, int num_layers, const snb200_
         P.has_bn = L.bn_weight != nullptr; P.relu = L.relu; P.training = training;
         P.out = (l == num_layers - 1) ? out : buf[l & 1];
         P.out_inner = (l == num_layers - 1) ? out_transpose_inner : 0;
+        P.counter = (training && L.bn_weight) ? L.bn_num_batches_tracked : nullptr;
         const size_t smem = (size_t)min(b, kFcRowChunk) * L.c_in * sizeof(float);
         static PerDeviceOnce fc_once;
         if (fc_once.first()) cudaFuncSetAttribute(fc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -69,6 +69,9 @@ struct HeadParams {
     float *act[2];               // (b, max width) scratch
     float *out;                  // (b, c_out_last)
     int out_inner;
+    // torch BatchNorm bookkeeping: int64 counters incremented once per training forward
+    int num_counters;
+    long long *counters[SNB200_MAX_CONV_LAYERS + SNB200_MAX_FC_LAYERS];
     int dbg;                     // bring-up switches (always 0 in the product): 1 = stop after pooling, 2 = no TMA weight prefetch
 };
 

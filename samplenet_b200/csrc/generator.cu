@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
             }
         }
     }
+    if (rank == csize - 1 && tid < P.num_counters) *P.counters[tid] += 1;
     HEAD_TS(2);
     cluster.sync();
     HEAD_TS(3);
@@ -429,6 +430,12 @@ static void fill_head_params(HeadParams &H, int b, int n, int tpc, int nconv, co
     H.act[0] = W.head_act[0]; H.act[1] = W.head_act[1];
     H.out = out; H.out_inner = out_transpose_inner;
     H.dbg = 0;
+    if (training) {
+        for (int l = 0; l < nconv; l++)
+            if (conv[l].bn_weight && conv[l].bn_num_batches_tracked) H.counters[H.num_counters++] = conv[l].bn_num_batches_tracked;
+        for (int l = 0; l < nfc; l++)
+            if (fc[l].bn_weight && fc[l].bn_num_batches_tracked) H.counters[H.num_counters++] = fc[l].bn_num_batches_tracked;
+    }
 }
 
 static bool tc_stack_supported(int nconv, const snb200_layer *conv)

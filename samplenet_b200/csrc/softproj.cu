@@ -26,11 +26,21 @@ struct SoftProjParams {
     int b, n, m, k, f;
     int queries_per_warp;
     const float *points, *query, *sigma, *feats;
+    int sigma_mode; float sigma_floor;
     int hard;
     float *proj, *prop;
     int *knn_idx;
     float *knn_val, *weights, *dist_over_sigma;
 };
+
+__device__ __forceinline__ float resolve_sigma(const float *p, int mode, float floor_v)
+{
+    const float t = __ldg(p);
+    if (mode == SNB200_SIGMA_FROM_T_REG) return fmaxf(t * t, floor_v);
+    if (mode == SNB200_SIGMA_FROM_T_CLS) return t * t;
+    if (mode == SNB200_SIGMA_FROM_T_REC) { const float u = fmaxf(t, floor_v); return u * u; }
+    return t;
+}
 
 template <int kLayout>
 __device__ __forceinline__ float ld_coord(const float *base, int npts, int p, int c)
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(kSpThreads) knn_softproj_kernel(const __grid_c
         }
         // soft_projection.py:92-95: sum((grouped - query)^2) / sigma, evaluated like torch does (separate
         // subtract, square, sum over xyz in order, true division)
-        const float sigma = __ldg(P.sigma);
+        const float sigma = resolve_sigma(P.sigma, P.sigma_mode, P.sigma_floor);
         const float dx = gx - qx, dy = gy - qy, dz = gz - qz;
         const float dist = __fdiv_rn(sqdist<false>(dx, dy, dz), sigma);
         // soft_projection.py:143: softmax(-dist) over the k neighbours
@@ -191,13 +201,14 @@ __global__ void __launch_bounds__(kSpThreads) knn_softproj_kernel(const __grid_c
     }
 }
 
-int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma, int hard,
+int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma, int sigma_mode,
+                        float sigma_floor, int hard,
                         const float *feats, int f, float *proj, float *prop, int *knn_idx, float *knn_val, float *weights,
                         float *dist_over_sigma, int flags, cudaStream_t stream)
 {
     SoftProjParams P;
     P.b = b; P.n = n; P.m = m; P.k = k; P.f = f;
-    P.points = points; P.query = query; P.sigma = sigma; P.feats = feats; P.hard = hard;
+    P.points = points; P.query = query; P.sigma = sigma; P.sigma_mode = sigma_mode; P.sigma_floor = sigma_floor; P.feats = feats; P.hard = hard;
     P.proj = proj; P.prop = prop; P.knn_idx = knn_idx; P.knn_val = knn_val; P.weights = weights; P.dist_over_sigma = dist_over_sigma;
     // one query per warp until the grid exceeds ~8 CTAs per SM, then amortise the tile staging over more queries
     int qpw = 1;
@@ -240,6 +251,7 @@ int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *poi
 struct SoftProjBwdParams {
     int b, n, m, k, f;
     const float *points, *query, *sigma, *feats;
+    int sigma_mode; float sigma_floor;
     const int *knn_idx;
     const float *weights, *grad_proj, *grad_prop;
     float *grad_query;
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(kSpThreads) softproj_bwd_query_kernel(const __
     const float wa = warp_sum(w * a);
     const float t = w * (a - wa);   // dL/d(-d_i)
     const float ddd = -t;           // dL/dd_i
-    const float sigma = __ldg(P.sigma);
+    const float sigma = resolve_sigma(P.sigma, P.sigma_mode, P.sigma_floor);
     const float dx = gx - qx, dy = gy - qy, dz = gz - qz;
     const float two_over_s = 2.0f / sigma;
     const float cx = ddd * two_over_s * dx, cy = ddd * two_over_s * dy, cz = ddd * two_over_s * dz;  // via the distance
@@ -393,7 +405,7 @@ size_t softproj_bwd_workspace(int b, int n, int m, int k, int f)
 }
 
 int launch_softproj_backward(int b, int n, int m, int k, int layout, const float *points, const float *query, const float *sigma,
-                             const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
+                             int sigma_mode, float sigma_floor, const float *feats, int f, const int *knn_idx, const float *weights, const float *grad_proj,
                              const float *grad_prop, float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
                              void *workspace, cudaStream_t stream)
 {
@@ -401,7 +413,8 @@ int launch_softproj_backward(int b, int n, int m, int k, int layout, const float
     float *sigma_partial = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align_up((size_t)b * m * k * 3 * sizeof(float), 256));
     SoftProjBwdParams P;
     P.b = b; P.n = n; P.m = m; P.k = k; P.f = f;
-    P.points = points; P.query = query; P.sigma = sigma; P.feats = feats; P.knn_idx = knn_idx; P.weights = weights;
+    P.points = points; P.query = query; P.sigma = sigma; P.sigma_mode = sigma_mode; P.sigma_floor = sigma_floor; P.feats = feats;
+    P.knn_idx = knn_idx; P.weights = weights;
     P.grad_proj = grad_proj; P.grad_prop = grad_prop; P.grad_query = grad_query;
     P.contrib = grad_points ? contrib : nullptr; P.wcontrib = nullptr;
     P.sigma_partial = grad_sigma ? sigma_partial : nullptr;

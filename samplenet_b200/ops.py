@@ -140,8 +140,10 @@ class SimplificationLossFunction(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------- kNN / projection
-def knn_soft_project_forward(points, query, k, layout, sigma=None, hard=False, feats=None, want=("proj",), unfused=False):
-    """One fused launch.  `want` is a subset of {"proj","prop","idx","val","weights","dist"}; returns a dict of tensors."""
+def knn_soft_project_forward(points, query, k, layout, sigma=None, hard=False, feats=None, want=("proj",), unfused=False,
+                             sigma_mode=0, sigma_floor=0.0):
+    """One fused launch.  `want` is a subset of {"proj","prop","idx","val","weights","dist"}; returns a dict of tensors.
+    sigma_mode / sigma_floor: how the `sigma` scalar is interpreted (see SNB200_SIGMA_* in the header)."""
     lay = _layout(layout)
     points, query = _req(points, "point_cloud"), _req(query, "query_cloud")
     if points.dim() != 3 or query.dim() != 3 or points.shape[0] != query.shape[0]:
@@ -178,14 +180,15 @@ def knn_soft_project_forward(points, query, k, layout, sigma=None, hard=False, f
         if "dist" in want:
             out["dist"] = torch.empty(b, m, k, device=dev)
         check(lib().snb200_knn_soft_project_forward(
-            b, n, m, k, lay, _p(points), _p(query), _p(sigma), int(bool(hard)), _p(feats), f, _p(out.get("proj")), _p(out.get("prop")),
+            b, n, m, k, lay, _p(points), _p(query), _p(sigma), int(sigma_mode), float(sigma_floor), int(bool(hard)), _p(feats), f,
+            _p(out.get("proj")), _p(out.get("prop")),
             _p(out.get("idx")), _p(out.get("val")), _p(out.get("weights")), _p(out.get("dist")), DIST_UNFUSED if unfused else DIST_FMA,
             _stream()), "knn_soft_project_forward")
     return out
 
 
 def soft_project_backward(points, query, sigma, feats, idx, weights, grad_proj, grad_prop, layout, need_points, need_query, need_feats,
-                          need_sigma):
+                          need_sigma, sigma_mode=0, sigma_floor=0.0):
     lay = _layout(layout)
     b = points.shape[0]
     n = points.shape[1] if lay == BNC else points.shape[2]
@@ -203,31 +206,37 @@ def soft_project_backward(points, query, sigma, feats, idx, weights, grad_proj, 
         gproj = None if grad_proj is None else _req(grad_proj, "grad_proj")
         gprop = None if grad_prop is None else _req(grad_prop, "grad_prop")
         check(lib().snb200_soft_project_backward(
-            b, n, m, k, lay, _p(points), _p(query), _p(sigma), _p(feats), f, _p(idx), _p(weights), _p(gproj), _p(gprop), _p(gp), _p(gq),
+            b, n, m, k, lay, _p(points), _p(query), _p(sigma), int(sigma_mode), float(sigma_floor), _p(feats), f, _p(idx), _p(weights),
+            _p(gproj), _p(gprop), _p(gp), _p(gq),
             _p(gf), _p(gs), _p(ws), int(wsb), _stream()), "soft_project_backward")
     return gp, gq, gf, gs
 
 
 class SoftProjectFunction(torch.autograd.Function):
-    """(points, query, sigma[, feats]) -> (proj, prop, weights, dist, idx); differentiable in points, query, sigma, feats."""
+    """(points, query, t[, feats]) -> (proj, prop, weights, dist, idx); differentiable in points, query, t, feats.
+
+    `t` is either sigma itself (sigma_mode 0) or the temperature parameter, in which case the kernel evaluates the
+    sub-project's clamp (sigma_mode 1: max(T^2, floor) registration; 2: T^2 classification; 3: max(T, floor)^2 reconstruction)
+    and the chain rule d sigma / d T is applied here in backward."""
 
     @staticmethod
-    def forward(ctx, points, query, sigma, feats, k, layout, hard, want_proj, want_prop):
+    def forward(ctx, points, query, t, feats, k, layout, hard, want_proj, want_prop, sigma_mode=0, sigma_floor=0.0):
         want = ["idx", "weights", "dist"]
         if want_proj:
             want.append("proj")
         if want_prop:
             want.append("prop")
         points = points.contiguous(); query = query.contiguous()
-        sig = sigma.detach().reshape(1).contiguous()
-        o = knn_soft_project_forward(points, query, k, layout, sig, hard, feats, want)
+        sig = t.detach().reshape(1).contiguous()
+        o = knn_soft_project_forward(points, query, k, layout, sig, hard, feats, want, sigma_mode=sigma_mode, sigma_floor=sigma_floor)
         ctx.layout = layout
         ctx.hard = hard
         ctx.has_feats = feats is not None
+        ctx.sigma_mode, ctx.sigma_floor = int(sigma_mode), float(sigma_floor)
         ctx.save_for_backward(points, query, sig, feats.contiguous() if feats is not None else None, o["idx"], o["weights"])
         proj = o.get("proj"); prop = o.get("prop")
         ctx.mark_non_differentiable(o["idx"])
-        ctx.sigma_shape = sigma.shape
+        ctx.sigma_shape = t.shape
         dev = points.device
         if proj is None:
             proj = torch.empty(0, device=dev)
@@ -245,13 +254,20 @@ class SoftProjectFunction(torch.autograd.Function):
         if g_prop is not None and g_prop.numel() == 0:
             g_prop = None
         if g_proj is None and g_prop is None:
-            return (None,) * 9
+            return (None,) * 11
         need = ctx.needs_input_grad
         gp, gq, gf, gs = soft_project_backward(points, query, sig, feats, idx, weights, g_proj, g_prop, ctx.layout, need[0], need[1],
-                                               need[3] and ctx.has_feats, need[2])
-        if gs is not None:
+                                               need[3] and ctx.has_feats, need[2], ctx.sigma_mode, ctx.sigma_floor)
+        if gs is not None:   # d sigma / d T for the temperature modes
+            tt, fl = sig, ctx.sigma_floor
+            if ctx.sigma_mode == 1:
+                gs = gs * torch.where(tt * tt > fl, 2.0 * tt, torch.zeros_like(tt))
+            elif ctx.sigma_mode == 2:
+                gs = gs * 2.0 * tt
+            elif ctx.sigma_mode == 3:
+                gs = gs * torch.where(tt > fl, 2.0 * tt, torch.zeros_like(tt))
             gs = gs.reshape(ctx.sigma_shape)
-        return gp, gq, gs, gf, None, None, None, None, None
+        return gp, gq, gs, gf, None, None, None, None, None, None, None
 
 
 def group_point(points, idx, layout="bnc"):
@@ -300,7 +316,7 @@ class GroupPointFunction(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------------------------------- generator
 def make_layers(specs):
-    """specs: list of dicts(weight, bias, bn=(weight,bias,running_mean,running_var,eps,momentum) or None, relu=bool)."""
+    """specs: list of dicts(weight, bias, bn=(weight,bias,running_mean,running_var,eps,momentum[,num_batches_tracked]) or None, relu=bool)."""
     arr = (Layer * len(specs))()
     keep = []
     for i, s in enumerate(specs):
@@ -311,15 +327,22 @@ def make_layers(specs):
         arr[i].weight, arr[i].bias = w.data_ptr(), bias.data_ptr()
         bn = s.get("bn")
         if bn is not None:
-            gw, gb, rm, rv, eps, mom = bn
+            gw, gb, rm, rv, eps, mom = bn[:6]
+            nbt = bn[6] if len(bn) > 6 else None
             gw, gb = _req(gw, "bn.weight"), _req(gb, "bn.bias")
             keep += [gw, gb]
             arr[i].bn_weight, arr[i].bn_bias = gw.data_ptr(), gb.data_ptr()
             arr[i].bn_running_mean = None if rm is None else rm.data_ptr()
             arr[i].bn_running_var = None if rv is None else rv.data_ptr()
             arr[i].bn_eps, arr[i].bn_momentum = float(eps), float(0.1 if mom is None else mom)
+            if nbt is not None:
+                if nbt.dtype != torch.int64 or not nbt.is_cuda:
+                    raise TypeError("num_batches_tracked must be an int64 CUDA tensor")
+                arr[i].bn_num_batches_tracked = nbt.data_ptr()
+            else:
+                arr[i].bn_num_batches_tracked = None
         else:
-            arr[i].bn_weight = arr[i].bn_bias = arr[i].bn_running_mean = arr[i].bn_running_var = None
+            arr[i].bn_weight = arr[i].bn_bias = arr[i].bn_running_mean = arr[i].bn_running_var = arr[i].bn_num_batches_tracked = None
             arr[i].bn_eps, arr[i].bn_momentum = 0.0, 0.0
         arr[i].relu = int(bool(s.get("relu", False)))
     return arr, keep

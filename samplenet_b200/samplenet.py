@@ -137,7 +137,7 @@ class SampleNet(nn.Module):
 
     @staticmethod
     def _bn_tuple(bn):
-        return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum)
+        return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.num_batches_tracked)
 
     def _layer_specs(self):
         conv = [dict(weight=c.weight, bias=c.bias, bn=self._bn_tuple(b), relu=True) for c, b in self._convs()]
@@ -169,11 +169,6 @@ class SampleNet(nn.Module):
         else:
             conv_specs, fc_specs = self._layer_specs()
             y, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, self.training, out_inner, exact_fp32=self.generator_precision == "fp32")
-        if self.training:  # BatchNorm bookkeeping the kernels do not do: one fused multi-tensor add for all 8 counters
-            counters = [bn.num_batches_tracked for _, bn in self._convs() + self._fcs() if bn is not None and bn.num_batches_tracked is not None]
-            if counters:
-                with torch.no_grad():
-                    torch._foreach_add_(counters, 1)
         return y
 
     # ------------------------------------------------------------------------------------------ forward

@@ -58,8 +58,11 @@ class SoftProjection(nn.Module):
         return torch.clamp(self._temperature ** 2, min=self._min_sigma_value)
 
     def _run(self, point_cloud, query_cloud, point_features, want_proj, want_prop, hard=False, layout=None):
-        return ops.SoftProjectFunction.apply(point_cloud, query_cloud, self.sigma(), point_features, self._group_size,
-                                             layout or self._layout, hard, want_proj, want_prop)
+        # the kernel evaluates sigma = max(T^2, min_sigma) itself (no elementwise launches on the step's critical path)
+        if self._min_sigma_value is None:
+            self._min_sigma_value = float(self._min_sigma)
+        return ops.SoftProjectFunction.apply(point_cloud, query_cloud, self._temperature, point_features, self._group_size,
+                                             layout or self._layout, hard, want_proj, want_prop, 1, self._min_sigma_value)
 
     def project_and_propagate(self, point_cloud, point_features, query_cloud):
         proj, prop, _, _, _ = self._run(point_cloud, query_cloud, point_features, True, True)

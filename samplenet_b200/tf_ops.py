@@ -71,8 +71,9 @@ class SoftProjection(nn.Module):
         return self.project(point_cloud, query_cloud, hard)
 
     def project(self, point_cloud, query_cloud, hard=False):
-        proj, _, w, d, _ = ops.SoftProjectFunction.apply(point_cloud, query_cloud, self.sigma, None, self._group_size, "bnc",
-                                                         bool(hard), True, False)
+        mode = 2 if self._sigma_mode == "cls" else 3
+        proj, _, w, d, _ = ops.SoftProjectFunction.apply(point_cloud, query_cloud, self._temperature, None, self._group_size, "bnc",
+                                                         bool(hard), True, False, mode, self._min_sigma)
         return proj, w.unsqueeze(-1), d.unsqueeze(-1)
 
 
