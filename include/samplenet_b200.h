@@ -113,6 +113,19 @@ int snb200_soft_project_backward(int b, int n, int m, int k, int layout, const f
                                  float *grad_points, float *grad_query, float *grad_feats, float *grad_sigma,
                                  void *workspace, size_t workspace_bytes, snb200_stream_t stream);
 
+/* The tail of a SampleNet training step in ONE launch: soft projection of the generated points onto the input cloud
+ * (registration/src/samplenet.py:114) + nn_distance(samp, ref) + the simplification-loss reductions (samplenet.py:175-180).
+ * ref (b,n_ref,3), samp (b,n_samp,3) BNC.  Outputs: proj (b,n_samp,3), knn_idx / weights / dist_over_sigma (b,n_samp,k) (saved
+ * for the projection backward), dist1/idx1 (b,n_samp), dist2/idx2 (b,n_ref), out4 as in snb200_simplification_loss_forward.
+ * workspace: snb200_project_and_loss_workspace_bytes() bytes of partial sums; ticket: DEVICE unsigned that must be zero at
+ * the first call and is left zero by every call (allocate once, never touch).  n_ref <= 4096 (one shared-memory tile). */
+size_t snb200_project_and_loss_workspace_bytes(int b, int n_samp, int n_ref);
+int snb200_project_and_loss_forward(int b, int n_ref, int n_samp, int k, const float *ref, const float *samp, const float *sigma,
+                                    int sigma_mode, float sigma_floor, float *proj, int *knn_idx, float *weights,
+                                    float *dist_over_sigma, float *dist1, int *idx1, float *dist2, int *idx2, float weight21,
+                                    float *out4, void *workspace, size_t workspace_bytes, unsigned *ticket, int flags,
+                                    snb200_stream_t stream);
+
 /* group_point: points (b,n,c) BNC [or (b,c,n) BCN], idx (b,m,ns) -> out (b,m,ns,c) BNC [or (b,c,m,ns) BCN].
  * Replaces groupPointLauncher / groupPointGradLauncher (tf_grouping.cpp:142,173; tf_grouping_g.cu:40-78) and
  * pointnet2 grouping_operation.  The grad launcher overwrites grad_points (zeroes it first). */

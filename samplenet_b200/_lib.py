@@ -44,6 +44,8 @@ _SIGNATURES = {
     "snb200_knn_soft_project_forward": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp, _int, _float, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "snb200_soft_project_backward_workspace_bytes": (_size, [_int, _int, _int, _int, _int]),
     "snb200_soft_project_backward": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp, _int, _float, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _size, _vp]),
+    "snb200_project_and_loss_workspace_bytes": (_size, [_int, _int, _int]),
+    "snb200_project_and_loss_forward": (_int, [_int, _int, _int, _int, _vp, _vp, _vp, _int, _float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _float, _vp, _vp, _size, _vp, _int, _vp]),
     "snb200_group_point": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "snb200_group_point_grad": (_int, [_int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "snb200_encoder_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer)]),

@@ -59,6 +59,11 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
 int debug_head_timestamps(long long *host_out64);
 int debug_conv_stack_timestamps(long long *host_out64);
 
+size_t tail_workspace_bytes(int b, int n_samp, int n_ref);
+int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, const float *samp, const float *sigma, int sigma_mode, float sigma_floor,
+                      float *proj, int *knn_idx, float *weights, float *dist_over_sigma, float *dist1, int *idx1, float *dist2, int *idx2,
+                      float w21, float *out4, float *partial, unsigned *ticket, int flags, cudaStream_t stream);
+
 static int check_layers(const char *who, int num_layers, const snb200_layer *layers, int max_layers)
 {
     SNB_REQUIRE(layers != nullptr && num_layers >= 1 && num_layers <= max_layers, "%s: num_layers=%d out of range [1,%d]", who, num_layers, max_layers);
@@ -149,6 +154,30 @@ SNB_API int snb200_soft_project_backward(int b, int n, int m, int k, int layout,
     }
     return launch_softproj_backward(b, n, m, k, layout, points, query, sigma, sigma_mode, sigma_floor, feats, f, knn_idx, weights, grad_proj, grad_prop, grad_points,
                                     grad_query, grad_feats, grad_sigma, workspace, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_project_and_loss_workspace_bytes(int b, int n_samp, int n_ref)
+{
+    if (b < 1 || n_samp < 1 || n_ref < 1) return 0;
+    return tail_workspace_bytes(b, n_samp, n_ref);
+}
+
+SNB_API int snb200_project_and_loss_forward(int b, int n_ref, int n_samp, int k, const float *ref, const float *samp, const float *sigma,
+                                            int sigma_mode, float sigma_floor, float *proj, int *knn_idx, float *weights, float *dist_over_sigma,
+                                            float *dist1, int *idx1, float *dist2, int *idx2, float weight21, float *out4, void *workspace,
+                                            size_t workspace_bytes, unsigned *ticket, int flags, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 1 && b <= 65535 && n_ref >= 1 && n_samp >= 1, "project_and_loss_forward: bad sizes b=%d n_ref=%d n_samp=%d", b, n_ref, n_samp);
+    SNB_REQUIRE(n_ref <= 4096 && n_samp <= 4096, "project_and_loss_forward: clouds above 4096 points need the separate entry points (n_ref=%d n_samp=%d)", n_ref, n_samp);
+    SNB_REQUIRE(k >= 1 && k <= 32 && k <= n_ref, "project_and_loss_forward: group size k=%d outside [1, min(32, n_ref)]", k);
+    SNB_REQUIRE(sigma_mode >= 0 && sigma_mode <= 3, "project_and_loss_forward: unknown sigma_mode %d", sigma_mode);
+    SNB_REQUIRE(ref && samp && sigma && proj && knn_idx && weights && dist1 && idx1 && dist2 && idx2 && out4 && ticket, "project_and_loss_forward: null pointer");
+    if (!workspace || workspace_bytes < tail_workspace_bytes(b, n_samp, n_ref)) {
+        set_error("project_and_loss_forward: workspace %zu < %zu bytes", workspace_bytes, tail_workspace_bytes(b, n_samp, n_ref));
+        return SNB200_EWORKSPACE;
+    }
+    return launch_tail_fused(b, n_ref, n_samp, k, ref, samp, sigma, sigma_mode, sigma_floor, proj, knn_idx, weights, dist_over_sigma, dist1, idx1, dist2,
+                             idx2, weight21, out4, reinterpret_cast<float *>(workspace), ticket, flags, (cudaStream_t)stream);
 }
 
 SNB_API int snb200_group_point(int b, int n, int c, int m, int ns, int layout, const float *points, const int *idx, float *out, snb200_stream_t stream)

@@ -12,87 +12,9 @@
 // register-blocked per thread so that every candidate read from shared memory feeds Q distance evaluations, and the
 // group's partial minima are merged by log2(S) shuffle steps on the (distance, index) pair, lowest index winning
 // ties exactly like the reference's strict '<' scan.
-#include "common.cuh"
+#include "pairwise_device.cuh"
 
 namespace snb {
-
-constexpr int kChamferThreads = 256;
-constexpr int kChamferTile = 4096;  // candidates per shared-memory stage (48 KB)
-
-struct ChamferDir {
-    const float *q;   // queries   (b, nq, 3)
-    const float *c;   // candidates (b, nc, 3)
-    float *dist;      // (b, nq)
-    int *idx;         // (b, nq)
-    int nq, nc;
-    int S;            // lanes per query (power of two <= 32)
-    int tiles;        // CTAs along x for this direction
-};
-
-struct ChamferParams {
-    ChamferDir d[2];
-};
-
-template <int Q, bool kFma>
-__device__ __forceinline__ void chamfer_dir(const ChamferDir &D, int tile, int bi, float *s_c, uint64_t *bar)
-{
-    const int S = D.S;
-    const int groups = kChamferThreads / S;  // query groups per CTA
-    const int g = threadIdx.x / S;           // my group
-    const int l = threadIdx.x % S;           // my lane inside the group
-    const int q0 = (tile * groups + g) * Q;  // first of my Q queries
-
-    const float *qp = D.q + (size_t)bi * D.nq * 3;
-    const float *cp = D.c + (size_t)bi * D.nc * 3;
-
-    float qx[Q], qy[Q], qz[Q], best[Q];
-    int besti[Q];
-#pragma unroll
-    for (int t = 0; t < Q; t++) {
-        const int qi = min(q0 + t, D.nq - 1);  // clamp: out-of-range slots compute a duplicate and are not stored
-        qx[t] = __ldg(qp + qi * 3 + 0);
-        qy[t] = __ldg(qp + qi * 3 + 1);
-        qz[t] = __ldg(qp + qi * 3 + 2);
-        best[t] = INFINITY;
-        besti[t] = 0x7fffffff;
-    }
-
-    uint32_t phase = 0;
-    for (int c0 = 0; c0 < D.nc; c0 += kChamferTile) {
-        const int cn = min(kChamferTile, D.nc - c0);
-        if (c0 > 0) __syncthreads();  // everyone finished with the previous tile
-        stage_floats(s_c, cp + (size_t)c0 * 3, cn * 3, bar, phase);
-#pragma unroll 4
-        for (int j = l; j < cn; j += S) {
-            const float cx = s_c[j * 3 + 0], cy = s_c[j * 3 + 1], cz = s_c[j * 3 + 2];
-#pragma unroll
-            for (int t = 0; t < Q; t++) {
-                // (candidate - query), as chamfer_distance.cu:30-33
-                const float d = sqdist<kFma>(cx - qx[t], cy - qy[t], cz - qz[t]);
-                if (d < best[t]) {  // strict '<' and ascending j per lane: lowest index among equal distances
-                    best[t] = d;
-                    besti[t] = c0 + j;
-                }
-            }
-        }
-    }
-    // merge the S partial results of the group: lexicographic min on (distance, index)
-#pragma unroll
-    for (int t = 0; t < Q; t++) {
-        for (int o = S >> 1; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(kFullMask, best[t], o);
-            const int oi = __shfl_xor_sync(kFullMask, besti[t], o);
-            if (od < best[t] || (od == best[t] && oi < besti[t])) {
-                best[t] = od;
-                besti[t] = oi;
-            }
-        }
-        if (l == 0 && q0 + t < D.nq) {
-            D.dist[(size_t)bi * D.nq + q0 + t] = best[t];
-            D.idx[(size_t)bi * D.nq + q0 + t] = besti[t];
-        }
-    }
-}
 
 template <int Q, bool kFma>
 __global__ void __launch_bounds__(kChamferThreads) chamfer_forward_kernel(const __grid_constant__ ChamferParams P)

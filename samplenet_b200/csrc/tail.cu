@@ -1,0 +1,141 @@
+// tail.cu -- the SampleNet step's tail in ONE launch: soft projection of the generated points (fused kNN + softmax + gather),
+// Chamfer nn_distance between generated and input cloud (both directions) and the three simplification-loss reductions.
+//
+// In the reference these are knn_cuda.KNN + grouping + ~8 torch ops (samplenet.py:114), then -- when the trainer asks for the
+// loss -- two Chamfer launches and four reductions (samplenet.py:175-180).  The projection and the Chamfer distances depend
+// only on (x, simp), not on each other, so they run as different CTA roles of one grid; the per-CTA partial sums / maxima are
+// combined by the last CTA to finish (ticket counter) in a fixed order, which keeps the loss bit-reproducible.
+#include "pairwise_device.cuh"
+
+namespace snb {
+
+struct TailParams {
+    SoftProjParams sp;      // kNN + projection role (BNC)
+    ChamferParams ch;       // d[0]: samp -> ref, d[1]: ref -> samp
+    int knn_ctas;           // CTAs along x of the projection role
+    int b, n_samp, n_ref;
+    float w21;              // weight of the ref->samp term
+    float *partial;         // (b, chamfer_ctas, 2): per-CTA sum / max of its distances
+    unsigned *ticket;       // zero before the launch; reset to zero by the last CTA
+    float *out4;            // mean(d1), mean_b(max d1), mean(d2), loss
+};
+
+template <bool kFma>
+__global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__ TailParams P)
+{
+    extern __shared__ __align__(16) float s_dyn[];
+    __shared__ uint64_t bar;
+    __shared__ float s_rs[8], s_rm[8];
+    __shared__ unsigned s_ticket;
+    const int bx = blockIdx.x, bi = blockIdx.y;
+    if (bx < P.knn_ctas) {   // ---- role A: projection
+        knn_softproj_body<SNB200_BNC, kFma>(P.sp, bx, bi, s_dyn, &bar);
+        return;
+    }
+    // ---- role B: one Chamfer tile
+    const int cx = bx - P.knn_ctas;
+    const int ntiles = P.ch.d[0].tiles + P.ch.d[1].tiles;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    float my_sum = 0.f, my_max = -INFINITY;
+    if (cx < P.ch.d[0].tiles) chamfer_dir<1, kFma>(P.ch.d[0], cx, bi, s_dyn, &bar, &my_sum, &my_max);
+    else chamfer_dir<1, kFma>(P.ch.d[1], cx - P.ch.d[0].tiles, bi, s_dyn, &bar, &my_sum, &my_max);
+    // CTA partials (fixed order: warp shuffle tree, then warps in index order)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    my_sum = warp_sum(my_sum);
+    my_max = warp_max(my_max);
+    if (lane == 0) { s_rs[warp] = my_sum; s_rm[warp] = my_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ts = 0.f, tm = -INFINITY;
+        for (int w = 0; w < 8; w++) { ts += s_rs[w]; tm = fmaxf(tm, s_rm[w]); }
+        float *pp = P.partial + ((size_t)bi * ntiles + cx) * 2;
+        pp[0] = ts; pp[1] = tm;
+        __threadfence();
+        s_ticket = atomicAdd(P.ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != (unsigned)(P.b * ntiles) - 1u) return;
+    // ---- last CTA: combine (every partial is visible: each writer fenced before taking its ticket)
+    __threadfence();
+    __shared__ float s_a[256], s_b[256], s_c[256];
+    float a1 = 0.f, amax = 0.f, a2 = 0.f;
+    const int t0 = P.ch.d[0].tiles;
+    for (int c = threadIdx.x; c < P.b; c += 256) {
+        const volatile float *pp = P.partial + (size_t)c * ntiles * 2;
+        float s1 = 0.f, mx = -INFINITY, s2 = 0.f;
+        for (int t = 0; t < t0; t++) { s1 += pp[t * 2]; mx = fmaxf(mx, pp[t * 2 + 1]); }
+        for (int t = t0; t < ntiles; t++) s2 += pp[t * 2];
+        a1 += s1; amax += mx; a2 += s2;
+    }
+    s_a[threadIdx.x] = a1; s_b[threadIdx.x] = amax; s_c[threadIdx.x] = a2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            s_a[threadIdx.x] += s_a[threadIdx.x + s]; s_b[threadIdx.x] += s_b[threadIdx.x + s]; s_c[threadIdx.x] += s_c[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float c12 = s_a[0] / ((float)P.b * (float)P.n_samp);
+        const float mc = s_b[0] / (float)P.b;
+        const float c21 = s_c[0] / ((float)P.b * (float)P.n_ref);
+        P.out4[0] = c12; P.out4[1] = mc; P.out4[2] = c21;
+        P.out4[3] = c12 + mc + P.w21 * c21;
+        *P.ticket = 0u;   // ready for the next launch
+    }
+}
+
+// S (lanes per query) for one Chamfer direction -- same policy as chamfer.cu
+static void tail_plan_dir(ChamferDir &D, int b)
+{
+    int S = 1;
+    while (S < 32) {
+        const long long ctas = (long long)b * ((D.nq + (kChamferThreads / S) - 1) / (kChamferThreads / S));
+        if (ctas >= 2 * kNumSMs) break;
+        if (D.nc / (S * 2) < 16) break;
+        S *= 2;
+    }
+    D.S = S;
+    const int per_cta = kChamferThreads / S;
+    D.tiles = (D.nq + per_cta - 1) / per_cta;
+}
+
+size_t tail_workspace_bytes(int b, int n_samp, int n_ref)
+{
+    ChamferDir d0 = {nullptr, nullptr, nullptr, nullptr, n_samp, n_ref, 1, 0}, d1 = {nullptr, nullptr, nullptr, nullptr, n_ref, n_samp, 1, 0};
+    tail_plan_dir(d0, b); tail_plan_dir(d1, b);
+    return (size_t)b * (d0.tiles + d1.tiles) * 2 * sizeof(float);
+}
+
+int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, const float *samp, const float *sigma, int sigma_mode, float sigma_floor,
+                      float *proj, int *knn_idx, float *weights, float *dist_over_sigma, float *dist1, int *idx1, float *dist2, int *idx2,
+                      float w21, float *out4, float *partial, unsigned *ticket, int flags, cudaStream_t stream)
+{
+    TailParams P;
+    memset(&P, 0, sizeof(P));
+    SoftProjParams &S = P.sp;
+    S.b = b; S.n = n_ref; S.m = n_samp; S.k = k; S.f = 0; S.queries_per_warp = 1;
+    S.points = ref; S.query = samp; S.sigma = sigma; S.sigma_mode = sigma_mode; S.sigma_floor = sigma_floor; S.hard = 0;
+    S.proj = proj; S.knn_idx = knn_idx; S.weights = weights; S.dist_over_sigma = dist_over_sigma;
+    P.knn_ctas = (n_samp + kSpWarps - 1) / kSpWarps;
+    P.ch.d[0] = {samp, ref, dist1, idx1, n_samp, n_ref, 1, 0};
+    P.ch.d[1] = {ref, samp, dist2, idx2, n_ref, n_samp, 1, 0};
+    tail_plan_dir(P.ch.d[0], b); tail_plan_dir(P.ch.d[1], b);
+    P.b = b; P.n_samp = n_samp; P.n_ref = n_ref; P.w21 = w21; P.partial = partial; P.ticket = ticket; P.out4 = out4;
+    const size_t smem = (size_t)min(max(n_ref, n_samp), kSpTile) * 3 * sizeof(float);
+    static PerDeviceOnce once;
+    if (once.first()) {
+        cudaFuncSetAttribute(tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+    }
+    dim3 grid(P.knn_ctas + P.ch.d[0].tiles + P.ch.d[1].tiles, b);
+    if (flags & SNB200_DIST_UNFUSED) tail_fused_kernel<false><<<grid, 256, smem, stream>>>(P);
+    else tail_fused_kernel<true><<<grid, 256, smem, stream>>>(P);
+    return check_launch("project_and_simplification_loss");
+}
+
+}  // namespace snb

@@ -270,6 +270,90 @@ class SoftProjectFunction(torch.autograd.Function):
         return gp, gq, gs, gf, None, None, None, None, None, None, None
 
 
+_TICKETS = {}
+
+
+def _ticket(dev):
+    """One zero-initialised device counter per GPU for the last-CTA reduction of the fused tail (the kernel leaves it zero)."""
+    key = (dev.type, dev.index)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = torch.zeros(1, device=dev, dtype=torch.int32)
+        _TICKETS[key] = t
+    return t
+
+
+def project_and_loss_forward(ref, samp, k, t, sigma_mode, sigma_floor, weight21, unfused=False):
+    """One launch: proj, (idx, weights, dist) for the projection backward, Chamfer dist/idx both ways, out4 loss terms."""
+    ref, samp = _req(ref, "ref_pc"), _req(samp, "samp_pc")
+    b, n, _ = ref.shape
+    m = samp.shape[1]
+    dev = ref.device
+    tt = _req(t.detach().reshape(1), "temperature")
+    with torch.cuda.device(dev):
+        proj = torch.empty_like(samp)
+        idx = torch.empty(b, m, k, device=dev, dtype=torch.int32)
+        w = torch.empty(b, m, k, device=dev); d = torch.empty(b, m, k, device=dev)
+        dist1 = torch.empty(b, m, device=dev); idx1 = torch.empty(b, m, device=dev, dtype=torch.int32)
+        dist2 = torch.empty(b, n, device=dev); idx2 = torch.empty(b, n, device=dev, dtype=torch.int32)
+        out4 = torch.empty(4, device=dev)
+        wsb = int(lib().snb200_project_and_loss_workspace_bytes(b, m, n))
+        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        check(lib().snb200_project_and_loss_forward(b, n, m, int(k), _p(ref), _p(samp), _p(tt), int(sigma_mode), float(sigma_floor), _p(proj), _p(idx),
+                                                    _p(w), _p(d), _p(dist1), _p(idx1), _p(dist2), _p(idx2), float(weight21), _p(out4), _p(ws), wsb,
+                                                    _p(_ticket(dev)), DIST_UNFUSED if unfused else DIST_FMA, _stream()), "project_and_loss_forward")
+    return proj, idx, w, d, dist1, idx1, dist2, idx2, out4
+
+
+class ProjectAndLossFunction(torch.autograd.Function):
+    """(ref, samp, temperature) -> (proj, loss_w1, terms): the projection of `samp` onto `ref` together with the simplification
+    loss of (samp, ref) evaluated for weight 1 (`loss_w1`) and its three terms (`terms` = [mean c12, mean max c12, mean c21]).
+    Backward = soft-projection backward + Chamfer backward (both deterministic kernels)."""
+
+    @staticmethod
+    def forward(ctx, ref, samp, t, k, sigma_mode, sigma_floor):
+        ref = ref.contiguous(); samp = samp.contiguous()
+        proj, idx, w, d, dist1, idx1, dist2, idx2, out4 = project_and_loss_forward(ref, samp, k, t, sigma_mode, sigma_floor, 1.0)
+        ctx.save_for_backward(ref, samp, t.detach().reshape(1).contiguous(), idx, w, dist1, idx1, idx2)
+        ctx.sigma_mode, ctx.sigma_floor, ctx.t_shape = int(sigma_mode), float(sigma_floor), t.shape
+        return proj, out4[3], out4[:3]
+
+    @staticmethod
+    def backward(ctx, g_proj, g_unit, g_terms):
+        ref, samp, tt, idx, w, dist1, idx1, idx2 = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        b, m = dist1.shape
+        n = idx2.shape[1]
+        dev = ref.device
+        g_ref = g_samp = g_t = None
+        if g_proj is not None:
+            gp, gq, _, gs = soft_project_backward(ref, samp, tt, None, idx, w, g_proj.contiguous(), None, "bnc", need[0], need[1], False, need[2],
+                                                  ctx.sigma_mode, ctx.sigma_floor)
+            g_ref, g_samp = gp, gq
+            if gs is not None:
+                fl = ctx.sigma_floor
+                if ctx.sigma_mode == 1:
+                    gs = gs * torch.where(tt * tt > fl, 2.0 * tt, torch.zeros_like(tt))
+                elif ctx.sigma_mode == 2:
+                    gs = gs * 2.0 * tt
+                elif ctx.sigma_mode == 3:
+                    gs = gs * torch.where(tt > fl, 2.0 * tt, torch.zeros_like(tt))
+                g_t = gs.reshape(ctx.t_shape)
+        if g_unit is not None or g_terms is not None:
+            zero = torch.zeros((), device=dev)
+            gu = g_unit if g_unit is not None else zero
+            gt = g_terms if g_terms is not None else torch.zeros(3, device=dev)
+            a0, a1, a2 = gu + gt[0], gu + gt[1], gu + gt[2]
+            g1 = (a0 / (b * m)).expand(b, m).clone()
+            g1.scatter_add_(1, dist1.argmax(dim=1, keepdim=True), (a1 / b).expand(b, 1).contiguous())
+            g2 = (a2 / (b * n)).expand(b, n).contiguous()
+            gs_c, gr_c = nn_distance_backward(samp, ref, g1, idx1, g2, idx2)
+            g_samp = gs_c if g_samp is None else g_samp + gs_c
+            if need[0]:
+                g_ref = gr_c if g_ref is None else g_ref + gr_c
+        return (g_ref if need[0] else None), g_samp, g_t, None, None, None
+
+
 def group_point(points, idx, layout="bnc"):
     lay = _layout(layout)
     points, idx = _req(points, "points"), _req(idx, "idx", torch.int32)

@@ -119,6 +119,9 @@ class SampleNet(nn.Module):
         # "3xtf32": conv layers 2..5 on the tensor cores, error-compensated to fp32 accuracy (default);
         # "fp32":   exact-fp32 CUDA-core conv stack.  Not part of the reference signature; plain attribute.
         self.generator_precision = "3xtf32"
+        # project + Chamfer + loss reductions of (simp, x) in one launch when forward() runs in training mode ("bnc" in and out)
+        self.fused_tail = True
+        self._tail = None
 
     # ------------------------------------------------------------------------------------------ generator plumbing
     def _convs(self):
@@ -187,9 +190,19 @@ class SampleNet(nn.Module):
 
         match = None
         proj = None
+        self._tail = None
         if self.training:
             if not self.skip_projection:
-                proj = self.project.project(x, simp_in, layout=layout)
+                if self.fused_tail and layout == "bnc" and self.output_shape == "bnc" and x.shape[1] <= 4096 and m <= 4096:
+                    # projection + Chamfer + loss reductions of (simp, x) in one launch; the loss terms are kept for
+                    # get_simplification_loss(x, simp, ...) (same tensors => no further launch)
+                    sp = self.project
+                    if sp._min_sigma_value is None:
+                        sp._min_sigma_value = float(sp._min_sigma)
+                    proj, loss_w1, terms = ops.ProjectAndLossFunction.apply(x, simp_in, sp._temperature, sp._group_size, 1, sp._min_sigma_value)
+                    self._tail = (x, simp_in, x._version, simp_in._version, loss_w1, terms)
+                else:
+                    proj = self.project.project(x, simp_in, layout=layout)
             else:
                 proj = simp_in
         else:  # Inference: nearest input point per generated point, unique, FPS completion -- all on the GPU
@@ -226,7 +239,14 @@ class SampleNet(nn.Module):
         if self.skip_projection or not self.training:
             return torch.tensor(0).to(ref_pc)
         # ref_pc and samp_pc are B x N x 3 matrices
-        return ops.SimplificationLossFunction.apply(samp_pc, ref_pc, gamma + delta * pc_size)
+        w = gamma + delta * pc_size
+        tail = getattr(self, "_tail", None)
+        if tail is not None and tail[0] is ref_pc and tail[1] is samp_pc and tail[2] == ref_pc._version and tail[3] == samp_pc._version:
+            # the forward pass already evaluated Chamfer(samp, ref) and its reductions in the projection launch
+            if w == 1:
+                return tail[4]
+            return tail[5][0] + tail[5][1] + w * tail[5][2]
+        return ops.SimplificationLossFunction.apply(samp_pc, ref_pc, w)
 
     def get_projection_loss(self):
         sigma = self.project.sigma()

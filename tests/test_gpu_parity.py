@@ -533,3 +533,44 @@ def test_tc_gemm_3xtf32(sb, rows, c_in, c_out):
     err = (D.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 5e-6 * scale, (err, scale)
+
+
+def test_fused_tail_matches_separate_kernels(sb, oracle):
+    """projection + Chamfer + loss reductions in one launch == the stand-alone kernels, forward and backward; the cache in
+    SampleNet only answers for the very tensors forward() returned."""
+    torch.manual_seed(11)
+    net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda().train()
+    x = torch.rand(8, 1024, 3, device="cuda") - 0.5
+    outs = []
+    for fused in (True, False):
+        net.fused_tail = fused
+        net.zero_grad()
+        simp, proj = net(x)
+        loss = net.get_simplification_loss(x, simp, 64, 1, 0)
+        loss2 = net.get_simplification_loss(x, simp, 64, 0.5, 0.01)
+        (loss + 0.3 * loss2 + (proj ** 2).sum()).backward()
+        outs.append((proj.detach().clone(), loss.detach().clone(), loss2.detach().clone(), net.fc4.weight.grad.clone(), net.project._temperature.grad.clone()))
+    for a, c in zip(outs[0], outs[1]):
+        np.testing.assert_allclose(_n(a), _n(c), rtol=2e-5, atol=1e-6)
+    # oracle check of the fused launch itself, identical inputs
+    xs = _n(x); ss = _n(simp)
+    proj_f, idx_f, w_f, d_f, d1, i1, d2, i2, out4 = sb.ops.project_and_loss_forward(x, simp.detach(), 8, net.project._temperature, 1, 1e-2, 1.0)
+    _, idx = oracle.knn_point(8, xs, ss, contract=True, tie_mode=1)
+    assert np.array_equal(_n(idx_f), idx)
+    e1, j1, e2, j2 = oracle.nn_distance(ss, xs, contract=True)
+    assert np.array_equal(_n(i1), j1) and np.array_equal(_n(i2), j2) and np.array_equal(_n(d1), e1) and np.array_equal(_n(d2), e2)
+    np.testing.assert_allclose(float(out4[3]), float(oracle.simplification_loss(xs, ss, 64, 1, 0, contract=True)), rtol=3e-6)
+    # cache discipline: a different (equal-valued) tensor, or an in-place edit, must not be answered from the cache
+    net.fused_tail = True
+    simp, proj = net(x)
+    l_hit = net.get_simplification_loss(x, simp, 64)
+    l_miss = net.get_simplification_loss(x, simp.clone(), 64)
+    np.testing.assert_allclose(float(l_hit), float(l_miss), rtol=1e-6)
+    with torch.no_grad():
+        simp.mul_(1.5)
+    l_edit = net.get_simplification_loss(x, simp, 64)
+    assert abs(float(l_edit) - float(l_hit)) > 1e-4
+    # deterministic: the ticket counter is left at zero and two launches agree bit for bit
+    a = sb.ops.project_and_loss_forward(x, ss_t := simp.detach(), 8, net.project._temperature, 1, 1e-2, 1.0)[-1].clone()
+    c = sb.ops.project_and_loss_forward(x, ss_t, 8, net.project._temperature, 1, 1e-2, 1.0)[-1].clone()
+    assert torch.equal(a, c) and int(sb.ops._ticket(x.device)) == 0
