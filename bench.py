@@ -164,6 +164,7 @@ def time_kernels(sb, net, x):
         out["knn_softproj_us"] = graph_time_us(lambda: sb.ops.knn_soft_project_forward(x, simp, K_NN, "bnc", sigma, want=("proj", "idx", "weights", "dist")))
         out["chamfer_us"] = graph_time_us(lambda: sb.ops.nn_distance_forward(simp, x))
         out["chamfer_plus_reduce_us"] = graph_time_us(lambda: sb.ops.simplification_loss_forward(simp, x, 1.0))
+        out["tail_fused_us"] = graph_time_us(lambda: sb.ops.project_and_loss_forward(x, simp, K_NN, net.project._temperature, 1, 1e-2, 1.0))
     return out
 
 

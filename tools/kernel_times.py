@@ -64,7 +64,9 @@ def main():
         out["knn_softproj"] = graph_time(lambda: sb.ops.knn_soft_project_forward(x, simp, K, "bnc", sigma, want=("proj", "idx", "weights", "dist")))
         out["chamfer_fwd"] = graph_time(lambda: sb.ops.nn_distance_forward(simp, x))
         out["chamfer_fwd+reduce"] = graph_time(lambda: sb.ops.simplification_loss_forward(simp, x, 1.0))
-        out["sigma_torch_ops"] = graph_time(lambda: net.project.sigma())
+        out["tail_fused_project_chamfer_loss"] = graph_time(lambda: sb.ops.project_and_loss_forward(x, simp, K, net.project._temperature, 1, 1e-2, 1.0))
+        xb = torch.empty_like(x)
+        out["input_copy_d2d"] = graph_time(lambda: xb.copy_(x))
         step = sb.GraphedStep(net, B, N)
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(5):
