@@ -18,6 +18,7 @@ struct TailParams {
     float *partial;         // (b, chamfer_ctas, 2): per-CTA sum / max of its distances
     unsigned *ticket;       // zero before the launch; reset to zero by the last CTA
     float *out4;            // mean(d1), mean_b(max d1), mean(d2), loss
+    unsigned smem_floats;   // dynamic shared memory available to the final reduction
 };
 
 template <bool kFma>
@@ -59,17 +60,35 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     }
     __syncthreads();
     if (s_ticket != (unsigned)(P.b * ntiles) - 1u) return;
-    // ---- last CTA: combine (every partial is visible: each writer fenced before taking its ticket)
+    // ---- last CTA: combine (every partial is visible: each writer fenced before taking its ticket).  The partials are pulled
+    //      into shared memory with all loads in flight (one L2 round trip), then summed per cloud and across clouds in a fixed order.
     __threadfence();
     __shared__ float s_a[256], s_b[256], s_c[256];
     float a1 = 0.f, amax = 0.f, a2 = 0.f;
     const int t0 = P.ch.d[0].tiles;
-    for (int c = threadIdx.x; c < P.b; c += 256) {
-        const volatile float *pp = P.partial + (size_t)c * ntiles * 2;
-        float s1 = 0.f, mx = -INFINITY, s2 = 0.f;
-        for (int t = 0; t < t0; t++) { s1 += pp[t * 2]; mx = fmaxf(mx, pp[t * 2 + 1]); }
-        for (int t = t0; t < ntiles; t++) s2 += pp[t * 2];
-        a1 += s1; amax += mx; a2 += s2;
+    float2 *s_p = reinterpret_cast<float2 *>(s_dyn);
+    const int cap_clouds = max(1, (int)(P.smem_floats / 2) / ntiles);           // clouds per shared-memory pass
+    for (int cbase = 0; cbase < P.b; cbase += cap_clouds) {
+        const int nc = min(cap_clouds, P.b - cbase);
+        const int ne = nc * ntiles;
+        __syncthreads();
+        const float2 *src = reinterpret_cast<const float2 *>(P.partial) + (size_t)cbase * ntiles;
+        for (int e0 = threadIdx.x; e0 < ne; e0 += 256 * 4) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (e0 + u * 256 < ne) ? __ldcg(src + e0 + u * 256) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e0 + u * 256 < ne) s_p[e0 + u * 256] = v[u];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < nc; c += 256) {
+            const float2 *pp = s_p + (size_t)c * ntiles;
+            float s1 = 0.f, mx = -INFINITY, s2 = 0.f;
+            for (int t = 0; t < t0; t++) { s1 += pp[t].x; mx = fmaxf(mx, pp[t].y); }
+            for (int t = t0; t < ntiles; t++) s2 += pp[t].x;
+            a1 += s1; amax += mx; a2 += s2;
+        }
     }
     s_a[threadIdx.x] = a1; s_b[threadIdx.x] = amax; s_c[threadIdx.x] = a2;
     __syncthreads();
@@ -126,7 +145,9 @@ int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, con
     P.ch.d[1] = {ref, samp, dist2, idx2, n_ref, n_samp, 1, 0};
     tail_plan_dir(P.ch.d[0], b); tail_plan_dir(P.ch.d[1], b);
     P.b = b; P.n_samp = n_samp; P.n_ref = n_ref; P.w21 = w21; P.partial = partial; P.ticket = ticket; P.out4 = out4;
-    const size_t smem = (size_t)min(max(n_ref, n_samp), kSpTile) * 3 * sizeof(float);
+    size_t smem = (size_t)min(max(n_ref, n_samp), kSpTile) * 3 * sizeof(float);
+    if (smem < 16384) smem = 16384;
+    P.smem_floats = (unsigned)(smem / sizeof(float));
     static PerDeviceOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);

@@ -14,6 +14,57 @@ import torch
 from . import _lib
 
 
+class PipelinedHostStep:
+    """End-to-end streaming of host batches through two `GraphedStep`s (double buffering): while step i computes, the pinned host
+    batch of step i+1 is already crossing PCIe on a copy stream.  Every step still ends with its loss on the host.
+
+        pipe = PipelinedHostStep(net, 32, 1024)
+        pipe.submit(batch0)                      # prime
+        for i in range(steps):
+            pipe.submit(next_batch)              # H2D of step i+1, asynchronous
+            loss_i = pipe.step()                 # replay step i, read its loss (synchronises)
+    """
+
+    def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None):
+        self.slots = [GraphedStep(net, batch_size, num_points, gamma, delta, device) for _ in range(2)]
+        self.device = self.slots[0].device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.head = 0   # next slot to fill
+        self.tail = 0   # next slot to run
+        self.pending = 0
+        self.launches_per_step = self.slots[0].launches_per_step
+        for e in self.consumed:
+            e.record(torch.cuda.current_stream(self.device))
+
+    def submit(self, x_pinned):
+        if self.pending >= 2:
+            raise RuntimeError("PipelinedHostStep: both buffers are in flight; call step() first")
+        k = self.head
+        self.copy_stream.wait_event(self.consumed[k])          # the graph that last read this buffer has finished
+        with torch.cuda.stream(self.copy_stream):
+            self.slots[k].x.copy_(x_pinned, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.head ^= 1
+        self.pending += 1
+
+    def step(self):
+        if self.pending == 0:
+            raise RuntimeError("PipelinedHostStep: nothing submitted")
+        k = self.tail
+        st = torch.cuda.current_stream(self.device)
+        st.wait_event(self.ready[k])
+        g = self.slots[k]
+        g.graph.replay()
+        g.loss_host.copy_(g.loss_flat, non_blocking=True)
+        self.consumed[k].record(st)
+        st.synchronize()
+        self.tail ^= 1
+        self.pending -= 1
+        return float(g.loss_host[0])
+
+
 class GraphedStep:
     def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None, warmup=2):
         self.net = net
