@@ -224,8 +224,9 @@ def run_ours(args, rank, world, local_rank):
         pipe.step()
 
     def e2e_step(i):
-        pipe.submit(host_pool[(args.warmup + i + 1) % pool_n])
-        pipe.step()
+        pipe.launch()                                                    # step i: replay + loss read-back (async)
+        pipe.submit(host_pool[(args.warmup + i + 1) % pool_n])           # batch i+1 crosses PCIe meanwhile
+        pipe.finish()                                                    # loss of step i on the host
 
     ms_e2e = timed_region(e2e_step, args.steps)
     pipe.step()  # drain the last prefetched batch

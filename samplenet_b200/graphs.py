@@ -21,8 +21,9 @@ class PipelinedHostStep:
         pipe = PipelinedHostStep(net, 32, 1024)
         pipe.submit(batch0)                      # prime
         for i in range(steps):
-            pipe.submit(next_batch)              # H2D of step i+1, asynchronous
-            loss_i = pipe.step()                 # replay step i, read its loss (synchronises)
+            pipe.launch()                        # replay step i + loss read-back, asynchronous
+            pipe.submit(next_batch)              # H2D of step i+1 on the copy stream while step i computes
+            loss_i = pipe.finish()               # synchronise, loss of step i on the host
     """
 
     def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None):
@@ -49,7 +50,8 @@ class PipelinedHostStep:
         self.head ^= 1
         self.pending += 1
 
-    def step(self):
+    def launch(self):
+        """Enqueue the oldest submitted batch: graph replay + loss read-back (asynchronous)."""
         if self.pending == 0:
             raise RuntimeError("PipelinedHostStep: nothing submitted")
         k = self.tail
@@ -59,10 +61,19 @@ class PipelinedHostStep:
         g.graph.replay()
         g.loss_host.copy_(g.loss_flat, non_blocking=True)
         self.consumed[k].record(st)
-        st.synchronize()
+        self._inflight = k
+
+    def finish(self):
+        """Wait for the launched step and return its loss (host float)."""
+        k = self._inflight
+        torch.cuda.current_stream(self.device).synchronize()
         self.tail ^= 1
         self.pending -= 1
-        return float(g.loss_host[0])
+        return float(self.slots[k].loss_host[0])
+
+    def step(self):
+        self.launch()
+        return self.finish()
 
 
 class GraphedStep:
