@@ -31,6 +31,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 B, N, M, K_NN = 32, 1024, 64, 8
+B_SAT = 2048
 BOTTLENECK = 128
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "point-clouds/sec SampleNet fwd+Chamfer (B=32, N=1024->64)"
@@ -165,6 +166,13 @@ def time_kernels(sb, net, x):
         out["chamfer_us"] = graph_time_us(lambda: sb.ops.nn_distance_forward(simp, x))
         out["chamfer_plus_reduce_us"] = graph_time_us(lambda: sb.ops.simplification_loss_forward(simp, x, 1.0))
         out["tail_fused_us"] = graph_time_us(lambda: sb.ops.project_and_loss_forward(x, simp, K_NN, net.project._temperature, 1, 1e-2, 1.0))
+        # the same pairwise kernels with the machine filled (B_SAT clouds per launch): what they do when launch latency is amortised
+        g = torch.Generator(device="cpu").manual_seed(7)
+        xs = (torch.rand(B_SAT, N, 3, generator=g) - 0.5).to(x.device)
+        ss = (xs[:, torch.randperm(N, generator=g)[:M]] + 0.02 * torch.randn(B_SAT, M, 3, generator=g).to(x.device)).contiguous()
+        out["sat_knn_softproj_us"] = graph_time_us(lambda: sb.ops.knn_soft_project_forward(xs, ss, K_NN, "bnc", sigma, want=("proj", "idx", "weights", "dist")), reps=5)
+        out["sat_chamfer_us"] = graph_time_us(lambda: sb.ops.nn_distance_forward(ss, xs), reps=5)
+        out["sat_tail_fused_us"] = graph_time_us(lambda: sb.ops.project_and_loss_forward(xs, ss, K_NN, net.project._temperature, 1, 1e-2, 1.0), reps=5)
     return out
 
 
@@ -262,6 +270,19 @@ def run_ours(args, rank, world, local_rank):
                     "frac": pair_bytes_cd / (kt["chamfer_us"] * 1e-6) / 1e9 / pk["hbm_gbs"], "us": kt["chamfer_us"],
                     "algorithmic_bytes": pair_bytes_cd},
         "note": "0.4-0.7 MB per launch: these launches are latency-bound at B=32 (SURVEY.md section 7); fractions reported as required",
+    }
+    sat_bytes = B_SAT * (12 * N + 12 * M + 12 * M + 8 * (N + M))          # fused single pass, SURVEY.md section 8(d): 22 528 B/cloud
+    sat_pairs = 3.0 * B_SAT * N * M                                       # kNN + both Chamfer directions
+    roofline_pairwise["saturated_B"] = {
+        "clouds_per_launch": B_SAT,
+        "tail_fused": {"us": kt["sat_tail_fused_us"], "clouds_per_s": B_SAT / (kt["sat_tail_fused_us"] * 1e-6),
+                       "hbm_gbs_algorithmic": sat_bytes / (kt["sat_tail_fused_us"] * 1e-6) / 1e9,
+                       "hbm_frac": sat_bytes / (kt["sat_tail_fused_us"] * 1e-6) / 1e9 / pk["hbm_gbs"],
+                       "pair_gflops": 8.0 * sat_pairs / (kt["sat_tail_fused_us"] * 1e-6) / 1e9},
+        "knn_softproj": {"us": kt["sat_knn_softproj_us"], "hbm_gbs_algorithmic": pair_bytes_sp / B * B_SAT / (kt["sat_knn_softproj_us"] * 1e-6) / 1e9},
+        "chamfer": {"us": kt["sat_chamfer_us"], "hbm_gbs_algorithmic": pair_bytes_cd / B * B_SAT / (kt["sat_chamfer_us"] * 1e-6) / 1e9},
+        "note": "arithmetic intensity of the pair work is 3*N*M*8 flop / 22.5 KB = 70 flop/B per cloud before top-k bookkeeping: with the machine "
+                "full these kernels are FP32-issue bound, not HBM bound (SURVEY.md section 8(d) caveat)",
     }
     # ---- CPU baseline beside it (bounded: a few full B=32 steps)
     cpu_val, cpu_ms, cores, kind = cpu_reference_arm(6, 2)

@@ -89,6 +89,35 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
                     stage_floats(s_pts + 2 * tile_cap, pts + 2 * (size_t)n + p0, pn, &bar, phase);
                 }
             }
+            if (live && k <= 32) {
+                // Pass 1 (bound): every lane takes the minimum over its candidates of this tile.  The k-th smallest of the 32 lane
+                // minima bounds the k-th neighbour distance from above (k distinct candidates lie at or below it), so pass 2 only
+                // has to insert the handful of candidates at or below that bound instead of every running improvement
+                // (~k(1+ln(n/k)) insertions for a cold list).  Results are unchanged: the same candidates end in the list.
+                float mn = INFINITY;
+#pragma unroll 4
+                for (int j = lane; j < pn; j += 32) {
+                    float cx, cy, cz;
+                    if (kLayout == SNB200_BNC) {
+                        cx = s_pts[j * 3 + 0]; cy = s_pts[j * 3 + 1]; cz = s_pts[j * 3 + 2];
+                    } else {
+                        cx = s_pts[j]; cy = s_pts[tile_cap + j]; cz = s_pts[2 * tile_cap + j];
+                    }
+                    const float dd = sqdist<kFma>(cx - qx, cy - qy, cz - qz);
+                    mn = (dd < mn) ? dd : mn;
+                }
+                int rank = 0;   // position of my minimum among the 32 (ties by lane)
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float o = __shfl_sync(kFullMask, mn, j);
+                    rank += (o < mn || (o == mn && j < lane)) ? 1 : 0;
+                }
+                const unsigned kth = __ballot_sync(kFullMask, rank == k - 1);
+                if (kth) {      // (no lane has that rank only when NaNs break the ordering: keep the running bound)
+                    const float tau = __shfl_sync(kFullMask, mn, __ffs(kth) - 1);
+                    if (tau < INFINITY) thr = fminf(thr, __uint_as_float(__float_as_uint(tau) + 1u));   // admit d <= tau
+                }
+            }
             if (live) {
                 for (int base = 0; base < pn; base += 128) {
                     float d[4];
@@ -121,7 +150,7 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
                                 if (lane > 0 && v < up_v) { lv = up_v; li = up_i; }
                                 else if (v < lv) { lv = v; li = vi; }
                             }
-                            thr = __shfl_sync(kFullMask, lv, k - 1);
+                            thr = fminf(thr, __shfl_sync(kFullMask, lv, k - 1));
                         }
                     }
                 }
@@ -139,7 +168,10 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
 
         // neighbour coordinates: from global (L2-resident; the tile in shared memory may be a later one)
         float gx = 0, gy = 0, gz = 0;
-        if (has) {
+        if (has && ntiles == 1) {          // the whole cloud is still staged
+            if (kLayout == SNB200_BNC) { gx = s_pts[li * 3 + 0]; gy = s_pts[li * 3 + 1]; gz = s_pts[li * 3 + 2]; }
+            else { gx = s_pts[li]; gy = s_pts[tile_cap + li]; gz = s_pts[2 * tile_cap + li]; }
+        } else if (has) {
             gx = ld_coord<kLayout>(pts, n, li, 0);
             gy = ld_coord<kLayout>(pts, n, li, 1);
             gz = ld_coord<kLayout>(pts, n, li, 2);

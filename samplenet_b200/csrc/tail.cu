@@ -28,14 +28,17 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     __shared__ uint64_t bar;
     __shared__ float s_rs[8], s_rm[8];
     __shared__ unsigned s_ticket;
-    const int bx = blockIdx.x, bi = blockIdx.y;
-    if (bx < P.knn_ctas) {   // ---- role A: projection
-        knn_softproj_body<SNB200_BNC, kFma>(P.sp, bx, bi, s_dyn, &bar);
+    // 1-D grid, projection CTAs first: they are the long pole (a dependent top-k chain per query), so they must all be in the
+    // first wave; the short Chamfer tiles fill in behind them.
+    const int n_knn = P.b * P.knn_ctas;
+    if ((int)blockIdx.x < n_knn) {   // ---- role A: projection
+        knn_softproj_body<SNB200_BNC, kFma>(P.sp, (int)blockIdx.x % P.knn_ctas, (int)blockIdx.x / P.knn_ctas, s_dyn, &bar);
         return;
     }
     // ---- role B: one Chamfer tile
-    const int cx = bx - P.knn_ctas;
     const int ntiles = P.ch.d[0].tiles + P.ch.d[1].tiles;
+    const int bi = ((int)blockIdx.x - n_knn) / ntiles;
+    const int cx = ((int)blockIdx.x - n_knn) % ntiles;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -108,13 +111,14 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     }
 }
 
-// S (lanes per query) for one Chamfer direction -- same policy as chamfer.cu
+// S (lanes per query) for one Chamfer direction -- as chamfer.cu, but aiming at one CTA per SM per direction: the grid also
+// carries the projection CTAs and should stay within a single wave.
 static void tail_plan_dir(ChamferDir &D, int b)
 {
     int S = 1;
     while (S < 32) {
         const long long ctas = (long long)b * ((D.nq + (kChamferThreads / S) - 1) / (kChamferThreads / S));
-        if (ctas >= 2 * kNumSMs) break;
+        if (ctas >= kNumSMs) break;
         if (D.nc / (S * 2) < 16) break;
         S *= 2;
     }
@@ -146,14 +150,16 @@ int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, con
     tail_plan_dir(P.ch.d[0], b); tail_plan_dir(P.ch.d[1], b);
     P.b = b; P.n_samp = n_samp; P.n_ref = n_ref; P.w21 = w21; P.partial = partial; P.ticket = ticket; P.out4 = out4;
     size_t smem = (size_t)min(max(n_ref, n_samp), kSpTile) * 3 * sizeof(float);
-    if (smem < 16384) smem = 16384;
+    if (smem < 4096) smem = 4096;
     P.smem_floats = (unsigned)(smem / sizeof(float));
     static PerDeviceOnce once;
     if (once.first()) {
         cudaFuncSetAttribute(tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
         cudaFuncSetAttribute(tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        cudaFuncSetAttribute(tail_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(tail_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    dim3 grid(P.knn_ctas + P.ch.d[0].tiles + P.ch.d[1].tiles, b);
+    dim3 grid((unsigned)((long long)b * (P.knn_ctas + P.ch.d[0].tiles + P.ch.d[1].tiles)));
     if (flags & SNB200_DIST_UNFUSED) tail_fused_kernel<false><<<grid, 256, smem, stream>>>(P);
     else tail_fused_kernel<true><<<grid, 256, smem, stream>>>(P);
     return check_launch("project_and_simplification_loss");
