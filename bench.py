@@ -132,6 +132,14 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------- GPU arm
 def graph_time_us(fn, reps=20, replays=20):
     """Warm in-graph time of one stage: R back-to-back launches captured in one CUDA graph, CUDA events on the replay stream."""
+    if os.environ.get("SNB200_NO_GRAPH") == "1":   # profiler runs: plain launches (numbers then include host launch gaps)
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); b.synchronize()
+        return a.elapsed_time(b) * 1e3 / reps
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):

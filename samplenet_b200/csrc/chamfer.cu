@@ -33,33 +33,18 @@ __global__ void __launch_bounds__(kChamferThreads) chamfer_forward_kernel(const 
         chamfer_dir<Q, kFma>(P.d[1], blockIdx.x - P.d[0].tiles, bi, s_c, &bar);
 }
 
-// Choose lanes-per-query S and the register blocking Q for one direction.
-static void plan_dir(ChamferDir &D, int b, int Q)
-{
-    // Enough groups to give every SM a few CTAs, but never fewer than 16 candidates per lane (reduction overhead).
-    int S = 1;
-    while (S < 32) {
-        const long long ctas = (long long)b * ((D.nq + (kChamferThreads / S) * Q - 1) / ((kChamferThreads / S) * Q));
-        if (ctas >= 2 * kNumSMs) break;
-        if (D.nc / (S * 2) < 16) break;
-        S *= 2;
-    }
-    D.S = S;
-    const int per_cta = (kChamferThreads / S) * Q;
-    D.tiles = (D.nq + per_cta - 1) / per_cta;
-}
-
 int launch_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                            int *idx2, int flags, cudaStream_t stream)
 {
     ChamferParams P;
     P.d[0] = {xyz1, xyz2, dist1, idx1, n, m, 1, 0};
     P.d[1] = {xyz2, xyz1, dist2, idx2, m, n, 1, 0};
-    // register blocking only pays when a direction has many queries
+    // register blocking (every candidate read from shared memory feeds Q distance evaluations) only pays when BOTH directions
+    // have many queries; with a short side (64 generated points) it would idle most of the CTA
     const long long pairs = (long long)b * n * m;
-    const int Q = (pairs >= (1ll << 24)) ? 4 : 1;
-    plan_dir(P.d[0], b, Q);
-    plan_dir(P.d[1], b, Q);
+    const int Q = (pairs >= (1ll << 24) && min(n, m) >= 1024) ? 4 : 1;
+    plan_chamfer_dir(P.d[0], b, Q, 2 * kNumSMs);
+    plan_chamfer_dir(P.d[1], b, Q, 2 * kNumSMs);
     const int max_nc = max(n, m);
     const size_t smem = (size_t)min(max_nc, kChamferTile) * 3 * sizeof(float);
     dim3 grid(P.d[0].tiles + P.d[1].tiles, b);

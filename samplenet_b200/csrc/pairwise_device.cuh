@@ -239,6 +239,24 @@ struct ChamferParams {
     ChamferDir d[2];
 };
 
+// Choose the lanes-per-query S of one direction (Q = queries register-blocked per thread): no more thread slots per CTA than
+// there are queries (a 64-query direction must not leave 3/4 of a 256-thread CTA idle), then enough CTAs to reach `target_ctas`,
+// but never fewer than 16 candidates per lane (the log2(S) merge would dominate).
+inline void plan_chamfer_dir(ChamferDir &D, int b, int Q, int target_ctas)
+{
+    int S = 1;
+    while (S < 32) {
+        if (D.nc / (S * 2) < 16) break;
+        const int per_cta = (kChamferThreads / S) * Q;
+        const long long ctas = (long long)b * ((D.nq + per_cta - 1) / per_cta);
+        if (per_cta <= D.nq && ctas >= target_ctas) break;
+        S *= 2;
+    }
+    D.S = S;
+    const int per_cta = (kChamferThreads / S) * Q;
+    D.tiles = (D.nq + per_cta - 1) / per_cta;
+}
+
 template <int Q, bool kFma>
 __device__ __forceinline__ void chamfer_dir(const ChamferDir &D, int tile, int bi, float *s_c, uint64_t *bar, float *acc_sum = nullptr,
                                             float *acc_max = nullptr)

@@ -111,21 +111,8 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     }
 }
 
-// S (lanes per query) for one Chamfer direction -- as chamfer.cu, but aiming at one CTA per SM per direction: the grid also
-// carries the projection CTAs and should stay within a single wave.
-static void tail_plan_dir(ChamferDir &D, int b)
-{
-    int S = 1;
-    while (S < 32) {
-        const long long ctas = (long long)b * ((D.nq + (kChamferThreads / S) - 1) / (kChamferThreads / S));
-        if (ctas >= kNumSMs) break;
-        if (D.nc / (S * 2) < 16) break;
-        S *= 2;
-    }
-    D.S = S;
-    const int per_cta = kChamferThreads / S;
-    D.tiles = (D.nq + per_cta - 1) / per_cta;
-}
+// One CTA per SM per direction is enough here: the grid also carries the projection CTAs and should stay within a single wave.
+static void tail_plan_dir(ChamferDir &D, int b) { plan_chamfer_dir(D, b, 1, kNumSMs); }
 
 size_t tail_workspace_bytes(int b, int n_samp, int n_ref)
 {

@@ -9,6 +9,8 @@ compiler would do, and it is part of the public API:
     simp, proj, loss = step(x_cuda)                                    # x already in HBM
     loss_host = step.run_from_host(x_pinned)                           # H2D copy + replay + D2H of the loss, synchronised
 """
+import os
+
 import torch
 
 from . import _lib
@@ -58,7 +60,7 @@ class PipelinedHostStep:
         st = torch.cuda.current_stream(self.device)
         st.wait_event(self.ready[k])
         g = self.slots[k]
-        g.graph.replay()
+        g.replay()
         g.loss_host.copy_(g.loss_flat, non_blocking=True)
         self.consumed[k].record(st)
         self._inflight = k
@@ -106,17 +108,29 @@ class GraphedStep:
                 self.simp, self.proj, self.loss = body()
             self.launches_per_step = _lib.launch_count() - before
         self.loss_flat = self.loss.reshape(1)
+        # SNB200_NO_GRAPH=1: launch the same kernels one by one instead of replaying the graph -- for profilers only (ncu cannot
+        # attribute a cooperative launch inside a graph); results land in the same static buffers
+        self._body = body
+        self.eager = os.environ.get("SNB200_NO_GRAPH") == "1"
+
+    def replay(self):
+        if not self.eager:
+            self.graph.replay()
+            return
+        with torch.no_grad():
+            simp, proj, loss = self._body()
+            self.simp.copy_(simp); self.proj.copy_(proj); self.loss.copy_(loss)
 
     def __call__(self, x):
         """x: CUDA tensor shaped like the capture buffer (copied device-to-device), returns the static outputs."""
         self.x.copy_(x, non_blocking=True)
-        self.graph.replay()
+        self.replay()
         return self.simp, self.proj, self.loss
 
     def run_from_host(self, x_pinned):
         """End-to-end step: pinned host batch -> device, replay, loss back to the host (synchronised); returns float."""
         self.x.copy_(x_pinned, non_blocking=True)
-        self.graph.replay()
+        self.replay()
         self.loss_host.copy_(self.loss_flat, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return float(self.loss_host[0])
