@@ -19,6 +19,8 @@ struct SoftProjParams {
     float *proj, *prop;
     int *knn_idx;
     float *knn_val, *weights, *dist_over_sigma;
+    float *nn_dist;   // optional (b, m): distance to the nearest neighbour == nn_distance's dist1 of (query -> points)
+    int *nn_idx;      // optional (b, m): its index                         == idx1
 };
 
 __device__ __forceinline__ float resolve_sigma(const float *p, int mode, float floor_v)
@@ -39,7 +41,8 @@ __device__ __forceinline__ float ld_coord(const float *base, int npts, int p, in
 // Body of the fused kNN + soft projection for CTA (bx, bi); s_pts: dynamic shared memory (BNC: [tile*3] AoS; BCN: 3 rows of
 // `tile_cap`), bar: an mbarrier in shared memory (initialised here).
 template <int kLayout, bool kFma>
-__device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int bx, int bi, float *s_pts, uint64_t *barp)
+__device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int bx, int bi, float *s_pts, uint64_t *barp,
+                                                  float *acc_sum = nullptr, float *acc_max = nullptr)
 {
     uint64_t &bar = *barp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,11 +92,69 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
                     stage_floats(s_pts + 2 * tile_cap, pts + 2 * (size_t)n + p0, pn, &bar, phase);
                 }
             }
-            if (live && k <= 32) {
-                // Pass 1 (bound): every lane takes the minimum over its candidates of this tile.  The k-th smallest of the 32 lane
-                // minima bounds the k-th neighbour distance from above (k distinct candidates lie at or below it), so pass 2 only
-                // has to insert the handful of candidates at or below that bound instead of every running improvement
-                // (~k(1+ln(n/k)) insertions for a cold list).  Results are unchanged: the same candidates end in the list.
+            // One insertion into the warp-resident sorted list (lane i = i-th smallest so far, ascending by (distance, index)):
+            // candidates arrive in ascending index order, so strict '<' keeps the lower index first among equal distances.
+#define SNB_KNN_INSERT(V, VI)                                                   \
+            do {                                                                \
+                const float up_v = __shfl_up_sync(kFullMask, lv, 1);            \
+                const int up_i = __shfl_up_sync(kFullMask, li, 1);              \
+                if (lane > 0 && (V) < up_v) { lv = up_v; li = up_i; }           \
+                else if ((V) < lv) { lv = (V); li = (VI); }                     \
+            } while (0)
+            // Bound from the lane minima `mn` of a tile: the k-th smallest of the 32 lane minima is an upper bound of the k-th
+            // neighbour distance (k distinct candidates lie at or below it), so only the handful of candidates at or below it
+            // have to go through the list instead of every running improvement (~k(1+ln(n/k)) for a cold list).
+#define SNB_KNN_BOUND(MN)                                                                                       \
+            do {                                                                                                \
+                int rank = 0;                                                                                   \
+                _Pragma("unroll") for (int jj = 0; jj < 32; jj++) {                                             \
+                    const float o = __shfl_sync(kFullMask, (MN), jj);                                           \
+                    rank += (o < (MN) || (o == (MN) && jj < lane)) ? 1 : 0;                                     \
+                }                                                                                               \
+                const unsigned kth = __ballot_sync(kFullMask, rank == k - 1);                                   \
+                if (kth) { /* (no lane has that rank only when NaNs break the ordering: keep the running bound) */ \
+                    const float tau = __shfl_sync(kFullMask, (MN), __ffs(kth) - 1);                             \
+                    if (tau < INFINITY) thr = fminf(thr, __uint_as_float(__float_as_uint(tau) + 1u)); /* admit d <= tau */ \
+                }                                                                                               \
+            } while (0)
+            if (live && pn <= 1024) {
+                // Register path (the SampleNet sizes): the 32 distances of a lane stay in registers between the bound pass and the
+                // insertion pass, so every pair is evaluated once.
+                float d[32];
+                float mn = INFINITY;
+#pragma unroll
+                for (int u = 0; u < 32; u++) {
+                    const int j = u * 32 + lane;
+                    float dd = INFINITY;
+                    if (j < pn) {
+                        float cx, cy, cz;
+                        if (kLayout == SNB200_BNC) {
+                            cx = s_pts[j * 3 + 0]; cy = s_pts[j * 3 + 1]; cz = s_pts[j * 3 + 2];
+                        } else {
+                            cx = s_pts[j]; cy = s_pts[tile_cap + j]; cz = s_pts[2 * tile_cap + j];
+                        }
+                        dd = sqdist<kFma>(cx - qx, cy - qy, cz - qz);  // (dataset - query), tf_grouping.py:84
+                    }
+                    d[u] = dd;
+                    mn = (dd < mn) ? dd : mn;
+                }
+                SNB_KNN_BOUND(mn);
+#pragma unroll
+                for (int u = 0; u < 32; u++) {
+                    unsigned mask = __ballot_sync(kFullMask, d[u] < thr);
+                    if (mask) {
+                        while (mask) {
+                            const int src = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float v = __shfl_sync(kFullMask, d[u], src);
+                            const int vi = p0 + u * 32 + src;
+                            SNB_KNN_INSERT(v, vi);
+                        }
+                        thr = fminf(thr, __shfl_sync(kFullMask, lv, k - 1));
+                    }
+                }
+            } else if (live) {
+                // Generic path (tiles of up to kSpTile points): bound pass, then the distances are recomputed (bit-identical).
                 float mn = INFINITY;
 #pragma unroll 4
                 for (int j = lane; j < pn; j += 32) {
@@ -106,19 +167,7 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
                     const float dd = sqdist<kFma>(cx - qx, cy - qy, cz - qz);
                     mn = (dd < mn) ? dd : mn;
                 }
-                int rank = 0;   // position of my minimum among the 32 (ties by lane)
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float o = __shfl_sync(kFullMask, mn, j);
-                    rank += (o < mn || (o == mn && j < lane)) ? 1 : 0;
-                }
-                const unsigned kth = __ballot_sync(kFullMask, rank == k - 1);
-                if (kth) {      // (no lane has that rank only when NaNs break the ordering: keep the running bound)
-                    const float tau = __shfl_sync(kFullMask, mn, __ffs(kth) - 1);
-                    if (tau < INFINITY) thr = fminf(thr, __uint_as_float(__float_as_uint(tau) + 1u));   // admit d <= tau
-                }
-            }
-            if (live) {
+                SNB_KNN_BOUND(mn);
                 for (int base = 0; base < pn; base += 128) {
                     float d[4];
 #pragma unroll
@@ -132,7 +181,7 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
                             } else {
                                 cx = s_pts[j]; cy = s_pts[tile_cap + j]; cz = s_pts[2 * tile_cap + j];
                             }
-                            dd = sqdist<kFma>(cx - qx, cy - qy, cz - qz);  // (dataset - query), tf_grouping.py:84
+                            dd = sqdist<kFma>(cx - qx, cy - qy, cz - qz);
                         }
                         d[u] = dd;
                     }
@@ -145,16 +194,15 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
                                 mask &= mask - 1;
                                 const float v = __shfl_sync(kFullMask, d[u], src);
                                 const int vi = p0 + base + u * 32 + src;
-                                const float up_v = __shfl_up_sync(kFullMask, lv, 1);
-                                const int up_i = __shfl_up_sync(kFullMask, li, 1);
-                                if (lane > 0 && v < up_v) { lv = up_v; li = up_i; }
-                                else if (v < lv) { lv = v; li = vi; }
+                                SNB_KNN_INSERT(v, vi);
                             }
                             thr = fminf(thr, __shfl_sync(kFullMask, lv, k - 1));
                         }
                     }
                 }
             }
+#undef SNB_KNN_INSERT
+#undef SNB_KNN_BOUND
         }
         if (!live) continue;
 
@@ -164,6 +212,11 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
         li = min(li, n - 1);  // only reachable with NaN/Inf coordinates (nothing ever beat +inf): stay in bounds
         if (P.knn_idx && has) P.knn_idx[o] = li;
         if (P.knn_val && has) P.knn_val[o] = lv;
+        if (lane == 0) {   // the first neighbour is the nn_distance result of this query (same arithmetic, same tie rule)
+            if (P.nn_dist) P.nn_dist[(size_t)bi * m + qi] = lv;
+            if (P.nn_idx) P.nn_idx[(size_t)bi * m + qi] = li;
+            if (acc_sum) { *acc_sum += lv; *acc_max = fmaxf(*acc_max, lv); }
+        }
         if (!P.proj && !P.prop && !P.weights && !P.dist_over_sigma) continue;
 
         // neighbour coordinates: from global (L2-resident; the tile in shared memory may be a later one)

@@ -35,6 +35,7 @@ int launch_knn_softproj(int b, int n, int m, int k, int layout, const float *poi
     P.b = b; P.n = n; P.m = m; P.k = k; P.f = f;
     P.points = points; P.query = query; P.sigma = sigma; P.sigma_mode = sigma_mode; P.sigma_floor = sigma_floor; P.feats = feats; P.hard = hard;
     P.proj = proj; P.prop = prop; P.knn_idx = knn_idx; P.knn_val = knn_val; P.weights = weights; P.dist_over_sigma = dist_over_sigma;
+    P.nn_dist = nullptr; P.nn_idx = nullptr;
     // one query per warp until the grid exceeds ~8 CTAs per SM, then amortise the tile staging over more queries
     int qpw = 1;
     while ((long long)b * ((m + kSpWarps * qpw - 1) / (kSpWarps * qpw)) > 8ll * kNumSMs && qpw < 16) qpw *= 2;

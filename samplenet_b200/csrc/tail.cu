@@ -21,6 +21,8 @@ struct TailParams {
     unsigned smem_floats;   // dynamic shared memory available to the final reduction
 };
 
+constexpr int kTailQ = 2;   // queries register-blocked per thread in the input->generated scan
+
 template <bool kFma>
 __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__ TailParams P)
 {
@@ -29,24 +31,28 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     __shared__ float s_rs[8], s_rm[8];
     __shared__ unsigned s_ticket;
     // 1-D grid, projection CTAs first: they are the long pole (a dependent top-k chain per query), so they must all be in the
-    // first wave; the short Chamfer tiles fill in behind them.
+    // first wave; the short Chamfer tiles fill in behind them.  The projection role also IS the generated->input Chamfer
+    // direction: the nearest neighbour of a query is lane 0 of its top-k list (same arithmetic, same lowest-index tie rule), so
+    // dist1 / idx1 and their loss reductions come out of it for free and only the input->generated direction is scanned separately.
     const int n_knn = P.b * P.knn_ctas;
-    if ((int)blockIdx.x < n_knn) {   // ---- role A: projection
-        knn_softproj_body<SNB200_BNC, kFma>(P.sp, (int)blockIdx.x % P.knn_ctas, (int)blockIdx.x / P.knn_ctas, s_dyn, &bar);
-        return;
-    }
-    // ---- role B: one Chamfer tile
-    const int ntiles = P.ch.d[0].tiles + P.ch.d[1].tiles;
-    const int bi = ((int)blockIdx.x - n_knn) / ntiles;
-    const int cx = ((int)blockIdx.x - n_knn) % ntiles;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
+    const int ntiles = P.knn_ctas + P.ch.d[1].tiles;      // partial slots per cloud: projection CTAs, then direction-1 tiles
     float my_sum = 0.f, my_max = -INFINITY;
-    if (cx < P.ch.d[0].tiles) chamfer_dir<1, kFma>(P.ch.d[0], cx, bi, s_dyn, &bar, &my_sum, &my_max);
-    else chamfer_dir<1, kFma>(P.ch.d[1], cx - P.ch.d[0].tiles, bi, s_dyn, &bar, &my_sum, &my_max);
+    int bi, slot;
+    if ((int)blockIdx.x < n_knn) {   // ---- role A: projection + direction 0
+        bi = (int)blockIdx.x / P.knn_ctas;
+        slot = (int)blockIdx.x % P.knn_ctas;
+        knn_softproj_body<SNB200_BNC, kFma>(P.sp, slot, bi, s_dyn, &bar, &my_sum, &my_max);
+    } else {                         // ---- role B: one tile of direction 1
+        bi = ((int)blockIdx.x - n_knn) / P.ch.d[1].tiles;
+        const int cx = ((int)blockIdx.x - n_knn) % P.ch.d[1].tiles;
+        slot = P.knn_ctas + cx;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        chamfer_dir<kTailQ, kFma>(P.ch.d[1], cx, bi, s_dyn, &bar, &my_sum, &my_max);
+    }
     // CTA partials (fixed order: warp shuffle tree, then warps in index order)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     my_sum = warp_sum(my_sum);
@@ -56,7 +62,7 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     if (threadIdx.x == 0) {
         float ts = 0.f, tm = -INFINITY;
         for (int w = 0; w < 8; w++) { ts += s_rs[w]; tm = fmaxf(tm, s_rm[w]); }
-        float *pp = P.partial + ((size_t)bi * ntiles + cx) * 2;
+        float *pp = P.partial + ((size_t)bi * ntiles + slot) * 2;
         pp[0] = ts; pp[1] = tm;
         __threadfence();
         s_ticket = atomicAdd(P.ticket, 1u);
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     __threadfence();
     __shared__ float s_a[256], s_b[256], s_c[256];
     float a1 = 0.f, amax = 0.f, a2 = 0.f;
-    const int t0 = P.ch.d[0].tiles;
+    const int t0 = P.knn_ctas;
     float2 *s_p = reinterpret_cast<float2 *>(s_dyn);
     const int cap_clouds = max(1, (int)(P.smem_floats / 2) / ntiles);           // clouds per shared-memory pass
     for (int cbase = 0; cbase < P.b; cbase += cap_clouds) {
@@ -112,13 +118,13 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
 }
 
 // One CTA per SM per direction is enough here: the grid also carries the projection CTAs and should stay within a single wave.
-static void tail_plan_dir(ChamferDir &D, int b) { plan_chamfer_dir(D, b, 1, kNumSMs); }
+static void tail_plan_dir(ChamferDir &D, int b) { plan_chamfer_dir(D, b, kTailQ, kNumSMs); }
 
 size_t tail_workspace_bytes(int b, int n_samp, int n_ref)
 {
-    ChamferDir d0 = {nullptr, nullptr, nullptr, nullptr, n_samp, n_ref, 1, 0}, d1 = {nullptr, nullptr, nullptr, nullptr, n_ref, n_samp, 1, 0};
-    tail_plan_dir(d0, b); tail_plan_dir(d1, b);
-    return (size_t)b * (d0.tiles + d1.tiles) * 2 * sizeof(float);
+    ChamferDir d1 = {nullptr, nullptr, nullptr, nullptr, n_ref, n_samp, 1, 0};
+    tail_plan_dir(d1, b);
+    return (size_t)b * ((n_samp + kSpWarps - 1) / kSpWarps + d1.tiles) * 2 * sizeof(float);
 }
 
 int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, const float *samp, const float *sigma, int sigma_mode, float sigma_floor,
@@ -134,7 +140,9 @@ int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, con
     P.knn_ctas = (n_samp + kSpWarps - 1) / kSpWarps;
     P.ch.d[0] = {samp, ref, dist1, idx1, n_samp, n_ref, 1, 0};
     P.ch.d[1] = {ref, samp, dist2, idx2, n_ref, n_samp, 1, 0};
-    tail_plan_dir(P.ch.d[0], b); tail_plan_dir(P.ch.d[1], b);
+    P.ch.d[0].tiles = 0;            // direction 0 (generated -> input) rides on the projection role
+    S.nn_dist = dist1; S.nn_idx = idx1;
+    tail_plan_dir(P.ch.d[1], b);
     P.b = b; P.n_samp = n_samp; P.n_ref = n_ref; P.w21 = w21; P.partial = partial; P.ticket = ticket; P.out4 = out4;
     size_t smem = (size_t)min(max(n_ref, n_samp), kSpTile) * 3 * sizeof(float);
     if (smem < 4096) smem = 4096;
@@ -146,7 +154,7 @@ int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, con
         cudaFuncSetAttribute(tail_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(tail_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    dim3 grid((unsigned)((long long)b * (P.knn_ctas + P.ch.d[0].tiles + P.ch.d[1].tiles)));
+    dim3 grid((unsigned)((long long)b * (P.knn_ctas + P.ch.d[1].tiles)));
     if (flags & SNB200_DIST_UNFUSED) tail_fused_kernel<false><<<grid, 256, smem, stream>>>(P);
     else tail_fused_kernel<true><<<grid, 256, smem, stream>>>(P);
     return check_launch("project_and_simplification_loss");

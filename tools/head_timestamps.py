@@ -8,7 +8,7 @@ x = torch.rand(32, 1024, 3, device="cuda") - 0.5
 conv, fc = net._layer_specs()
 with torch.no_grad():
     for _ in range(5):
-        sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)
+        sb.ops.generator_forward(x, "bnc", conv, fc, True, 64, separate_head=True)
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 64)()
     sb._lib.lib().snb200_debug_head_timestamps(ctypes.addressof(buf))
