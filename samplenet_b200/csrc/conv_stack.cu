@@ -197,6 +197,25 @@ __device__ __forceinline__ void cs_grid_barrier(unsigned *counter, unsigned targ
     __syncthreads();
 }
 
+// Flag-in-data exchange lines ("LL"): a value and its validity flag travel in ONE 8-byte store, so a consumer that finds the flag
+// set has the value -- no fence, no separate flag word.  Loads bypass L1 (volatile).
+__device__ __forceinline__ void cs_ll_store(uint2 *p, float v)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(1u) : "memory");
+}
+__device__ __forceinline__ uint2 cs_ll_load1(const uint2 *p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 cs_ll_load2(const uint2 *p)   // two consecutive lines, 16-byte aligned
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // Column reduction of a 32x32 block held one row per lane: after the 5 halving steps lane i holds the combined value of
 // column i (31 shuffles instead of 160).  OP: 0 = sum, 1 = max, 2 = min.
 template <int OP>
@@ -648,19 +667,50 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // ================================================================================================================
     if (!P.fuse_head) return;
     const HeadParams &H = P.H;
+    // shared memory of the head (the conv stack's buffers are dead): input row group | partial sums | first weight rows of every layer
     float *s_in = reinterpret_cast<float *>(smem_raw);                 // [32 rows][c_in + 1] one row group of the input
-    int hcmax = H.c_feat;
-    for (int l = 0; l < H.num_fc; l++) hcmax = max(hcmax, H.fc[l].c_in);
+    int hcmax = H.c_feat, hcsum = 0;
+    for (int l = 0; l < H.num_fc; l++) { hcmax = max(hcmax, H.fc[l].c_in); hcsum += H.fc[l].c_in; }
     float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33;   // [8 K slices][8 channels][32 rows]
+    float *s_wall = s_part + 8 * 8 * 32;                                       // per layer [8 channels][c_in] weight rows
+    __shared__ uint64_t hbar[SNB200_MAX_FC_LAYERS];
     const double inv_cnt_h = 1.0 / H.count;
     CS_TS(36);
+    // ---- weights do not depend on activations: the first 8-channel group of EVERY layer is fetched now, one TMA bulk copy per
+    //      layer (the 8 rows are contiguous in HBM), completion on one mbarrier per layer; nobody touches them before the layer's math
+    if (tid == 0) {
+        for (int l = 0; l < H.num_fc; l++) mbar_init(&hbar[l], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        fence_proxy_async();   // the smem region was written through the generic proxy by the conv stack
+        int woff = 0;
+        for (int l = 0; l < H.num_fc; l++) {
+            const HeadLayer &L = H.fc[l];
+            const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
+            const int lo = blockIdx.x * cpc, hi = min(L.c_out, lo + cpc);
+            const bool tma_ok = (L.c_in & 3) == 0 && (hcmax & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+            if (lo < hi && tma_ok) {
+                const uint32_t bytes = (uint32_t)min(8, hi - lo) * L.c_in * 4u;
+                mbar_expect_tx(&hbar[l], bytes);
+                tma_load_1d(s_wall + woff, L.weight + (size_t)lo * L.c_in, bytes, &hbar[l]);
+            }
+            woff += 8 * L.c_in;
+        }
+    }
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
     // no grid barrier has been crossed yet.
     if (!(need_stats && P.L[P.num_layers - 1].has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);
-    // ---- phase P: pooled feature, spread over the grid; running statistics of the conv stack, spread over the grid
+    // From here on CTAs exchange activations point to point with flag-in-data lines (the NCCL "LL" idea): every value travels as an
+    // 8-byte {value, 1} pair written by ONE store; a consumer spins on the data lines themselves, so a value is usable one L2 round
+    // trip after it was stored -- no fence, no flag word, no grid barrier.  The exchange buffers are zeroed by the launch's memset.
+    //   stage 0 = the pooled feature, stage l+1 = the output of FC layer l
+    // ---- phase P: pooled feature, spread over the grid
     {
         const int total = H.b * H.c_feat;
         const int gt = blockIdx.x * kCsThreadsAll + tid, gn = G * kCsThreadsAll;
+        uint2 *ll0 = H.ll[0];
         for (int e = gt; e < total; e += gn) {
             const int bi = e / H.c_feat, c = e % H.c_feat;
             float mx = -INFINITY, mn = INFINITY;
@@ -691,30 +741,28 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);
             }
             if (H.last_relu) v = fmaxf(v, 0.f);
+            cs_ll_store(ll0 + e, v);
             H.feat[e] = v;
         }
     }
     CS_TS(37);
-    float *s_wh = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33 + 8 * 8 * 32;   // [8 channels][c_in] weight rows
-    if (H.num_fc > 0) {   // weights do not depend on activations: stage layer 1's rows while the barrier completes
-        const HeadLayer &L0 = H.fc[0];
-        const int cpc0 = max(8, (((L0.c_out + G - 1) / G + 7) / 8) * 8);
-        const int lo0 = blockIdx.x * cpc0, hi0 = min(L0.c_out, lo0 + cpc0);
-        if (lo0 < hi0) cs_head_stage_weights(L0, lo0, min(8, hi0 - lo0), s_wh, tid, producer);
-    }
-    cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // the pooled feature of every cloud is in place
     CS_TS(38);
 
-    const float *cur = H.feat;
+    int woff = 0;
     for (int l = 0; l < H.num_fc; l++) {
         const HeadLayer &L = H.fc[l];
         const bool lastfc = (l == H.num_fc - 1);
         float *dst = lastfc ? H.out : H.act[l & 1];
+        uint2 *lldst = lastfc ? nullptr : H.ll[l + 1];
+        const uint2 *llsrc = H.ll[l];
         const int c_in = L.c_in;
+        float *s_wh = s_wall + woff;
+        woff += 8 * c_in;
         // 8 output channels per pass and per CTA: few enough CTAs read the (shared) input that L2 does not serialise on it
         const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
         const int c_lo = blockIdx.x * cpc, c_hi = min(L.c_out, c_lo + cpc);
         const int nrg = (H.b + 31) >> 5;
+        const bool w_tma = (c_in & 3) == 0 && (hcmax & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
         CS_TS(39 + l * 6 + 0);
         for (int cb = c_lo; cb < c_hi; cb += 8) {                     // one group of 8 channels at a time
             const int nch = min(8, c_hi - cb);
@@ -726,7 +774,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             const float pbet = (cvw && L.has_bn) ? __ldg(L.beta + cw) : 0.f;
             const float prm = (cvw && L.has_bn && L.run_mean) ? L.run_mean[cw] : 0.f;
             const float prv = (cvw && L.has_bn && L.run_var) ? L.run_var[cw] : 1.f;
-            if (cb != c_lo) {   // (the first group of every layer was staged before the preceding grid barrier)
+            if (cb != c_lo || !w_tma) {   // (the first group of every layer was fetched by TMA at the start of the head)
                 __syncthreads();
                 cs_head_stage_weights(L, cb, nch, s_wh, tid, producer);
             }
@@ -737,37 +785,58 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             for (int gq = 0; gq < 8; gq++) {
                 if (gq < nrg) {
                     const int r0 = gq * 32, rn = min(32, H.b - r0);
-                    if (gq > 0) __syncthreads();
-                    if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride: coalesced 16-byte loads (lanes along k),
-                                      // conflict-free scalar stores, conflict-free lane = row reads
+                    if (gq > 0 || cb != c_lo || l > 0) __syncthreads();   // the previous user of s_in / s_part is done
+                    if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride (conflict-free lane = row reads).  Lanes run
+                                      // along k (8 lanes = one 128-byte run of {value, flag} pairs), a thread's 8 lines are requested
+                                      // together and re-requested until every flag is set.
                         const int ldi = c_in + 1;
-                        if ((c_in & 3) == 0) {
-                            const int q4 = c_in >> 2, total = 32 * q4;
-                            for (int e0 = tid; e0 < total; e0 += kCsProducers * 4) {
-                                float4 v[4];
+                        if ((c_in & 1) == 0) {
+                            const int h2 = c_in >> 1, items = 32 * h2;           // item = (row, pair of channels) = one 16-byte line
+                            for (int i0 = tid; i0 < items; i0 += kCsProducers * 8) {
+                                uint4 v[8];
+                                unsigned spin = 0;
+                                bool ok;
+                                do {
+                                    ok = true;
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const int e = e0 + u * kCsProducers;
-                                    const int r = e / q4, kq = e - r * q4;
-                                    v[u] = (e < total && r < rn) ? __ldcg(reinterpret_cast<const float4 *>(cur + (size_t)(r0 + r) * c_in) + kq) : make_float4(0, 0, 0, 0);
-                                }
+                                    for (int u = 0; u < 8; u++) {
+                                        const int i = i0 + u * kCsProducers;
+                                        const int r = i / h2, pq = i - r * h2;
+                                        if (i < items && r < rn) v[u] = cs_ll_load2(llsrc + (size_t)(r0 + r) * c_in + 2 * pq);
+                                        else v[u] = make_uint4(0u, 1u, 0u, 1u);
+                                    }
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const int e = e0 + u * kCsProducers;
-                                    if (e < total) {
-                                        const int r = e / q4, kq = e - r * q4;
-                                        float *d = s_in + r * ldi + kq * 4;
-                                        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                                    for (int u = 0; u < 8; u++) ok = ok && (v[u].y == 1u) && (v[u].w == 1u);
+                                    if (++spin > (1u << 24)) __trap();
+                                } while (!ok);
+#pragma unroll
+                                for (int u = 0; u < 8; u++) {
+                                    const int i = i0 + u * kCsProducers;
+                                    if (i < items) {
+                                        const int r = i / h2, pq = i - r * h2;
+                                        float *d = s_in + r * ldi + 2 * pq;
+                                        d[0] = __uint_as_float(v[u].x); d[1] = __uint_as_float(v[u].z);
                                     }
                                 }
                             }
                         } else {
                             for (int e = tid; e < 32 * c_in; e += kCsProducers) {
                                 const int r = e / c_in, k = e - r * c_in;
-                                s_in[r * ldi + k] = (r < rn) ? __ldcg(cur + (size_t)(r0 + r) * c_in + k) : 0.f;
+                                float xv = 0.f;
+                                if (r < rn) {
+                                    uint2 q;
+                                    unsigned spin = 0;
+                                    do {
+                                        q = cs_ll_load1(llsrc + (size_t)(r0 + r) * c_in + k);
+                                        if (++spin > (1u << 24)) __trap();
+                                    } while (q.y != 1u);
+                                    xv = __uint_as_float(q.x);
+                                }
+                                s_in[r * ldi + k] = xv;
                             }
                         }
                     }
+                    if (cb == c_lo && gq == 0 && w_tma) mbar_wait(&hbar[l], 0);   // this layer's first weight rows have landed
                     __syncthreads();
                     CS_TS(39 + l * 6 + 1);
                     if (producer) {   // warp -> (channel quad = warp & 1, K eighth = warp >> 1); lane = row
@@ -798,7 +867,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     }
                     __syncthreads();
                     CS_TS(39 + l * 6 + 2);
-                    if (warp < 8)   // fixed-order combination of the 4 K quarters: warp = channel, lane = row
+                    if (warp < 8)   // fixed-order combination of the 8 K eighths: warp = channel, lane = row
                     {
                         float t = 0.f;
 #pragma unroll
@@ -843,22 +912,17 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     if (r < H.b) {
                         float v = L.has_bn ? fmaf(yv[gq], scale, shift) : yv[gq];
                         if (L.relu) v = fmaxf(v, 0.f);
-                        const int oc = (lastfc && H.out_inner > 0) ? (cw % H.out_inner) * (L.c_out / H.out_inner) + cw / H.out_inner : cw;
-                        dst[(size_t)r * L.c_out + oc] = v;
+                        if (lastfc) {
+                            const int oc = (H.out_inner > 0) ? (cw % H.out_inner) * (L.c_out / H.out_inner) + cw / H.out_inner : cw;
+                            dst[(size_t)r * L.c_out + oc] = v;
+                        } else {
+                            cs_ll_store(lldst + (size_t)r * L.c_out + cw, v);   // the next layer's consumers spin on these lines
+                        }
                     }
                 }
             }
         }
-        cur = dst;
         CS_TS(39 + l * 6 + 3);
-        if (!lastfc) {
-            __syncthreads();                                           // everyone is done with this layer's weight rows
-            const HeadLayer &Ln = H.fc[l + 1];
-            const int cpcn = max(8, (((Ln.c_out + G - 1) / G + 7) / 8) * 8);
-            const int lon = blockIdx.x * cpcn, hin = min(Ln.c_out, lon + cpcn);
-            if (lon < hin) cs_head_stage_weights(Ln, lon, min(8, hin - lon), s_wh, tid, producer);
-            cs_grid_barrier(P.barrier, ++barrier_epoch * G);           // the next layer reads every CTA's channels
-        }
         CS_TS(39 + l * 6 + 4);
     }
     if (blockIdx.x == G - 1 && tid < H.num_counters) *H.counters[tid] += 1;
@@ -929,7 +993,9 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     if (head) {   // the fused tail reuses the same dynamic shared memory: input tile + partial sums + 8 weight rows
         int hcmax = head->c_feat;
         for (int l = 0; l < head->num_fc; l++) hcmax = max(hcmax, head->fc[l].c_in);
-        const size_t hs = ((size_t)hcmax * 33 + 2048 + (size_t)8 * hcmax) * sizeof(float) + 1024;
+        size_t hcsum = 0;
+        for (int l = 0; l < head->num_fc; l++) hcsum += head->fc[l].c_in;
+        const size_t hs = ((size_t)hcmax * 33 + 2048 + (size_t)8 * hcsum) * sizeof(float) + 1024;
         if (hs > 200 * 1024) { set_error("conv stack: FC width %d too large for the fused head", hcmax); return SNB200_EUNSUPPORTED; }
         smem = max(smem, hs);
     }
