@@ -197,19 +197,23 @@ __device__ __forceinline__ void cs_grid_barrier(unsigned *counter, unsigned targ
     __syncthreads();
 }
 
-// Flag-in-data exchange lines ("LL"): a value and its validity flag travel in ONE 8-byte store, so a consumer that finds the flag
-// set has the value -- no fence, no separate flag word.  Loads bypass L1 (volatile).
-__device__ __forceinline__ void cs_ll_store(uint2 *p, float v)
+// Self-validating exchange words: the exchange buffers are zeroed by the launch's memset and a producer never stores the bit
+// pattern 0 (+0.0f travels as -0.0f, which is the same number to every consumer), so "word != 0" means "value present": a
+// 4-byte store is atomic, a consumer spins on the data itself, and a value is usable one L2 round trip after it was stored -- no
+// fence, no flag word, no grid barrier.  Loads bypass L1 (volatile).
+__device__ __forceinline__ void cs_xchg_store(float *p, float v)
 {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(1u) : "memory");
+    unsigned u = __float_as_uint(v);
+    if (u == 0u) u = 0x80000000u;
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(u) : "memory");
 }
-__device__ __forceinline__ uint2 cs_ll_load1(const uint2 *p)
+__device__ __forceinline__ unsigned cs_xchg_load1(const float *p)
 {
-    uint2 v;
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint4 cs_ll_load2(const uint2 *p)   // two consecutive lines, 16-byte aligned
+__device__ __forceinline__ uint4 cs_xchg_load4(const float *p)   // four consecutive words, 16-byte aligned
 {
     uint4 v;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -675,6 +679,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     float *s_wall = s_part + 8 * 8 * 32;                                       // per layer [8 channels][c_in] weight rows
     __shared__ uint64_t hbar[SNB200_MAX_FC_LAYERS];
     const double inv_cnt_h = 1.0 / H.count;
+    const float inv_b = 1.0f / (float)H.b;
     CS_TS(36);
     // ---- weights do not depend on activations: the first 8-channel group of EVERY layer is fetched now, one TMA bulk copy per
     //      layer (the 8 rows are contiguous in HBM), completion on one mbarrier per layer; nobody touches them before the layer's math
@@ -702,15 +707,14 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
     // no grid barrier has been crossed yet.
     if (!(need_stats && P.L[P.num_layers - 1].has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);
-    // From here on CTAs exchange activations point to point with flag-in-data lines (the NCCL "LL" idea): every value travels as an
-    // 8-byte {value, 1} pair written by ONE store; a consumer spins on the data lines themselves, so a value is usable one L2 round
-    // trip after it was stored -- no fence, no flag word, no grid barrier.  The exchange buffers are zeroed by the launch's memset.
+    // From here on CTAs exchange activations point to point through self-validating words (cs_xchg_*): consumers spin on the data
+    // itself -- no fence, no flag word, no grid barrier.  The exchange buffers are zeroed by the launch's memset.
     //   stage 0 = the pooled feature, stage l+1 = the output of FC layer l
     // ---- phase P: pooled feature, spread over the grid
     {
         const int total = H.b * H.c_feat;
         const int gt = blockIdx.x * kCsThreadsAll + tid, gn = G * kCsThreadsAll;
-        uint2 *ll0 = H.ll[0];
+        float *ll0 = H.ll[0];
         for (int e = gt; e < total; e += gn) {
             const int bi = e / H.c_feat, c = e % H.c_feat;
             float mx = -INFINITY, mn = INFINITY;
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);
             }
             if (H.last_relu) v = fmaxf(v, 0.f);
-            cs_ll_store(ll0 + e, v);
+            cs_xchg_store(ll0 + e, v);
             H.feat[e] = v;
         }
     }
@@ -753,8 +757,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         const HeadLayer &L = H.fc[l];
         const bool lastfc = (l == H.num_fc - 1);
         float *dst = lastfc ? H.out : H.act[l & 1];
-        uint2 *lldst = lastfc ? nullptr : H.ll[l + 1];
-        const uint2 *llsrc = H.ll[l];
+        float *lldst = lastfc ? nullptr : H.ll[l + 1];
+        const float *llsrc = H.ll[l];
         const int c_in = L.c_in;
         float *s_wh = s_wall + woff;
         woff += 8 * c_in;
@@ -787,35 +791,37 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     const int r0 = gq * 32, rn = min(32, H.b - r0);
                     if (gq > 0 || cb != c_lo || l > 0) __syncthreads();   // the previous user of s_in / s_part is done
                     if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride (conflict-free lane = row reads).  Lanes run
-                                      // along k (8 lanes = one 128-byte run of {value, flag} pairs), a thread's 8 lines are requested
-                                      // together and re-requested until every flag is set.
+                                      // along k (coalesced 16-byte loads), a thread's loads are requested together and re-requested
+                                      // until every word is present.
                         const int ldi = c_in + 1;
-                        if ((c_in & 1) == 0) {
-                            const int h2 = c_in >> 1, items = 32 * h2;           // item = (row, pair of channels) = one 16-byte line
-                            for (int i0 = tid; i0 < items; i0 += kCsProducers * 8) {
-                                uint4 v[8];
+                        if ((c_in & 3) == 0) {
+                            const int q4 = c_in >> 2, items = 32 * q4;           // item = (row, 4 channels) = one 16-byte load
+                            for (int i0 = tid; i0 < items; i0 += kCsProducers * 4) {
+                                uint4 v[4];
                                 unsigned spin = 0;
                                 bool ok;
                                 do {
                                     ok = true;
 #pragma unroll
-                                    for (int u = 0; u < 8; u++) {
+                                    for (int u = 0; u < 4; u++) {
                                         const int i = i0 + u * kCsProducers;
-                                        const int r = i / h2, pq = i - r * h2;
-                                        if (i < items && r < rn) v[u] = cs_ll_load2(llsrc + (size_t)(r0 + r) * c_in + 2 * pq);
-                                        else v[u] = make_uint4(0u, 1u, 0u, 1u);
+                                        const int r = i / q4, kq = i - r * q4;
+                                        if (i < items && r < rn) v[u] = cs_xchg_load4(llsrc + (size_t)(r0 + r) * c_in + 4 * kq);
+                                        else v[u] = make_uint4(1u, 1u, 1u, 1u);
                                     }
 #pragma unroll
-                                    for (int u = 0; u < 8; u++) ok = ok && (v[u].y == 1u) && (v[u].w == 1u);
+                                    for (int u = 0; u < 4; u++) ok = ok && v[u].x != 0u && v[u].y != 0u && v[u].z != 0u && v[u].w != 0u;
                                     if (++spin > (1u << 24)) __trap();
                                 } while (!ok);
 #pragma unroll
-                                for (int u = 0; u < 8; u++) {
+                                for (int u = 0; u < 4; u++) {
                                     const int i = i0 + u * kCsProducers;
                                     if (i < items) {
-                                        const int r = i / h2, pq = i - r * h2;
-                                        float *d = s_in + r * ldi + 2 * pq;
-                                        d[0] = __uint_as_float(v[u].x); d[1] = __uint_as_float(v[u].z);
+                                        const int r = i / q4, kq = i - r * q4;
+                                        float *d = s_in + r * ldi + 4 * kq;
+                                        const bool live = r < rn;
+                                        d[0] = live ? __uint_as_float(v[u].x) : 0.f; d[1] = live ? __uint_as_float(v[u].y) : 0.f;
+                                        d[2] = live ? __uint_as_float(v[u].z) : 0.f; d[3] = live ? __uint_as_float(v[u].w) : 0.f;
                                     }
                                 }
                             }
@@ -824,13 +830,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                                 const int r = e / c_in, k = e - r * c_in;
                                 float xv = 0.f;
                                 if (r < rn) {
-                                    uint2 q;
-                                    unsigned spin = 0;
+                                    unsigned q, spin = 0;
                                     do {
-                                        q = cs_ll_load1(llsrc + (size_t)(r0 + r) * c_in + k);
+                                        q = cs_xchg_load1(llsrc + (size_t)(r0 + r) * c_in + k);
                                         if (++spin > (1u << 24)) __trap();
-                                    } while (q.y != 1u);
-                                    xv = __uint_as_float(q.x);
+                                    } while (q == 0u);
+                                    xv = __uint_as_float(q);
                                 }
                                 s_in[r * ldi + k] = xv;
                             }
@@ -876,36 +881,39 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     }
                 }
             }
+            CS_TS(39 + l * 6 + 3);
             if (cvw) {
                 float scale = 1.f, shift = 0.f;
 #pragma unroll
                 for (int gq = 0; gq < 8; gq++) yv[gq] += pbias;
+                float bn_mean = 0.f, bn_q = 0.f;
                 if (L.has_bn) {
                     float mean, var;
                     if (H.training) {
-                        float sm = 0.f;
+                        // batch statistics in one shuffle tree: deviations from a pivot sample (row 0), sum and sum of squares reduced
+                        // together; var = (S2 - S1^2/n)/n is well conditioned because the pivot lies inside the data
+                        const float pivot = __shfl_sync(kFullMask, yv[0], 0);
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                         for (int gq = 0; gq < 8; gq++)
-                            if (gq * 32 + lane < H.b) sm += yv[gq];
-                        mean = warp_sum(sm) / (float)H.b;
-                        float qq = 0.f;
+                            if (gq * 32 + lane < H.b) { const float d = yv[gq] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
 #pragma unroll
-                        for (int gq = 0; gq < 8; gq++)
-                            if (gq * 32 + lane < H.b) { const float d = yv[gq] - mean; qq = fmaf(d, d, qq); }
-                        qq = warp_sum(qq);
-                        var = qq / (float)H.b;
-                        if (lane == 0) {
-                            const float unb = H.b > 1 ? qq / (float)(H.b - 1) : var;
-                            if (L.run_mean) L.run_mean[cw] = (1.f - L.momentum) * prm + L.momentum * mean;
-                            if (L.run_var) L.run_var[cw] = (1.f - L.momentum) * prv + L.momentum * unb;
+                        for (int o = 16; o > 0; o >>= 1) {
+                            s1 += __shfl_xor_sync(kFullMask, s1, o);
+                            s2 += __shfl_xor_sync(kFullMask, s2, o);
                         }
+                        mean = fmaf(s1, inv_b, pivot);
+                        bn_q = fmaxf(fmaf(-s1 * inv_b, s1, s2), 0.f);        // sum of squared deviations from the mean
+                        var = bn_q * inv_b;
+                        bn_mean = mean;
                     } else {
                         mean = prm; var = prv;
                     }
-                    const float invstd = 1.0f / sqrtf(var + L.eps);
+                    const float invstd = rsqrtf(var + L.eps);
                     scale = pgam * invstd;
                     shift = pbet - mean * scale;
                 }
+                CS_TS(39 + l * 6 + 4);
 #pragma unroll
                 for (int gq = 0; gq < 8; gq++) {
                     const int r = gq * 32 + lane;
@@ -916,14 +924,18 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             const int oc = (H.out_inner > 0) ? (cw % H.out_inner) * (L.c_out / H.out_inner) + cw / H.out_inner : cw;
                             dst[(size_t)r * L.c_out + oc] = v;
                         } else {
-                            cs_ll_store(lldst + (size_t)r * L.c_out + cw, v);   // the next layer's consumers spin on these lines
+                            cs_xchg_store(lldst + (size_t)r * L.c_out + cw, v);   // the next layer's consumers spin on these words
                         }
                     }
                 }
+                if (L.has_bn && H.training && lane == 0) {   // running statistics: off the critical path
+                    const float unb = H.b > 1 ? bn_q / (float)(H.b - 1) : bn_q * inv_b;
+                    if (L.run_mean) L.run_mean[cw] = (1.f - L.momentum) * prm + L.momentum * bn_mean;
+                    if (L.run_var) L.run_var[cw] = (1.f - L.momentum) * prv + L.momentum * unb;
+                }
             }
         }
-        CS_TS(39 + l * 6 + 3);
-        CS_TS(39 + l * 6 + 4);
+        CS_TS(39 + l * 6 + 5);
     }
     if (blockIdx.x == G - 1 && tid < H.num_counters) *H.counters[tid] += 1;
     // ---- running statistics of the conv stack: off the critical path, taken by the CTAs from the top of the grid (idle in the

@@ -73,8 +73,8 @@ struct HeadParams {
     int num_counters;
     long long *counters[SNB200_MAX_CONV_LAYERS + SNB200_MAX_FC_LAYERS];
     int dbg;                     // bring-up switches (always 0 in the product): 1 = stop after pooling, 2 = no TMA weight prefetch
-    uint2 *ll[SNB200_MAX_FC_LAYERS + 1];   // fused head: flag-in-data exchange buffers, zero at launch: [0] pooled feature (b, c_feat),
-                                           // [l+1] output of FC layer l (b, c_out) -- {value, 1} pairs
+    float *ll[SNB200_MAX_FC_LAYERS + 1];   // fused head: self-validating exchange buffers, zero at launch: [0] pooled feature (b, c_feat),
+                                           // [l+1] output of FC layer l (b, c_out); a word of 0 means "not stored yet"
 };
 
 // persistent cooperative conv-stack kernel (conv_stack.cu); head != nullptr fuses the pool + FC head into the same launch

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kHeadThreads) fc_head_cluster_kernel(const __g
 struct GenWorkspace {
     float *act[2];
     char *stats_base; size_t stats_bytes;
-    double *mom; unsigned *counter; uint2 *ll[SNB200_MAX_FC_LAYERS + 1];
+    double *mom; unsigned *counter; float *ll[SNB200_MAX_FC_LAYERS + 1];
     double *stats[SNB200_MAX_CONV_LAYERS];
     float *tile_max, *tile_min;
     float *feat;
@@ -378,8 +378,8 @@ static GenWorkspace carve_gen_ws(void *base, int b, int n, int nconv, const snb2
     for (int l = 0; l <= SNB200_MAX_FC_LAYERS; l++) W.ll[l] = nullptr;
     for (int l = 0; l < nfc; l++) {   // exchange buffers of the fused head (zeroed with the statistics): the input of FC layer l
         const int width = (l == 0) ? conv[nconv - 1].c_out : fc[l - 1].c_out;
-        W.ll[l] = reinterpret_cast<uint2 *>(p + off + sb);
-        sb += align_up((size_t)b * width * sizeof(uint2), 256);
+        W.ll[l] = reinterpret_cast<float *>(p + off + sb);
+        sb += align_up((size_t)b * width * sizeof(float), 256);
     }
     W.stats_bytes = sb;
     off += sb;

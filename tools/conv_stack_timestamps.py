@@ -19,7 +19,7 @@ for l in range(4):
         names[3 + l * 8 + i] = "L%d %s" % (l + 2, n)
 names[36] = "head: start"; names[37] = "head: pooled"; names[38] = "head: barrier P done"
 for l in range(4):
-    for i, n in enumerate(["start", "input staged", "partials done", "stored", "barrier done"]):
+    for i, n in enumerate(["start", "input staged", "partials done", "combined", "BN scale/shift", "stored"]):
         names[39 + l * 6 + i] = "FC%d %s" % (l + 1, n)
 prev = t0
 for i in sorted(names):
