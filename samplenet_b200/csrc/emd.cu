@@ -19,23 +19,77 @@ namespace snb {
 
 constexpr int kEmdThreads = 512;
 constexpr int kEmdTile = 1024;  // opposite-side points per shared-memory tile (float4 each: 16 KB)
+constexpr int kEmdLevels = 10;  // tf_approxmatch_g.cu:13: j = 7 ... -2
 
 struct EmdParams {
     int b, n, m;
     int S;           // lanes per row
     const float *xyz1, *xyz2;
     float *match;    // (b, m, n)
-    float *temp;     // (b, 2*(n+m)): remainL[n], remainR[m], ratioL[n], ratioR[m]
+    float *temp;     // per cloud: remainL[n], remainR[m], then per level ratioL[n], ratioR[m]
 };
 
-// Row-parallel reduction: for every row r owned by this CTA group, acc = sum_j f(row r, column j) over all columns.
-// RowSide: 0 => rows are xyz1 points (k, n of them), columns xyz2 (l, m of them);  1 => rows xyz2, columns xyz1.
 __device__ __forceinline__ float emd_sq(float ax, float ay, float az, float bx, float by, float bz)
 {
     const float dx = bx - ax, dy = by - ay, dz = bz - az;
     return dx * dx + dy * dy + dz * dz;
 }
+// 2^x for x <= 0: one MUFU.EX2; results below the normal range flush to zero (they are below 1e-38 of a weight that is <= 1)
+__device__ __forceinline__ float emd_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float emd_level2(int lev)   // level = -4^lev (0 at the last level); exp(level*d) == exp2(level*log2(e)*d)
+{
+    const float level = (lev == -2) ? 0.f : -powf(4.0f, (float)lev);
+    return level * 1.44269504088896340736f;
+}
 
+// Row sums  acc[row] = sum_col exp2(level2 * |row - col|^2) * w[col]  for the rows this thread group owns; the column side (xyz + w as
+// float4) is staged through shared memory in tiles.  A row is shared by S lanes that take the columns j == lane (mod S).
+template <typename F>
+__device__ __forceinline__ void emd_row_pass(int nrows, int ncols, const float *prow, const float *pcol, const float *wcol, float level2, int S,
+                                             int rows_per_pass, int my_row_slot, int l_in, float4 *s_o, F &&finish)
+{
+    for (int r0 = 0; r0 < nrows; r0 += rows_per_pass) {
+        const int r = r0 + my_row_slot;
+        const bool live = r < nrows;
+        float x = 0, y = 0, z = 0;
+        if (live) { x = prow[r * 3 + 0]; y = prow[r * 3 + 1]; z = prow[r * 3 + 2]; }
+        float a0 = 0.f, a1 = 0.f;
+        for (int c0 = 0; c0 < ncols; c0 += kEmdTile) {
+            const int cn = min(kEmdTile, ncols - c0);
+            __syncthreads();
+            for (int c = threadIdx.x; c < cn; c += kEmdThreads)
+                s_o[c] = make_float4(pcol[(c0 + c) * 3 + 0], pcol[(c0 + c) * 3 + 1], pcol[(c0 + c) * 3 + 2], wcol[c0 + c]);
+            __syncthreads();
+            if (live) {
+                int c = l_in;
+#pragma unroll 2
+                for (; c + S < cn; c += 2 * S) {   // two independent accumulation chains
+                    const float4 o0 = s_o[c], o1 = s_o[c + S];
+                    a0 = fmaf(emd_ex2(level2 * emd_sq(x, y, z, o0.x, o0.y, o0.z)), o0.w, a0);
+                    a1 = fmaf(emd_ex2(level2 * emd_sq(x, y, z, o1.x, o1.y, o1.z)), o1.w, a1);
+                }
+                if (c < cn) {
+                    const float4 o0 = s_o[c];
+                    a0 = fmaf(emd_ex2(level2 * emd_sq(x, y, z, o0.x, o0.y, o0.z)), o0.w, a0);
+                }
+            }
+        }
+        float acc = a0 + a1;
+        for (int o = S >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+        if (live && l_in == 0) finish(r, acc);
+    }
+}
+
+// The reference read-modify-writes the (b, m, n) match tensor once per level (10 sweeps, 17 GB at the AE size).  Here the ten
+// levels only update the per-point vectors (the per-level ratioL / ratioR are kept: 10 x (n + m) floats per cloud), and `match`
+// is produced by ONE final pass that re-evaluates the ten weights of a pair in registers, in level order, and writes it once:
+//   match[l][k] = sum_lev exp(level_lev * d(k,l)) * ratioL_lev[k] * ratioR_lev[l]
+// One extra exp per pair and level buys the removal of all match traffic but the final store.
 __global__ void __launch_bounds__(kEmdThreads) approxmatch_kernel(const __grid_constant__ EmdParams P)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -46,13 +100,14 @@ __global__ void __launch_bounds__(kEmdThreads) approxmatch_kernel(const __grid_c
     const float *p1 = P.xyz1 + (size_t)bi * n * 3;
     const float *p2 = P.xyz2 + (size_t)bi * m * 3;
     float *match = P.match + (size_t)bi * n * m;
-    float *remainL = P.temp + (size_t)bi * (n + m) * 2, *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n;
+    float *remainL = P.temp + (size_t)bi * (n + m) * (1 + kEmdLevels), *remainR = remainL + n;
+    float *ratios = remainR + m;   // [level][ratioL (n) | ratioR (m)]
 
     __shared__ float4 s_o[kEmdTile];
 
-    const int rows_per_pass = (csize * kEmdThreads) / S;           // rows the whole cluster handles at once
+    const int rows_per_pass = (csize * kEmdThreads) / S;              // rows the whole cluster handles at once
     const int my_row_slot = (crank * kEmdThreads + threadIdx.x) / S;  // my row within a pass
-    const int l_in = threadIdx.x % S;                               // my lane within the row group
+    const int l_in = threadIdx.x % S;                                 // my lane within the row group
 
     float multiL, multiR;  // tf_approxmatch_g.cu:4-10 (integer division)
     if (n >= m) { multiL = 1; multiR = (float)(n / m); } else { multiL = (float)(m / n); multiR = 1; }
@@ -60,109 +115,77 @@ __global__ void __launch_bounds__(kEmdThreads) approxmatch_kernel(const __grid_c
     for (int j = crank * kEmdThreads + threadIdx.x; j < m; j += csize * kEmdThreads) remainR[j] = multiR;
     cluster.sync();
 
-    for (int lev = 7; lev >= -2; lev--) {
-        // level = -4^lev (0 at the last level); exp(level*d) == exp2(level*log2(e)*d)
-        const float level = (lev == -2) ? 0.f : -powf(4.0f, (float)lev);
-        const float level2 = level * 1.44269504088896340736f;
-        const bool first = (lev == 7);
+    for (int lev = 7, li = 0; lev >= -2; lev--, li++) {
+        const float level2 = emd_level2(lev);
+        float *ratioL = ratios + (size_t)li * (n + m), *ratioR = ratioL + n;
 
         // ---- phase 1 (:27-60): ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level*d) * remainR[l])
-        for (int r0 = 0; r0 < n; r0 += rows_per_pass) {
-            const int k = r0 + my_row_slot;
-            const bool live = k < n;
-            float x1 = 0, y1 = 0, z1 = 0;
-            if (live) { x1 = p1[k * 3 + 0]; y1 = p1[k * 3 + 1]; z1 = p1[k * 3 + 2]; }
-            float suml = 0.f;
-            for (int l0 = 0; l0 < m; l0 += kEmdTile) {
-                const int ln = min(kEmdTile, m - l0);
-                __syncthreads();
-                for (int l = threadIdx.x; l < ln; l += kEmdThreads)
-                    s_o[l] = make_float4(p2[(l0 + l) * 3 + 0], p2[(l0 + l) * 3 + 1], p2[(l0 + l) * 3 + 2], remainR[l0 + l]);
-                __syncthreads();
-                if (live)
-                    for (int l = l_in; l < ln; l += S) {
-                        const float4 o = s_o[l];
-                        suml += exp2f(level2 * emd_sq(x1, y1, z1, o.x, o.y, o.z)) * o.w;
-                    }
-            }
-            for (int o = S >> 1; o > 0; o >>= 1) suml += __shfl_xor_sync(kFullMask, suml, o);
-            if (live && l_in == 0) ratioL[k] = remainL[k] / (suml + 1e-9f);
-        }
+        emd_row_pass(n, m, p1, p2, remainR, level2, S, rows_per_pass, my_row_slot, l_in, s_o,
+                     [&](int k, float suml) { ratioL[k] = remainL[k] / (suml + 1e-9f); });
         cluster.sync();
-
         // ---- phase 2 (:75-111): per xyz2 point l: sumr = remainR[l] * sum_k exp(level*d) * ratioL[k]
-        for (int r0 = 0; r0 < m; r0 += rows_per_pass) {
-            const int l = r0 + my_row_slot;
-            const bool live = l < m;
-            float x2 = 0, y2 = 0, z2 = 0;
-            if (live) { x2 = p2[l * 3 + 0]; y2 = p2[l * 3 + 1]; z2 = p2[l * 3 + 2]; }
-            float sumr = 0.f;
-            for (int k0 = 0; k0 < n; k0 += kEmdTile) {
-                const int kn = min(kEmdTile, n - k0);
-                __syncthreads();
-                for (int k = threadIdx.x; k < kn; k += kEmdThreads)
-                    s_o[k] = make_float4(p1[(k0 + k) * 3 + 0], p1[(k0 + k) * 3 + 1], p1[(k0 + k) * 3 + 2], ratioL[k0 + k]);
-                __syncthreads();
-                if (live)
-                    for (int k = l_in; k < kn; k += S) {
-                        const float4 o = s_o[k];
-                        sumr += exp2f(level2 * emd_sq(o.x, o.y, o.z, x2, y2, z2)) * o.w;
-                    }
-            }
-            for (int o = S >> 1; o > 0; o >>= 1) sumr += __shfl_xor_sync(kFullMask, sumr, o);
-            if (live && l_in == 0) {
-                const float rr = remainR[l];
-                sumr *= rr;
-                const float consumption = fminf(rr / (sumr + 1e-9f), 1.0f);
-                ratioR[l] = consumption * rr;
-                remainR[l] = fmaxf(0.0f, rr - sumr);
-            }
-        }
+        emd_row_pass(m, n, p2, p1, ratioL, level2, S, rows_per_pass, my_row_slot, l_in, s_o, [&](int l, float sumr) {
+            const float rr = remainR[l];
+            sumr *= rr;
+            const float consumption = fminf(rr / (sumr + 1e-9f), 1.0f);
+            ratioR[l] = consumption * rr;
+            remainR[l] = fmaxf(0.0f, rr - sumr);
+        });
         cluster.sync();
+        // ---- phase 3 (:127-160) without the match update: remainL[k] -= sum_l exp(level*d) * ratioL[k] * ratioR[l]
+        emd_row_pass(n, m, p1, p2, ratioR, level2, S, rows_per_pass, my_row_slot, l_in, s_o,
+                     [&](int k, float suml) { remainL[k] = fmaxf(0.0f, remainL[k] - suml * ratioL[k]); });
+        cluster.sync();
+    }
 
-        // ---- phase 3 (:127-160): w = exp(level*d) * ratioL[k] * ratioR[l]; match[l][k] += w; remainL[k] -= sum_l w
-        // Rows are k; the S lanes of a row take different l.  To keep the match stores coalesced (k fastest) S is 1 here:
-        // consecutive threads own consecutive k and walk l together.
-        for (int r0 = 0; r0 < n; r0 += csize * kEmdThreads) {
-            const int k = r0 + crank * kEmdThreads + threadIdx.x;
-            const bool live = k < n;
-            float x1 = 0, y1 = 0, z1 = 0, rl = 0;
-            if (live) { x1 = p1[k * 3 + 0]; y1 = p1[k * 3 + 1]; z1 = p1[k * 3 + 2]; rl = ratioL[k]; }
-            float suml = 0.f;
-            for (int l0 = 0; l0 < m; l0 += kEmdTile) {
-                const int ln = min(kEmdTile, m - l0);
-                __syncthreads();
-                for (int l = threadIdx.x; l < ln; l += kEmdThreads)
-                    s_o[l] = make_float4(p2[(l0 + l) * 3 + 0], p2[(l0 + l) * 3 + 1], p2[(l0 + l) * 3 + 2], ratioR[l0 + l]);
-                __syncthreads();
-                if (live) {
-#pragma unroll 4
-                    for (int l = 0; l < ln; l++) {
-                        const float4 o = s_o[l];
-                        const float w = exp2f(level2 * emd_sq(x1, y1, z1, o.x, o.y, o.z)) * rl * o.w;
-                        float *mp = match + (size_t)(l0 + l) * n + k;
-                        *mp = first ? w : (*mp + w);
-                        suml += w;
-                    }
+    // ---- final pass: thread = k (coalesced stores along k), l walks the tile; ten weights per pair, summed in level order
+    float lv2[kEmdLevels];
+#pragma unroll
+    for (int li = 0; li < kEmdLevels; li++) lv2[li] = emd_level2(7 - li);
+    float *s_r = reinterpret_cast<float *>(s_o);            // [tile l][kEmdLevels] ratioR of the staged columns (reuses the tile buffer)
+    constexpr int kFinTile = (kEmdTile * 4) / (kEmdLevels + 3);   // columns per stage: xyz (3) + ten ratios
+    float *s_xyz = s_r + kFinTile * kEmdLevels;
+    for (int k0 = 0; k0 < n; k0 += csize * kEmdThreads) {
+        const int k = k0 + crank * kEmdThreads + threadIdx.x;
+        const bool live = k < n;
+        float x1 = 0, y1 = 0, z1 = 0, rl[kEmdLevels];
+        if (live) { x1 = p1[k * 3 + 0]; y1 = p1[k * 3 + 1]; z1 = p1[k * 3 + 2]; }
+#pragma unroll
+        for (int li = 0; li < kEmdLevels; li++) rl[li] = live ? ratios[(size_t)li * (n + m) + k] : 0.f;
+        for (int l0 = 0; l0 < m; l0 += kFinTile) {
+            const int ln = min(kFinTile, m - l0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < ln * kEmdLevels; e += kEmdThreads) {
+                const int l = e / kEmdLevels, li = e - l * kEmdLevels;
+                s_r[e] = ratios[(size_t)li * (n + m) + n + l0 + l];
+            }
+            for (int e = threadIdx.x; e < ln * 3; e += kEmdThreads) s_xyz[e] = p2[(size_t)l0 * 3 + e];
+            __syncthreads();
+            if (live) {
+                for (int l = 0; l < ln; l++) {
+                    const float d2 = emd_sq(x1, y1, z1, s_xyz[l * 3 + 0], s_xyz[l * 3 + 1], s_xyz[l * 3 + 2]);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int li = 0; li < kEmdLevels; li++) acc += emd_ex2(lv2[li] * d2) * rl[li] * s_r[l * kEmdLevels + li];
+                    match[(size_t)(l0 + l) * n + k] = acc;
                 }
             }
-            if (live) remainL[k] = fmaxf(0.0f, remainL[k] - suml);
         }
-        cluster.sync();
     }
 }
 
-size_t approxmatch_workspace_bytes(int b, int n, int m) { return (size_t)b * (n + m) * 2 * sizeof(float); }
+size_t approxmatch_workspace_bytes(int b, int n, int m) { return (size_t)b * (n + m) * (1 + kEmdLevels) * sizeof(float); }
 
 int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace, cudaStream_t stream)
 {
     EmdParams P;
     P.b = b; P.n = n; P.m = m; P.xyz1 = xyz1; P.xyz2 = xyz2; P.match = match; P.temp = reinterpret_cast<float *>(workspace);
-    // cluster size: as many CTAs per cloud as still have >= 1 row per thread in phase 3, bounded by the SM budget
-    int csize = 1;
+    // cluster size: as many CTAs per cloud as the SM budget allows (any size up to 8, not only powers of two), while every CTA
+    // still has rows to own
     const int rows = max(n, m);
-    while (csize < 8 && (long long)b * csize * 2 <= 2 * kNumSMs && csize * kEmdThreads < rows) csize *= 2;
-    // lanes per row for the reductions of phases 1/2: use the idle threads when rows < cluster threads
+    int csize = max(1, min(8, (2 * kNumSMs) / max(b, 1)));   // two 512-thread CTAs fit an SM (40 registers, 17 KB shared memory)
+    while (csize > 1 && (csize - 1) * kEmdThreads >= rows) csize--;
+    // lanes per row for the reductions: use the idle threads when rows < cluster threads
     int S = 1;
     while (S < 32 && (csize * kEmdThreads) / (S * 2) >= min(n, m)) S *= 2;
     P.S = S;
@@ -183,27 +206,48 @@ int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2
 
 // ------------------------------------------------------------------------------------------------------------------
 // match_cost (:183-225): cost[b] = sum_{k,l} match[b][l][k] * ||xyz1[k] - xyz2[l]||.
-// One cluster-free CTA per (cloud, slab of l); threads run along k so match reads are coalesced; per-CTA partials are
-// combined by the LAST CTA of each cloud in slab order (deterministic), using a per-cloud arrival counter in `cost`'s
-// shadow... kept simple: slabs write partials to a small static device buffer indexed by (cloud, slab).
+// Streaming kernels: `match` is read exactly once, 16 bytes per thread and load (k runs fastest in memory), several loads in
+// flight per thread; per-CTA partials are combined in slab order by a second tiny kernel (deterministic).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMcThreads = 256;
 constexpr int kMcSlabs = 16;
 
+template <bool kVec>
 __global__ void __launch_bounds__(kMcThreads) matchcost_partial_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                                       const float *__restrict__ match, float *__restrict__ partial)
 {
     __shared__ float s_red[kMcThreads / 32];
+    extern __shared__ float s_p2[];     // the slab's xyz2 points
     const int bi = blockIdx.y, slab = blockIdx.x;
     const int l_beg = (int)((long long)m * slab / kMcSlabs), l_end = (int)((long long)m * (slab + 1) / kMcSlabs);
     const float *p1 = xyz1 + (size_t)bi * n * 3, *p2 = xyz2 + (size_t)bi * m * 3;
     const float *mt = match + (size_t)bi * n * m;
+    for (int i = threadIdx.x; i < (l_end - l_beg) * 3; i += kMcThreads) s_p2[i] = p2[(size_t)l_beg * 3 + i];
+    __syncthreads();
     float sub = 0.f;
-    for (int k = threadIdx.x; k < n; k += kMcThreads) {
-        const float x1 = p1[k * 3 + 0], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
-        for (int l = l_beg; l < l_end; l++) {
-            const float x2 = __ldg(p2 + l * 3 + 0), y2 = __ldg(p2 + l * 3 + 1), z2 = __ldg(p2 + l * 3 + 2);
-            sub += sqrtf(emd_sq(x1, y1, z1, x2, y2, z2)) * mt[(size_t)l * n + k];
+    if (kVec) {
+        for (int k4 = threadIdx.x; k4 < (n >> 2); k4 += kMcThreads) {
+            float x1[4], y1[4], z1[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { x1[u] = p1[(k4 * 4 + u) * 3 + 0]; y1[u] = p1[(k4 * 4 + u) * 3 + 1]; z1[u] = p1[(k4 * 4 + u) * 3 + 2]; }
+            const float4 *row = reinterpret_cast<const float4 *>(mt + (size_t)l_beg * n) + k4;
+            const size_t stride4 = (size_t)(n >> 2);
+#pragma unroll 8
+            for (int l = l_beg; l < l_end; l++) {
+                const float4 w = __ldcs(row + (size_t)(l - l_beg) * stride4);   // streamed once: do not keep it in L2
+                const float x2 = s_p2[(l - l_beg) * 3 + 0], y2 = s_p2[(l - l_beg) * 3 + 1], z2 = s_p2[(l - l_beg) * 3 + 2];
+                sub += sqrtf(emd_sq(x1[0], y1[0], z1[0], x2, y2, z2)) * w.x;
+                sub += sqrtf(emd_sq(x1[1], y1[1], z1[1], x2, y2, z2)) * w.y;
+                sub += sqrtf(emd_sq(x1[2], y1[2], z1[2], x2, y2, z2)) * w.z;
+                sub += sqrtf(emd_sq(x1[3], y1[3], z1[3], x2, y2, z2)) * w.w;
+            }
+        }
+    } else {
+        for (int k = threadIdx.x; k < n; k += kMcThreads) {
+            const float x1 = p1[k * 3 + 0], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+#pragma unroll 4
+            for (int l = l_beg; l < l_end; l++)
+                sub += sqrtf(emd_sq(x1, y1, z1, s_p2[(l - l_beg) * 3 + 0], s_p2[(l - l_beg) * 3 + 1], s_p2[(l - l_beg) * 3 + 2])) * mt[(size_t)l * n + k];
         }
     }
     sub = warp_sum(sub);
@@ -225,64 +269,118 @@ __global__ void matchcost_final_kernel(int b, const float *__restrict__ partial,
     }
 }
 
-// grad1 (:263-291): grad1[k] = sum_l match[l][k] * (x1-x2) / max(|x1-x2|, 1e-10); thread per k, l broadcast from smem.
-__global__ void __launch_bounds__(256) matchcostgrad1_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                                                             const float *__restrict__ match, float *__restrict__ grad1)
+// grad1 (:263-291): grad1[k] = sum_l match[l][k] * (x1-x2) / max(|x1-x2|, 1e-10); thread per k (vector path: 4 consecutive k),
+// l broadcast from shared memory, loads of `match` several deep.
+constexpr int kMgThreads = 128;
+template <bool kVec>
+__global__ void __launch_bounds__(kMgThreads) matchcostgrad1_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                                   const float *__restrict__ match, float *__restrict__ grad1)
 {
+    constexpr int W = kVec ? 4 : 1;
     __shared__ float s_o[kEmdTile * 3];
     const int bi = blockIdx.y;
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    const bool live = k < n;
+    const int k0 = (blockIdx.x * kMgThreads + threadIdx.x) * W;
+    const bool live = k0 < n;
     const float *p1 = xyz1 + (size_t)bi * n * 3, *p2 = xyz2 + (size_t)bi * m * 3;
     const float *mt = match + (size_t)bi * n * m;
-    float x1 = 0, y1 = 0, z1 = 0;
-    if (live) { x1 = p1[k * 3 + 0]; y1 = p1[k * 3 + 1]; z1 = p1[k * 3 + 2]; }
-    float dx = 0, dy = 0, dz = 0;
+    float x1[W], y1[W], z1[W], dx[W], dy[W], dz[W];
+#pragma unroll
+    for (int u = 0; u < W; u++) {
+        const int k = min(k0 + u, n - 1);
+        x1[u] = p1[k * 3 + 0]; y1[u] = p1[k * 3 + 1]; z1[u] = p1[k * 3 + 2];
+        dx[u] = dy[u] = dz[u] = 0.f;
+    }
     for (int l0 = 0; l0 < m; l0 += kEmdTile) {
         const int ln = min(kEmdTile, m - l0);
         __syncthreads();
-        for (int i = threadIdx.x; i < ln * 3; i += 256) s_o[i] = p2[(size_t)l0 * 3 + i];
+        for (int i = threadIdx.x; i < ln * 3; i += kMgThreads) s_o[i] = p2[(size_t)l0 * 3 + i];
         __syncthreads();
-        if (live)
+        if (live) {
+#pragma unroll 8
             for (int l = 0; l < ln; l++) {
-                const float ex = x1 - s_o[l * 3 + 0], ey = y1 - s_o[l * 3 + 1], ez = z1 - s_o[l * 3 + 2];
-                const float d = mt[(size_t)(l0 + l) * n + k] * rsqrtf(fmaxf(ex * ex + ey * ey + ez * ez, 1e-20f));
-                dx += ex * d; dy += ey * d; dz += ez * d;
+                float w[W];
+                if (kVec) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(mt + (size_t)(l0 + l) * n + k0));
+                    w[0] = v.x; w[W > 1 ? 1 : 0] = v.y; w[W > 2 ? 2 : 0] = v.z; w[W > 3 ? 3 : 0] = v.w;
+                } else {
+                    w[0] = __ldcs(mt + (size_t)(l0 + l) * n + k0);
+                }
+                const float x2 = s_o[l * 3 + 0], y2 = s_o[l * 3 + 1], z2 = s_o[l * 3 + 2];
+#pragma unroll
+                for (int u = 0; u < W; u++) {
+                    const float ex = x1[u] - x2, ey = y1[u] - y2, ez = z1[u] - z2;
+                    const float d = w[u] * rsqrtf(fmaxf(ex * ex + ey * ey + ez * ez, 1e-20f));
+                    dx[u] += ex * d; dy[u] += ey * d; dz[u] += ez * d;
+                }
             }
+        }
     }
     if (live) {
-        float *g = grad1 + ((size_t)bi * n + k) * 3;
-        g[0] = dx; g[1] = dy; g[2] = dz;
+#pragma unroll
+        for (int u = 0; u < W; u++)
+            if (k0 + u < n) {
+                float *g = grad1 + ((size_t)bi * n + k0 + u) * 3;
+                g[0] = dx[u]; g[1] = dy[u]; g[2] = dz[u];
+            }
     }
 }
 
-// grad2 (:229-262): grad2[l] = sum_k match[l][k] * (x2-x1) / max(|x2-x1|, 1e-10); one warp per l, lanes along k (coalesced).
+// grad2 (:229-262): grad2[l] = sum_k match[l][k] * (x2-x1) / max(|x2-x1|, 1e-10); one warp per l, lanes along k (coalesced; vector
+// path: 4 consecutive k per lane and load), xyz1 staged in shared memory.
+template <bool kVec>
 __global__ void __launch_bounds__(256) matchcostgrad2_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                              const float *__restrict__ match, float *__restrict__ grad2)
 {
+    constexpr int W = kVec ? 4 : 1;
+    __shared__ float s_p1[kEmdTile * 3];
     const int bi = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int l = blockIdx.x * 8 + warp;
-    if (l >= m) return;
+    const bool live = l < m;
     const float *p1 = xyz1 + (size_t)bi * n * 3, *p2 = xyz2 + (size_t)bi * m * 3;
-    const float *mt = match + (size_t)bi * n * m + (size_t)l * n;
-    const float x2 = p2[l * 3 + 0], y2 = p2[l * 3 + 1], z2 = p2[l * 3 + 2];
+    const float *mt = match + (size_t)bi * n * m + (size_t)min(l, m - 1) * n;
+    float x2 = 0, y2 = 0, z2 = 0;
+    if (live) { x2 = p2[l * 3 + 0]; y2 = p2[l * 3 + 1]; z2 = p2[l * 3 + 2]; }
     float sx = 0, sy = 0, sz = 0;
-    for (int k = lane; k < n; k += 32) {
-        const float ex = x2 - __ldg(p1 + k * 3 + 0), ey = y2 - __ldg(p1 + k * 3 + 1), ez = z2 - __ldg(p1 + k * 3 + 2);
-        const float d = mt[k] * rsqrtf(fmaxf(ex * ex + ey * ey + ez * ez, 1e-20f));
-        sx += ex * d; sy += ey * d; sz += ez * d;
+    for (int k0 = 0; k0 < n; k0 += kEmdTile) {
+        const int kn = min(kEmdTile, n - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kn * 3; i += 256) s_p1[i] = p1[(size_t)k0 * 3 + i];
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int k = lane * W; k < kn; k += 32 * W) {
+                float w[W];
+                if (kVec) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(mt + k0 + k));
+                    w[0] = v.x; w[W > 1 ? 1 : 0] = v.y; w[W > 2 ? 2 : 0] = v.z; w[W > 3 ? 3 : 0] = v.w;
+                } else {
+                    w[0] = __ldcs(mt + k0 + k);
+                }
+#pragma unroll
+                for (int u = 0; u < W; u++) {
+                    const float ex = x2 - s_p1[(k + u) * 3 + 0], ey = y2 - s_p1[(k + u) * 3 + 1], ez = z2 - s_p1[(k + u) * 3 + 2];
+                    const float d = w[u] * rsqrtf(fmaxf(ex * ex + ey * ey + ez * ez, 1e-20f));
+                    sx += ex * d; sy += ey * d; sz += ez * d;
+                }
+            }
+        }
     }
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    if (lane == 0) {
+    if (live && lane == 0) {
         float *g = grad2 + ((size_t)bi * m + l) * 3;
         g[0] = sx; g[1] = sy; g[2] = sz;
     }
 }
 
+static bool emd_vec_ok(int n, const float *match) { return (n & 3) == 0 && (reinterpret_cast<uintptr_t>(match) & 15) == 0; }
+
 int launch_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *cost, float *partial, cudaStream_t stream)
 {
-    matchcost_partial_kernel<<<dim3(kMcSlabs, b), kMcThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, partial);
+    const size_t smem = (size_t)((m + kMcSlabs - 1) / kMcSlabs + 1) * 3 * sizeof(float);
+    if (smem > 48 * 1024) { set_error("matchcost: m=%d too large", m); return SNB200_EUNSUPPORTED; }
+    if (emd_vec_ok(n, match)) matchcost_partial_kernel<true><<<dim3(kMcSlabs, b), kMcThreads, smem, stream>>>(b, n, m, xyz1, xyz2, match, partial);
+    else matchcost_partial_kernel<false><<<dim3(kMcSlabs, b), kMcThreads, smem, stream>>>(b, n, m, xyz1, xyz2, match, partial);
     int rc = check_launch("matchcost(partial)");
     if (rc) return rc;
     matchcost_final_kernel<<<(b + 127) / 128, 128, 0, stream>>>(b, partial, cost);
@@ -291,10 +389,13 @@ int launch_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, 
 
 int launch_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2, cudaStream_t stream)
 {
-    matchcostgrad1_kernel<<<dim3((n + 255) / 256, b), 256, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
+    const bool vec = emd_vec_ok(n, match);
+    if (vec) matchcostgrad1_kernel<true><<<dim3((n / 4 + kMgThreads - 1) / kMgThreads, b), kMgThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
+    else matchcostgrad1_kernel<false><<<dim3((n + kMgThreads - 1) / kMgThreads, b), kMgThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
     int rc = check_launch("matchcostgrad1");
     if (rc) return rc;
-    matchcostgrad2_kernel<<<dim3((m + 7) / 8, b), 256, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad2);
+    if (vec) matchcostgrad2_kernel<true><<<dim3((m + 7) / 8, b), 256, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad2);
+    else matchcostgrad2_kernel<false><<<dim3((m + 7) / 8, b), 256, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad2);
     return check_launch("matchcostgrad2");
 }
 

@@ -448,7 +448,11 @@ def test_emd_vs_oracle(sb, oracle, n, m):
     omt = oracle.approx_match(a, c)
     # same algorithm, different summation order + exp2f vs expf: the reference flags |diff| > 1e-2 (approxmatch.cpp:222)
     assert np.abs(_n(mt) - omt).max() < 2e-3
-    assert (np.argmax(_n(mt), axis=2) == np.argmax(omt, axis=2)).mean() > 0.995  # match assignments
+    # match assignments: the strongest partner of every xyz2 point agrees, except where the oracle's own top two weights are
+    # closer than the value tolerance above (then either is "the" assignment)
+    am, ao = np.argmax(_n(mt), axis=2), np.argmax(omt, axis=2)
+    gap = np.take_along_axis(omt, ao[..., None], 2)[..., 0] - np.take_along_axis(omt, am[..., None], 2)[..., 0]
+    assert (gap < 2e-3).all() and (am == ao).mean() > 0.97
     # on IDENTICAL match input the cost and gradient kernels are compared tightly
     x1 = _t(a).requires_grad_(True); x2 = _t(c).requires_grad_(True)
     cost = sb.tf_ops.match_cost(x1, x2, _t(omt))
