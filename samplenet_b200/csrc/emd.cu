@@ -27,6 +27,7 @@ struct EmdParams {
     const float *xyz1, *xyz2;
     float *match;    // (b, m, n)
     float *temp;     // per cloud: remainL[n], remainR[m], then per level ratioL[n], ratioR[m]
+    unsigned *counter;   // grid-barrier word, zero at launch
 };
 
 __device__ __forceinline__ float emd_sq(float ax, float ay, float az, float bx, float by, float bz)
@@ -47,41 +48,91 @@ __device__ __forceinline__ float emd_level2(int lev)   // level = -4^lev (0 at t
     return level * 1.44269504088896340736f;
 }
 
-// Row sums  acc[row] = sum_col exp2(level2 * |row - col|^2) * w[col]  for the rows this thread group owns; the column side (xyz + w as
-// float4) is staged through shared memory in tiles.  A row is shared by S lanes that take the columns j == lane (mod S).
-template <typename F>
-__device__ __forceinline__ void emd_row_pass(int nrows, int ncols, const float *prow, const float *pcol, const float *wcol, float level2, int S,
-                                             int rows_per_pass, int my_row_slot, int l_in, float4 *s_o, F &&finish)
+__device__ __forceinline__ void emd_grid_barrier(unsigned *counter, unsigned target)
 {
-    for (int r0 = 0; r0 < nrows; r0 += rows_per_pass) {
-        const int r = r0 + my_row_slot;
-        const bool live = r < nrows;
-        float x = 0, y = 0, z = 0;
-        if (live) { x = prow[r * 3 + 0]; y = prow[r * 3 + 1]; z = prow[r * 3 + 2]; }
-        float a0 = 0.f, a1 = 0.f;
-        for (int c0 = 0; c0 < ncols; c0 += kEmdTile) {
-            const int cn = min(kEmdTile, ncols - c0);
-            __syncthreads();
-            for (int c = threadIdx.x; c < cn; c += kEmdThreads)
-                s_o[c] = make_float4(pcol[(c0 + c) * 3 + 0], pcol[(c0 + c) * 3 + 1], pcol[(c0 + c) * 3 + 2], wcol[c0 + c]);
-            __syncthreads();
-            if (live) {
-                int c = l_in;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v, spin = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (++spin > (1u << 28)) __trap();
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+// Row sums over ALL clouds of the batch:  acc[bi][row] = sum_col exp2(level2 * |row - col|^2) * w[bi][col].
+// The b * nrows rows are one flat index space cut into equal contiguous chunks, one per CTA (a chunk may straddle clouds), so the
+// whole grid is busy whatever b is (the reference -- and a cluster-per-cloud split -- leave SMs idle unless b divides the chip).
+// Inside a CTA a row is shared by S lanes that take the columns j == lane (mod S); the column side (xyz + w as float4) is staged
+// through shared memory in tiles; two rows are register-blocked per thread slot when the chunk is long enough.
+// ROW / COL strides: rows are points of `prow` (nrows per cloud), columns points of `pcol` (ncols per cloud); `wcol` and the
+// vectors `finish` touches are per-cloud vectors addressed through `vec_stride`.
+template <typename F>
+__device__ __forceinline__ void emd_row_pass(int b, int nrows, int ncols, const float *prow, const float *pcol, const float *wcol, size_t vec_stride,
+                                             float level2, int S, float4 *s_o, F &&finish)
+{
+    const long long total = (long long)b * nrows;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = min(total, per * blockIdx.x), hi = min(total, lo + per);
+    const int slots = kEmdThreads / S;              // row slots per pass
+    const int slot = threadIdx.x / S, l_in = threadIdx.x % S;
+    long long seg = lo;
+    while (seg < hi) {                              // one cloud segment at a time (uniform over the CTA)
+        const int bi = (int)(seg / nrows);
+        const int r_beg = (int)(seg - (long long)bi * nrows);
+        const int r_end = (int)min((long long)nrows, r_beg + (hi - seg));
+        const float *pr = prow + (size_t)bi * nrows * 3, *pc = pcol + (size_t)bi * ncols * 3;
+        const float *wc = wcol + (size_t)bi * vec_stride;
+        for (int r0 = r_beg; r0 < r_end;) {
+            const bool two = (r_end - r0) > slots;       // enough rows left to give every slot a second one (CTA-uniform)
+            const int ra = r0 + slot, rb = r0 + slots + slot;
+            const bool la = ra < r_end, lb = two && rb < r_end;
+            float xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
+            if (la) { xa = pr[ra * 3 + 0]; ya = pr[ra * 3 + 1]; za = pr[ra * 3 + 2]; }
+            if (lb) { xb = pr[rb * 3 + 0]; yb = pr[rb * 3 + 1]; zb = pr[rb * 3 + 2]; }
+            float a0 = 0.f, a1 = 0.f;
+            for (int c0 = 0; c0 < ncols; c0 += kEmdTile) {
+                const int cn = min(kEmdTile, ncols - c0);
+                __syncthreads();
+                for (int c = threadIdx.x; c < cn; c += kEmdThreads)
+                    s_o[c] = make_float4(pc[(c0 + c) * 3 + 0], pc[(c0 + c) * 3 + 1], pc[(c0 + c) * 3 + 2], wc[c0 + c]);
+                __syncthreads();
+                if (la && two) {   // one shared-memory read feeds two rows
+#pragma unroll 4
+                    for (int c = l_in; c < cn; c += S) {
+                        const float4 o = s_o[c];
+                        a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o.x, o.y, o.z)), o.w, a0);
+                        a1 = fmaf(emd_ex2(level2 * emd_sq(xb, yb, zb, o.x, o.y, o.z)), o.w, a1);
+                    }
+                } else if (la) {
+                    int c = l_in;
 #pragma unroll 2
-                for (; c + S < cn; c += 2 * S) {   // two independent accumulation chains
-                    const float4 o0 = s_o[c], o1 = s_o[c + S];
-                    a0 = fmaf(emd_ex2(level2 * emd_sq(x, y, z, o0.x, o0.y, o0.z)), o0.w, a0);
-                    a1 = fmaf(emd_ex2(level2 * emd_sq(x, y, z, o1.x, o1.y, o1.z)), o1.w, a1);
-                }
-                if (c < cn) {
-                    const float4 o0 = s_o[c];
-                    a0 = fmaf(emd_ex2(level2 * emd_sq(x, y, z, o0.x, o0.y, o0.z)), o0.w, a0);
+                    for (; c + S < cn; c += 2 * S) {   // two independent accumulation chains
+                        const float4 o0 = s_o[c], o1 = s_o[c + S];
+                        a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
+                        a1 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o1.x, o1.y, o1.z)), o1.w, a1);
+                    }
+                    if (c < cn) {
+                        const float4 o0 = s_o[c];
+                        a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
+                    }
                 }
             }
+            if (!two) { a0 += a1; a1 = 0.f; }
+            for (int o = S >> 1; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(kFullMask, a0, o);
+                a1 += __shfl_xor_sync(kFullMask, a1, o);
+            }
+            if (l_in == 0) {
+                if (la) finish(bi, ra, a0);
+                if (lb) finish(bi, rb, a1);
+            }
+            r0 += two ? 2 * slots : slots;
         }
-        float acc = a0 + a1;
-        for (int o = S >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
-        if (live && l_in == 0) finish(r, acc);
+        seg += r_end - r_beg;
     }
 }
 
@@ -90,117 +141,121 @@ __device__ __forceinline__ void emd_row_pass(int nrows, int ncols, const float *
 // is produced by ONE final pass that re-evaluates the ten weights of a pair in registers, in level order, and writes it once:
 //   match[l][k] = sum_lev exp(level_lev * d(k,l)) * ratioL_lev[k] * ratioR_lev[l]
 // One extra exp per pair and level buys the removal of all match traffic but the final store.
-__global__ void __launch_bounds__(kEmdThreads) approxmatch_kernel(const __grid_constant__ EmdParams P)
+// Persistent cooperative grid (2 CTAs per SM), phases separated by a grid barrier (31 per launch).
+__global__ void __launch_bounds__(kEmdThreads, 2) approxmatch_kernel(const __grid_constant__ EmdParams P)
 {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int crank = cluster.block_rank();
-    const int csize = cluster.num_blocks();
-    const int bi = blockIdx.x / csize;
-    const int n = P.n, m = P.m, S = P.S;
-    const float *p1 = P.xyz1 + (size_t)bi * n * 3;
-    const float *p2 = P.xyz2 + (size_t)bi * m * 3;
-    float *match = P.match + (size_t)bi * n * m;
-    float *remainL = P.temp + (size_t)bi * (n + m) * (1 + kEmdLevels), *remainR = remainL + n;
-    float *ratios = remainR + m;   // [level][ratioL (n) | ratioR (m)]
+    const int n = P.n, m = P.m, S = P.S, b = P.b;
+    const size_t vs = (size_t)(n + m) * (1 + kEmdLevels);    // floats of per-point vectors per cloud
+    float *remainL = P.temp, *remainR = remainL + n;          // + bi * vs
+    float *ratios = remainR + m;                              // [level][ratioL (n) | ratioR (m)]
+    unsigned *counter = P.counter;
+    const unsigned G = gridDim.x;
+    unsigned epoch = 0;
 
     __shared__ float4 s_o[kEmdTile];
 
-    const int rows_per_pass = (csize * kEmdThreads) / S;              // rows the whole cluster handles at once
-    const int my_row_slot = (crank * kEmdThreads + threadIdx.x) / S;  // my row within a pass
-    const int l_in = threadIdx.x % S;                                 // my lane within the row group
-
     float multiL, multiR;  // tf_approxmatch_g.cu:4-10 (integer division)
     if (n >= m) { multiL = 1; multiR = (float)(n / m); } else { multiL = (float)(m / n); multiR = 1; }
-    for (int j = crank * kEmdThreads + threadIdx.x; j < n; j += csize * kEmdThreads) remainL[j] = multiL;
-    for (int j = crank * kEmdThreads + threadIdx.x; j < m; j += csize * kEmdThreads) remainR[j] = multiR;
-    cluster.sync();
+    for (long long e = (long long)blockIdx.x * kEmdThreads + threadIdx.x; e < (long long)b * (n + m); e += (long long)G * kEmdThreads) {
+        const int bi = (int)(e / (n + m)), j = (int)(e - (long long)bi * (n + m));
+        (P.temp + (size_t)bi * vs)[j] = j < n ? multiL : multiR;
+    }
+    emd_grid_barrier(counter, ++epoch * G);
 
     for (int lev = 7, li = 0; lev >= -2; lev--, li++) {
         const float level2 = emd_level2(lev);
-        float *ratioL = ratios + (size_t)li * (n + m), *ratioR = ratioL + n;
+        float *ratioL = ratios + (size_t)li * (n + m), *ratioR = ratioL + n;   // + bi * vs
 
         // ---- phase 1 (:27-60): ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level*d) * remainR[l])
-        emd_row_pass(n, m, p1, p2, remainR, level2, S, rows_per_pass, my_row_slot, l_in, s_o,
-                     [&](int k, float suml) { ratioL[k] = remainL[k] / (suml + 1e-9f); });
-        cluster.sync();
+        emd_row_pass(b, n, m, P.xyz1, P.xyz2, remainR, vs, level2, S, s_o,
+                     [&](int bi, int k, float suml) { ratioL[bi * vs + k] = remainL[bi * vs + k] / (suml + 1e-9f); });
+        emd_grid_barrier(counter, ++epoch * G);
         // ---- phase 2 (:75-111): per xyz2 point l: sumr = remainR[l] * sum_k exp(level*d) * ratioL[k]
-        emd_row_pass(m, n, p2, p1, ratioL, level2, S, rows_per_pass, my_row_slot, l_in, s_o, [&](int l, float sumr) {
-            const float rr = remainR[l];
+        emd_row_pass(b, m, n, P.xyz2, P.xyz1, ratioL, vs, level2, S, s_o, [&](int bi, int l, float sumr) {
+            const float rr = remainR[bi * vs + l];
             sumr *= rr;
             const float consumption = fminf(rr / (sumr + 1e-9f), 1.0f);
-            ratioR[l] = consumption * rr;
-            remainR[l] = fmaxf(0.0f, rr - sumr);
+            ratioR[bi * vs + l] = consumption * rr;
+            remainR[bi * vs + l] = fmaxf(0.0f, rr - sumr);
         });
-        cluster.sync();
+        emd_grid_barrier(counter, ++epoch * G);
         // ---- phase 3 (:127-160) without the match update: remainL[k] -= sum_l exp(level*d) * ratioL[k] * ratioR[l]
-        emd_row_pass(n, m, p1, p2, ratioR, level2, S, rows_per_pass, my_row_slot, l_in, s_o,
-                     [&](int k, float suml) { remainL[k] = fmaxf(0.0f, remainL[k] - suml * ratioL[k]); });
-        cluster.sync();
+        emd_row_pass(b, n, m, P.xyz1, P.xyz2, ratioR, vs, level2, S, s_o,
+                     [&](int bi, int k, float suml) { remainL[bi * vs + k] = fmaxf(0.0f, remainL[bi * vs + k] - suml * ratioL[bi * vs + k]); });
+        emd_grid_barrier(counter, ++epoch * G);
     }
 
-    // ---- final pass: thread = k (coalesced stores along k), l walks the tile; ten weights per pair, summed in level order
+    // ---- final pass: work item = (cloud, block of 512 k, chunk of kFinTile l); thread = k (coalesced stores along k); ten weights
+    //      per pair, summed in level order
     float lv2[kEmdLevels];
 #pragma unroll
     for (int li = 0; li < kEmdLevels; li++) lv2[li] = emd_level2(7 - li);
     float *s_r = reinterpret_cast<float *>(s_o);            // [tile l][kEmdLevels] ratioR of the staged columns (reuses the tile buffer)
     constexpr int kFinTile = (kEmdTile * 4) / (kEmdLevels + 3);   // columns per stage: xyz (3) + ten ratios
     float *s_xyz = s_r + kFinTile * kEmdLevels;
-    for (int k0 = 0; k0 < n; k0 += csize * kEmdThreads) {
-        const int k = k0 + crank * kEmdThreads + threadIdx.x;
+    const int kblocks = (n + kEmdThreads - 1) / kEmdThreads, lchunks = (m + kFinTile - 1) / kFinTile;
+    const long long items = (long long)b * kblocks * lchunks;
+    for (long long it = blockIdx.x; it < items; it += G) {
+        const int lc = (int)(it % lchunks);
+        const int kb = (int)((it / lchunks) % kblocks);
+        const int bi = (int)(it / ((long long)lchunks * kblocks));
+        const float *p1 = P.xyz1 + (size_t)bi * n * 3, *p2 = P.xyz2 + (size_t)bi * m * 3;
+        const float *rat = ratios + (size_t)bi * vs;
+        float *match = P.match + (size_t)bi * n * m;
+        const int k = kb * kEmdThreads + threadIdx.x;
         const bool live = k < n;
         float x1 = 0, y1 = 0, z1 = 0, rl[kEmdLevels];
         if (live) { x1 = p1[k * 3 + 0]; y1 = p1[k * 3 + 1]; z1 = p1[k * 3 + 2]; }
 #pragma unroll
-        for (int li = 0; li < kEmdLevels; li++) rl[li] = live ? ratios[(size_t)li * (n + m) + k] : 0.f;
-        for (int l0 = 0; l0 < m; l0 += kFinTile) {
-            const int ln = min(kFinTile, m - l0);
-            __syncthreads();
-            for (int e = threadIdx.x; e < ln * kEmdLevels; e += kEmdThreads) {
-                const int l = e / kEmdLevels, li = e - l * kEmdLevels;
-                s_r[e] = ratios[(size_t)li * (n + m) + n + l0 + l];
-            }
-            for (int e = threadIdx.x; e < ln * 3; e += kEmdThreads) s_xyz[e] = p2[(size_t)l0 * 3 + e];
-            __syncthreads();
-            if (live) {
-                for (int l = 0; l < ln; l++) {
-                    const float d2 = emd_sq(x1, y1, z1, s_xyz[l * 3 + 0], s_xyz[l * 3 + 1], s_xyz[l * 3 + 2]);
-                    float acc = 0.f;
+        for (int li = 0; li < kEmdLevels; li++) rl[li] = live ? rat[(size_t)li * (n + m) + k] : 0.f;
+        const int l0 = lc * kFinTile, ln = min(kFinTile, m - l0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < ln * kEmdLevels; e += kEmdThreads) {
+            const int l = e / kEmdLevels, li = e - l * kEmdLevels;
+            s_r[e] = rat[(size_t)li * (n + m) + n + l0 + l];
+        }
+        for (int e = threadIdx.x; e < ln * 3; e += kEmdThreads) s_xyz[e] = p2[(size_t)l0 * 3 + e];
+        __syncthreads();
+        if (live) {
+#pragma unroll 2
+            for (int l = 0; l < ln; l++) {
+                const float d2 = emd_sq(x1, y1, z1, s_xyz[l * 3 + 0], s_xyz[l * 3 + 1], s_xyz[l * 3 + 2]);
+                float acc = 0.f;
 #pragma unroll
-                    for (int li = 0; li < kEmdLevels; li++) acc += emd_ex2(lv2[li] * d2) * rl[li] * s_r[l * kEmdLevels + li];
-                    match[(size_t)(l0 + l) * n + k] = acc;
-                }
+                for (int li = 0; li < kEmdLevels; li++) acc += emd_ex2(lv2[li] * d2) * rl[li] * s_r[l * kEmdLevels + li];
+                __stcs(match + (size_t)(l0 + l) * n + k, acc);     // written once, read later by other kernels: streaming store
             }
         }
     }
 }
 
-size_t approxmatch_workspace_bytes(int b, int n, int m) { return (size_t)b * (n + m) * (1 + kEmdLevels) * sizeof(float); }
+size_t approxmatch_workspace_bytes(int b, int n, int m) { return (size_t)b * (n + m) * (1 + kEmdLevels) * sizeof(float) + 256; }
 
 int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace, cudaStream_t stream)
 {
+    if (b == 0) return SNB200_OK;
     EmdParams P;
-    P.b = b; P.n = n; P.m = m; P.xyz1 = xyz1; P.xyz2 = xyz2; P.match = match; P.temp = reinterpret_cast<float *>(workspace);
-    // cluster size: as many CTAs per cloud as the SM budget allows (any size up to 8, not only powers of two), while every CTA
-    // still has rows to own
-    const int rows = max(n, m);
-    int csize = max(1, min(8, (2 * kNumSMs) / max(b, 1)));   // two 512-thread CTAs fit an SM (40 registers, 17 KB shared memory)
-    while (csize > 1 && (csize - 1) * kEmdThreads >= rows) csize--;
-    // lanes per row for the reductions: use the idle threads when rows < cluster threads
+    P.b = b; P.n = n; P.m = m; P.xyz1 = xyz1; P.xyz2 = xyz2; P.match = match;
+    P.counter = reinterpret_cast<unsigned *>(workspace);                       // grid-barrier word (first 256 bytes of the workspace)
+    P.temp = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + 256);
+    // grid: every SM gets two CTAs unless the batch is too small to give each CTA rows
+    int dev = 0, per_sm = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, approxmatch_kernel, kEmdThreads, 0);
+    if (per_sm < 1) { set_error("approxmatch: kernel does not fit an SM"); return SNB200_ECUDA; }
+    const long long rows = (long long)b * min(n, m);
+    int grid = min(per_sm, 2) * sms;
+    // lanes per row for the reductions: spread short batches over the idle threads (>= 16 columns per lane)
     int S = 1;
-    while (S < 32 && (csize * kEmdThreads) / (S * 2) >= min(n, m)) S *= 2;
+    while (S < 32 && rows * (S * 2) <= (long long)grid * kEmdThreads / 2 && min(n, m) / (S * 2) >= 16) S *= 2;
     P.S = S;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(b * csize);
-    cfg.blockDim = dim3(kEmdThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, approxmatch_kernel, P);
-    if (e != cudaSuccess) { set_error("approxmatch: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SNB200_ECUDA; }
+    const long long slots_needed = (rows * S + kEmdThreads - 1) / kEmdThreads;   // CTAs that would get at least one full pass
+    grid = (int)max(1ll, min((long long)grid, slots_needed));
+    cudaMemsetAsync(P.counter, 0, sizeof(unsigned), stream);
+    void *args[] = {(void *)&P};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)approxmatch_kernel, dim3(grid), dim3(kEmdThreads), args, 0, stream);
+    if (e != cudaSuccess) { set_error("approxmatch: cooperative launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SNB200_ECUDA; }
     return check_launch("approxmatch");
 }
 
