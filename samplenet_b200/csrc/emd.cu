@@ -72,67 +72,86 @@ __device__ __forceinline__ void emd_grid_barrier(unsigned *counter, unsigned tar
 // vectors `finish` touches are per-cloud vectors addressed through `vec_stride`.
 template <typename F>
 __device__ __forceinline__ void emd_row_pass(int b, int nrows, int ncols, const float *prow, const float *pcol, const float *wcol, size_t vec_stride,
-                                             float level2, int S, float4 *s_o, F &&finish)
+                                             float level2, int S, float4 (*s_o)[kEmdTile], F &&finish)
 {
     const long long total = (long long)b * nrows;
     const long long per = (total + gridDim.x - 1) / gridDim.x;
     const long long lo = min(total, per * blockIdx.x), hi = min(total, lo + per);
     const int slots = kEmdThreads / S;              // row slots per pass
     const int slot = threadIdx.x / S, l_in = threadIdx.x % S;
-    long long seg = lo;
-    while (seg < hi) {                              // one cloud segment at a time (uniform over the CTA)
-        const int bi = (int)(seg / nrows);
-        const int r_beg = (int)(seg - (long long)bi * nrows);
-        const int r_end = (int)min((long long)nrows, r_beg + (hi - seg));
-        const float *pr = prow + (size_t)bi * nrows * 3, *pc = pcol + (size_t)bi * ncols * 3;
-        const float *wc = wcol + (size_t)bi * vec_stride;
-        for (int r0 = r_beg; r0 < r_end;) {
-            const bool two = (r_end - r0) > slots;       // enough rows left to give every slot a second one (CTA-uniform)
-            const int ra = r0 + slot, rb = r0 + slots + slot;
-            const bool la = ra < r_end, lb = two && rb < r_end;
-            float xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
-            if (la) { xa = pr[ra * 3 + 0]; ya = pr[ra * 3 + 1]; za = pr[ra * 3 + 2]; }
-            if (lb) { xb = pr[rb * 3 + 0]; yb = pr[rb * 3 + 1]; zb = pr[rb * 3 + 2]; }
-            float a0 = 0.f, a1 = 0.f;
-            for (int c0 = 0; c0 < ncols; c0 += kEmdTile) {
-                const int cn = min(kEmdTile, ncols - c0);
-                __syncthreads();
+    // A pass covers up to `slots` (or 2 x slots) consecutive flat rows taken from at most TWO consecutive clouds: the column tiles of
+    // both clouds are staged side by side and every thread reads the tile of its own row's cloud, so a chunk that straddles a cloud
+    // boundary still costs one sweep over the columns (a per-cloud loop would cost two and stall the whole grid at the next barrier).
+    for (long long f0 = lo; f0 < hi;) {
+        const int bi0 = (int)(f0 / nrows);
+        const long long cap = min(hi, (long long)(bi0 + 2) * nrows);             // rows of clouds bi0 and bi0 + 1 only
+        const long long split = (long long)(bi0 + 1) * nrows;                    // first flat row of cloud bi0 + 1
+        const bool two = (cap - f0) > slots && cap <= split;                     // second row per slot only inside one cloud (shares the LDS)
+        const long long fend = min(cap, f0 + (two ? 2 : 1) * (long long)slots);
+        const bool second_cloud = fend > split;                                  // CTA-uniform
+        const long long fa = f0 + slot, fb = f0 + slots + slot;
+        const bool la = fa < fend, lb = two && fb < fend;
+        const int sel = (la && fa >= split) ? 1 : 0;
+        const int bia = bi0 + sel;
+        const int ra = (int)(fa - (long long)bia * nrows), rb = (int)(fb - (long long)bi0 * nrows);
+        float xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
+        if (la) { const float *pr = prow + ((size_t)bia * nrows + ra) * 3; xa = pr[0]; ya = pr[1]; za = pr[2]; }
+        if (lb) { const float *pr = prow + ((size_t)bi0 * nrows + rb) * 3; xb = pr[0]; yb = pr[1]; zb = pr[2]; }
+        // the per-pair chain LDS -> 6 FMA-pipe ops -> MUFU -> FMA is ~70 cycles long: four independent accumulators (times the
+        // unroll) keep enough pairs in flight per thread for the issue slots to be the limit, not that latency
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c0 = 0; c0 < ncols; c0 += kEmdTile) {
+            const int cn = min(kEmdTile, ncols - c0);
+            __syncthreads();
+            for (int q = 0; q < (second_cloud ? 2 : 1); q++) {
+                const float *pc = pcol + (size_t)(bi0 + q) * ncols * 3;
+                const float *wc = wcol + (size_t)(bi0 + q) * vec_stride;
                 for (int c = threadIdx.x; c < cn; c += kEmdThreads)
-                    s_o[c] = make_float4(pc[(c0 + c) * 3 + 0], pc[(c0 + c) * 3 + 1], pc[(c0 + c) * 3 + 2], wc[c0 + c]);
-                __syncthreads();
-                if (la && two) {   // one shared-memory read feeds two rows
-#pragma unroll 4
-                    for (int c = l_in; c < cn; c += S) {
-                        const float4 o = s_o[c];
-                        a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o.x, o.y, o.z)), o.w, a0);
-                        a1 = fmaf(emd_ex2(level2 * emd_sq(xb, yb, zb, o.x, o.y, o.z)), o.w, a1);
-                    }
-                } else if (la) {
-                    int c = l_in;
+                    s_o[q][c] = make_float4(pc[(c0 + c) * 3 + 0], pc[(c0 + c) * 3 + 1], pc[(c0 + c) * 3 + 2], wc[c0 + c]);
+            }
+            __syncthreads();
+            const float4 *so = s_o[sel];
+            if (la && two) {   // one shared-memory read feeds two rows: a0/a2 row a, a1/a3 row b
+                int c = l_in;
 #pragma unroll 2
-                    for (; c + S < cn; c += 2 * S) {   // two independent accumulation chains
-                        const float4 o0 = s_o[c], o1 = s_o[c + S];
-                        a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
-                        a1 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o1.x, o1.y, o1.z)), o1.w, a1);
-                    }
-                    if (c < cn) {
-                        const float4 o0 = s_o[c];
-                        a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
-                    }
+                for (; c + S < cn; c += 2 * S) {
+                    const float4 o0 = so[c], o1 = so[c + S];
+                    a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
+                    a1 = fmaf(emd_ex2(level2 * emd_sq(xb, yb, zb, o0.x, o0.y, o0.z)), o0.w, a1);
+                    a2 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o1.x, o1.y, o1.z)), o1.w, a2);
+                    a3 = fmaf(emd_ex2(level2 * emd_sq(xb, yb, zb, o1.x, o1.y, o1.z)), o1.w, a3);
+                }
+                if (c < cn) {
+                    const float4 o0 = so[c];
+                    a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
+                    a1 = fmaf(emd_ex2(level2 * emd_sq(xb, yb, zb, o0.x, o0.y, o0.z)), o0.w, a1);
+                }
+            } else if (la) {
+                int c = l_in;
+#pragma unroll 2
+                for (; c + 3 * S < cn; c += 4 * S) {
+                    const float4 o0 = so[c], o1 = so[c + S], o2 = so[c + 2 * S], o3 = so[c + 3 * S];
+                    a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
+                    a1 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o1.x, o1.y, o1.z)), o1.w, a1);
+                    a2 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o2.x, o2.y, o2.z)), o2.w, a2);
+                    a3 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o3.x, o3.y, o3.z)), o3.w, a3);
+                }
+                for (; c < cn; c += S) {
+                    const float4 o0 = so[c];
+                    a0 = fmaf(emd_ex2(level2 * emd_sq(xa, ya, za, o0.x, o0.y, o0.z)), o0.w, a0);
                 }
             }
-            if (!two) { a0 += a1; a1 = 0.f; }
-            for (int o = S >> 1; o > 0; o >>= 1) {
-                a0 += __shfl_xor_sync(kFullMask, a0, o);
-                a1 += __shfl_xor_sync(kFullMask, a1, o);
-            }
-            if (l_in == 0) {
-                if (la) finish(bi, ra, a0);
-                if (lb) finish(bi, rb, a1);
-            }
-            r0 += two ? 2 * slots : slots;
         }
-        seg += r_end - r_beg;
+        if (two) { a0 += a2; a1 += a3; } else { a0 = (a0 + a1) + (a2 + a3); a1 = 0.f; }
+        for (int o = S >> 1; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(kFullMask, a0, o);
+            a1 += __shfl_xor_sync(kFullMask, a1, o);
+        }
+        if (l_in == 0) {
+            if (la) finish(bia, ra, a0);
+            if (lb) finish(bi0, rb, a1);
+        }
+        f0 = fend;
     }
 }
 
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(kEmdThreads, 2) approxmatch_kernel(const __gri
     const unsigned G = gridDim.x;
     unsigned epoch = 0;
 
-    __shared__ float4 s_o[kEmdTile];
+    __shared__ float4 s_o[2][kEmdTile];
 
     float multiL, multiR;  // tf_approxmatch_g.cu:4-10 (integer division)
     if (n >= m) { multiL = 1; multiR = (float)(n / m); } else { multiL = (float)(m / n); multiR = 1; }
@@ -190,7 +209,7 @@ __global__ void __launch_bounds__(kEmdThreads, 2) approxmatch_kernel(const __gri
     float lv2[kEmdLevels];
 #pragma unroll
     for (int li = 0; li < kEmdLevels; li++) lv2[li] = emd_level2(7 - li);
-    float *s_r = reinterpret_cast<float *>(s_o);            // [tile l][kEmdLevels] ratioR of the staged columns (reuses the tile buffer)
+    float *s_r = reinterpret_cast<float *>(&s_o[0][0]);     // [tile l][kEmdLevels] ratioR of the staged columns (reuses the tile buffer)
     constexpr int kFinTile = (kEmdTile * 4) / (kEmdLevels + 3);   // columns per stage: xyz (3) + ten ratios
     float *s_xyz = s_r + kFinTile * kEmdLevels;
     const int kblocks = (n + kEmdThreads - 1) / kEmdThreads, lchunks = (m + kFinTile - 1) / kFinTile;
@@ -250,8 +269,8 @@ int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2
     int S = 1;
     while (S < 32 && rows * (S * 2) <= (long long)grid * kEmdThreads / 2 && min(n, m) / (S * 2) >= 16) S *= 2;
     P.S = S;
-    const long long slots_needed = (rows * S + kEmdThreads - 1) / kEmdThreads;   // CTAs that would get at least one full pass
-    grid = (int)max(1ll, min((long long)grid, slots_needed));
+    const long long warps_needed = (rows * S + 31) / 32;   // keep the whole grid unless CTAs would get less than a warp of rows
+    grid = (int)max(1ll, min((long long)grid, warps_needed));
     cudaMemsetAsync(P.counter, 0, sizeof(unsigned), stream);
     void *args[] = {(void *)&P};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)approxmatch_kernel, dim3(grid), dim3(kEmdThreads), args, 0, stream);
@@ -287,14 +306,20 @@ __global__ void __launch_bounds__(kMcThreads) matchcost_partial_kernel(int b, in
             for (int u = 0; u < 4; u++) { x1[u] = p1[(k4 * 4 + u) * 3 + 0]; y1[u] = p1[(k4 * 4 + u) * 3 + 1]; z1[u] = p1[(k4 * 4 + u) * 3 + 2]; }
             const float4 *row = reinterpret_cast<const float4 *>(mt + (size_t)l_beg * n) + k4;
             const size_t stride4 = (size_t)(n >> 2);
-#pragma unroll 8
-            for (int l = l_beg; l < l_end; l++) {
-                const float4 w = __ldcs(row + (size_t)(l - l_beg) * stride4);   // streamed once: do not keep it in L2
-                const float x2 = s_p2[(l - l_beg) * 3 + 0], y2 = s_p2[(l - l_beg) * 3 + 1], z2 = s_p2[(l - l_beg) * 3 + 2];
-                sub += sqrtf(emd_sq(x1[0], y1[0], z1[0], x2, y2, z2)) * w.x;
-                sub += sqrtf(emd_sq(x1[1], y1[1], z1[1], x2, y2, z2)) * w.y;
-                sub += sqrtf(emd_sq(x1[2], y1[2], z1[2], x2, y2, z2)) * w.z;
-                sub += sqrtf(emd_sq(x1[3], y1[3], z1[3], x2, y2, z2)) * w.w;
+            const int nl = l_end - l_beg;
+            for (int lb = 0; lb < nl; lb += 8) {   // 8 independent 16-byte loads in flight per thread, then the arithmetic
+                float4 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[u] = (lb + u < nl) ? __ldcs(row + (size_t)(lb + u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int l = min(lb + u, nl - 1);
+                    const float x2 = s_p2[l * 3 + 0], y2 = s_p2[l * 3 + 1], z2 = s_p2[l * 3 + 2];
+                    sub += sqrtf(emd_sq(x1[0], y1[0], z1[0], x2, y2, z2)) * w[u].x;
+                    sub += sqrtf(emd_sq(x1[1], y1[1], z1[1], x2, y2, z2)) * w[u].y;
+                    sub += sqrtf(emd_sq(x1[2], y1[2], z1[2], x2, y2, z2)) * w[u].z;
+                    sub += sqrtf(emd_sq(x1[3], y1[3], z1[3], x2, y2, z2)) * w[u].w;
+                }
             }
         }
     } else {
@@ -324,17 +349,20 @@ __global__ void matchcost_final_kernel(int b, const float *__restrict__ partial,
     }
 }
 
-// grad1 (:263-291): grad1[k] = sum_l match[l][k] * (x1-x2) / max(|x1-x2|, 1e-10); thread per k (vector path: 4 consecutive k),
-// l broadcast from shared memory, loads of `match` several deep.
-constexpr int kMgThreads = 128;
+// grad1 (:263-291): grad1[k] = sum_l match[l][k] * (x1-x2) / max(|x1-x2|, 1e-10).  CTA = 8 warps over a block of k: lane = k (vector
+// path: 4 consecutive k), warp w takes the rows l == w (mod 8) with 8 loads in flight; the 8 partial sums of a k are combined through
+// shared memory in warp order (deterministic).
+constexpr int kMgThreads = 256;
 template <bool kVec>
 __global__ void __launch_bounds__(kMgThreads) matchcostgrad1_kernel(int b, int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                                    const float *__restrict__ match, float *__restrict__ grad1)
 {
     constexpr int W = kVec ? 4 : 1;
     __shared__ float s_o[kEmdTile * 3];
+    __shared__ float s_acc[8][32 * W * 3];
     const int bi = blockIdx.y;
-    const int k0 = (blockIdx.x * kMgThreads + threadIdx.x) * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = (blockIdx.x * 32 + lane) * W;
     const bool live = k0 < n;
     const float *p1 = xyz1 + (size_t)bi * n * 3, *p2 = xyz2 + (size_t)bi * m * 3;
     const float *mt = match + (size_t)bi * n * m;
@@ -351,32 +379,45 @@ __global__ void __launch_bounds__(kMgThreads) matchcostgrad1_kernel(int b, int n
         for (int i = threadIdx.x; i < ln * 3; i += kMgThreads) s_o[i] = p2[(size_t)l0 * 3 + i];
         __syncthreads();
         if (live) {
-#pragma unroll 8
-            for (int l = 0; l < ln; l++) {
-                float w[W];
-                if (kVec) {
-                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(mt + (size_t)(l0 + l) * n + k0));
-                    w[0] = v.x; w[W > 1 ? 1 : 0] = v.y; w[W > 2 ? 2 : 0] = v.z; w[W > 3 ? 3 : 0] = v.w;
-                } else {
-                    w[0] = __ldcs(mt + (size_t)(l0 + l) * n + k0);
-                }
-                const float x2 = s_o[l * 3 + 0], y2 = s_o[l * 3 + 1], z2 = s_o[l * 3 + 2];
+            for (int lb = warp; lb < ln; lb += 8 * 8) {
+                float w[8][W];
 #pragma unroll
-                for (int u = 0; u < W; u++) {
-                    const float ex = x1[u] - x2, ey = y1[u] - y2, ez = z1[u] - z2;
-                    const float d = w[u] * rsqrtf(fmaxf(ex * ex + ey * ey + ez * ez, 1e-20f));
-                    dx[u] += ex * d; dy[u] += ey * d; dz[u] += ez * d;
+                for (int q = 0; q < 8; q++) {
+                    const int l = lb + 8 * q;
+                    if (kVec) {
+                        const float4 v = (l < ln) ? __ldcs(reinterpret_cast<const float4 *>(mt + (size_t)(l0 + l) * n + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        w[q][0] = v.x; w[q][W > 1 ? 1 : 0] = v.y; w[q][W > 2 ? 2 : 0] = v.z; w[q][W > 3 ? 3 : 0] = v.w;
+                    } else {
+                        w[q][0] = (l < ln) ? __ldcs(mt + (size_t)(l0 + l) * n + k0) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int l = min(lb + 8 * q, ln - 1);
+                    const float x2 = s_o[l * 3 + 0], y2 = s_o[l * 3 + 1], z2 = s_o[l * 3 + 2];
+#pragma unroll
+                    for (int u = 0; u < W; u++) {
+                        const float ex = x1[u] - x2, ey = y1[u] - y2, ez = z1[u] - z2;
+                        const float d = w[q][u] * rsqrtf(fmaxf(ex * ex + ey * ey + ez * ez, 1e-20f));
+                        dx[u] += ex * d; dy[u] += ey * d; dz[u] += ez * d;
+                    }
                 }
             }
         }
     }
-    if (live) {
 #pragma unroll
-        for (int u = 0; u < W; u++)
-            if (k0 + u < n) {
-                float *g = grad1 + ((size_t)bi * n + k0 + u) * 3;
-                g[0] = dx[u]; g[1] = dy[u]; g[2] = dz[u];
-            }
+    for (int u = 0; u < W; u++) {
+        s_acc[warp][(lane * W + u) * 3 + 0] = dx[u]; s_acc[warp][(lane * W + u) * 3 + 1] = dy[u]; s_acc[warp][(lane * W + u) * 3 + 2] = dz[u];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * W * 3; e += kMgThreads) {
+        const int k = blockIdx.x * 32 * W + e / 3;
+        if (k < n) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; w8++) t += s_acc[w8][e];
+            grad1[((size_t)bi * n) * 3 + (size_t)blockIdx.x * 32 * W * 3 + e] = t;
+        }
     }
 }
 
@@ -445,8 +486,8 @@ int launch_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, 
 int launch_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2, cudaStream_t stream)
 {
     const bool vec = emd_vec_ok(n, match);
-    if (vec) matchcostgrad1_kernel<true><<<dim3((n / 4 + kMgThreads - 1) / kMgThreads, b), kMgThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
-    else matchcostgrad1_kernel<false><<<dim3((n + kMgThreads - 1) / kMgThreads, b), kMgThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
+    if (vec) matchcostgrad1_kernel<true><<<dim3((n + 127) / 128, b), kMgThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
+    else matchcostgrad1_kernel<false><<<dim3((n + 31) / 32, b), kMgThreads, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad1);
     int rc = check_launch("matchcostgrad1");
     if (rc) return rc;
     if (vec) matchcostgrad2_kernel<true><<<dim3((m + 7) / 8, b), 256, 0, stream>>>(b, n, m, xyz1, xyz2, match, grad2);

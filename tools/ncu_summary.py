@@ -44,7 +44,7 @@ def main():
                     u = units[h.index(name)]
                     try:
                         x = float(v)
-                        if scale == 1e-3 and u in ("ns", "nsecond"): x *= 1e-3
+                        if scale == 1e-3: x *= {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(u, 1.0)
                         if "byte" in u.lower():
                             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                             x *= mult
