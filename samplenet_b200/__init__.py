@@ -7,7 +7,7 @@ Importing the package does not need a GPU; calling any op does, and raises if th
 (no CPU fallback).
 """
 from . import _lib, ops, sputils, tf_ops  # noqa: F401
-from .graphs import GraphedStep, PipelinedHostStep  # noqa: F401
+from .graphs import GraphedStep, PipelinedHostStep, GraphedTrainStep  # noqa: F401
 from .chamfer_distance import ChamferDistance, ChamferDistanceFunction  # noqa: F401
 from .samplenet import SampleNet  # noqa: F401
 from .soft_projection import SoftProjection, knn_point  # noqa: F401

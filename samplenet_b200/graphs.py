@@ -134,3 +134,60 @@ class GraphedStep:
         self.loss_host.copy_(self.loss_flat, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return float(self.loss_host[0])
+
+
+class GraphedTrainStep:
+    """One whole TRAINING step -- forward, simplification + projection loss, backward, ONE flat-bucket gradient all-reduce (when a
+    process group is initialised) and the Adam update -- captured in a CUDA graph and replayed with one host call.
+
+        step = GraphedTrainStep(net, batch_size=32, num_points=1024, lr=1e-3)      # net: SampleNet, "bnc" in/out, training mode
+        loss = step(x_cuda)                                                          # 0-dim CUDA tensor (static buffer)
+
+    The eager training step is ~120 small launches (the generator's backward recomputes through torch ops) and is bound by host
+    launch overhead; the graph removes that.  The optimizer is `torch.optim.Adam(..., capturable=True)`; extra loss terms can be
+    supplied as `extra_loss(simp, proj) -> scalar` (e.g. the task network's loss in the reference trainers)."""
+
+    def __init__(self, net, batch_size, num_points, lr=1e-3, gamma=1, delta=0, alpha=0.01, lmbda=0.01, extra_loss=None, device=None, warmup=3):
+        from .parallel import FlatBucketDataParallel
+
+        dev = torch.device(device) if device is not None else next(net.parameters()).device
+        self.net, self.device = net, dev
+        if net.input_shape != "bnc" or net.output_shape != "bnc":
+            raise ValueError("GraphedTrainStep expects a SampleNet with input_shape = output_shape = 'bnc'")
+        self.ddp = FlatBucketDataParallel(net)
+        params = [p for p in net.parameters() if p.requires_grad]
+        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=True)
+        self.x = torch.zeros(batch_size, num_points, 3, device=dev)
+        m = net.num_out_points
+
+        def body():
+            self.ddp.zero_grad()
+            simp, proj = self.ddp(self.x)
+            loss = alpha * net.get_simplification_loss(self.x, simp, m, gamma, delta) + lmbda * net.get_projection_loss()
+            if extra_loss is not None:
+                loss = loss + extra_loss(simp, proj)
+            else:
+                loss = loss + (proj * proj).mean() * 0.0 + proj.sum() * 0.0   # keeps the projection (and its backward) in the step
+            loss.backward()
+            self.ddp.sync_gradients()
+            self.ddp.wait()
+            self.optimizer.step()
+            return loss.detach()
+
+        self.stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.device(dev):
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self.stream):
+                for _ in range(warmup):
+                    body()
+            self.stream.synchronize()
+            before = _lib.launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.loss = body()
+            self.launches_per_step = _lib.launch_count() - before
+
+    def __call__(self, x):
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.loss

