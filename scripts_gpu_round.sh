@@ -9,3 +9,7 @@ timeout -k 10 600 python bench.py --steps 200 --warmup 20 > gpurun_out/${TAG}_be
 timeout -k 10 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 SNB200_NO_GRAPH=1 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
 tail -5 gpurun_out/${TAG}_smoke.log; tail -40 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+# ncu --set full of the two step kernels (same bench command, eager launches) and the secondary configurations
+SNB200_NO_GRAPH=1 timeout -k 10 900 ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k 'regex:conv_stack|tail_fused' -s 8 -c 4 -o gpurun_out/${TAG}_prof -f python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout -k 10 600 python tools/bench_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err; echo "configs rc=$?"
+

@@ -13,3 +13,5 @@ for f in sorted(glob.glob('gpurun_out/*_bench_n[12].json')):
     except Exception as e: print(f, 'ERR', e)
 PY
 tail -3 gpurun_out/${TAG}_bench_n2.err
+timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/bench_configs.py --only train > gpurun_out/${TAG}_train_n2.jsonl 2> gpurun_out/${TAG}_train_n2.err; echo "train n2 rc=$?"; cat gpurun_out/${TAG}_train_n2.jsonl | cut -c1-300
+
