@@ -17,60 +17,63 @@ from . import _lib
 
 
 class PipelinedHostStep:
-    """End-to-end streaming of host batches through two `GraphedStep`s (double buffering): while step i computes, the pinned host
-    batch of step i+1 is already crossing PCIe on a copy stream.  Every step still ends with its loss on the host.
+    """End-to-end streaming of host batches through two `GraphedStep`s (double buffering): the pinned host batch of a later step
+    crosses PCIe on a copy stream while an earlier step computes, and up to two steps are in flight so the GPU always has the next
+    graph queued while the host reads the previous loss.  Every step still ends with its loss on the host.
 
         pipe = PipelinedHostStep(net, 32, 1024)
-        pipe.submit(batch0)                      # prime
-        for i in range(steps):
-            pipe.launch()                        # replay step i + loss read-back, asynchronous
-            pipe.submit(next_batch)              # H2D of step i+1 on the copy stream while step i computes
-            loss_i = pipe.finish()               # synchronise, loss of step i on the host
+        pipe.submit(batch0); pipe.launch()                 # step 0 in flight
+        pipe.submit(batch1); pipe.launch()                 # step 1 queued behind it
+        for i in range(2, steps):
+            loss = pipe.finish()                           # loss of the oldest step in flight, on the host
+            pipe.submit(batch_i); pipe.launch()            # its buffers are free again: refill and queue
+        pipe.finish(); pipe.finish()
     """
 
     def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None):
         self.slots = [GraphedStep(net, batch_size, num_points, gamma, delta, device) for _ in range(2)]
         self.device = self.slots[0].device
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        self.head = 0   # next slot to fill
-        self.tail = 0   # next slot to run
-        self.pending = 0
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # input of the slot has arrived
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]       # graph + loss read-back of the slot have finished
+        self.head = 0          # next slot to fill
+        self.next_launch = 0   # next slot to launch
+        self.submitted = []    # slots filled but not launched
+        self.inflight = []     # slots launched but not finished (oldest first)
         self.launches_per_step = self.slots[0].launches_per_step
-        for e in self.consumed:
+        for e in self.done:
             e.record(torch.cuda.current_stream(self.device))
 
     def submit(self, x_pinned):
-        if self.pending >= 2:
-            raise RuntimeError("PipelinedHostStep: both buffers are in flight; call step() first")
         k = self.head
-        self.copy_stream.wait_event(self.consumed[k])          # the graph that last read this buffer has finished
+        if k in self.submitted or k in self.inflight:
+            raise RuntimeError("PipelinedHostStep: both buffers are busy; call finish() first")
+        self.copy_stream.wait_event(self.done[k])              # the graph that last read this buffer has finished (device-side wait)
         with torch.cuda.stream(self.copy_stream):
             self.slots[k].x.copy_(x_pinned, non_blocking=True)
             self.ready[k].record(self.copy_stream)
+        self.submitted.append(k)
         self.head ^= 1
-        self.pending += 1
 
     def launch(self):
         """Enqueue the oldest submitted batch: graph replay + loss read-back (asynchronous)."""
-        if self.pending == 0:
+        if not self.submitted:
             raise RuntimeError("PipelinedHostStep: nothing submitted")
-        k = self.tail
+        k = self.submitted.pop(0)
         st = torch.cuda.current_stream(self.device)
         st.wait_event(self.ready[k])
         g = self.slots[k]
         g.replay()
         g.loss_host.copy_(g.loss_flat, non_blocking=True)
-        self.consumed[k].record(st)
-        self._inflight = k
+        self.done[k].record(st)
+        self.inflight.append(k)
 
     def finish(self):
-        """Wait for the launched step and return its loss (host float)."""
-        k = self._inflight
-        torch.cuda.current_stream(self.device).synchronize()
-        self.tail ^= 1
-        self.pending -= 1
+        """Wait for the oldest step in flight and return its loss (host float)."""
+        if not self.inflight:
+            raise RuntimeError("PipelinedHostStep: nothing in flight")
+        k = self.inflight.pop(0)
+        self.done[k].synchronize()
         return float(self.slots[k].loss_host[0])
 
     def step(self):
