@@ -31,7 +31,7 @@ class PipelinedHostStep:
     """
 
     def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None):
-        self.slots = [GraphedStep(net, batch_size, num_points, gamma, delta, device) for _ in range(2)]
+        self.slots = [GraphedStep(net, batch_size, num_points, gamma, delta, device, loss_to_host=True) for _ in range(2)]
         self.device = self.slots[0].device
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # input of the slot has arrived
@@ -63,8 +63,7 @@ class PipelinedHostStep:
         st = torch.cuda.current_stream(self.device)
         st.wait_event(self.ready[k])
         g = self.slots[k]
-        g.replay()
-        g.loss_host.copy_(g.loss_flat, non_blocking=True)
+        g.replay()                                            # includes the loss read-back into g.loss_host
         self.done[k].record(st)
         self.inflight.append(k)
 
@@ -82,8 +81,9 @@ class PipelinedHostStep:
 
 
 class GraphedStep:
-    def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None, warmup=2):
+    def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None, warmup=2, loss_to_host=False):
         self.net = net
+        self.loss_to_host = bool(loss_to_host)   # make the 4-byte loss read-back into pinned memory a node of the graph
         dev = torch.device(device) if device is not None else next(net.parameters()).device
         self.device = dev
         shape = (batch_size, num_points, 3) if net.input_shape == "bnc" else (batch_size, 3, num_points)
@@ -109,8 +109,10 @@ class GraphedStep:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.simp, self.proj, self.loss = body()
+                self.loss_flat = self.loss.reshape(1)
+                if self.loss_to_host:
+                    self.loss_host.copy_(self.loss_flat, non_blocking=True)     # the loss read-back is a node of the graph
             self.launches_per_step = _lib.launch_count() - before
-        self.loss_flat = self.loss.reshape(1)
         # SNB200_NO_GRAPH=1: launch the same kernels one by one instead of replaying the graph -- for profilers only (ncu cannot
         # attribute a cooperative launch inside a graph); results land in the same static buffers
         self._body = body
@@ -123,6 +125,8 @@ class GraphedStep:
         with torch.no_grad():
             simp, proj, loss = self._body()
             self.simp.copy_(simp); self.proj.copy_(proj); self.loss.copy_(loss)
+            if self.loss_to_host:
+                self.loss_host.copy_(self.loss_flat, non_blocking=True)
 
     def __call__(self, x):
         """x: CUDA tensor shaped like the capture buffer (copied device-to-device), returns the static outputs."""
@@ -134,7 +138,8 @@ class GraphedStep:
         """End-to-end step: pinned host batch -> device, replay, loss back to the host (synchronised); returns float."""
         self.x.copy_(x_pinned, non_blocking=True)
         self.replay()
-        self.loss_host.copy_(self.loss_flat, non_blocking=True)
+        if not self.loss_to_host:
+            self.loss_host.copy_(self.loss_flat, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return float(self.loss_host[0])
 
