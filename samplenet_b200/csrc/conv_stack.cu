@@ -17,6 +17,9 @@
 //     on the fly from the cloud and its statistics follow analytically from the batch's 9 input moments (phase 0);
 //   * the last layer never materialises: only per-tile column max / min leave the SM (the max-pool commutes with the monotone
 //     BN+ReLU map).
+//   * the max-pool finalise and the FC head (fc1..fc4 with BatchNorm over the batch) run as the tail of the same launch, 8 output
+//     channels per CTA; the 32 KB activation matrix of a layer travels between CTAs as self-validating words (a zeroed buffer,
+//     producers never store the bit pattern 0, consumers spin on the data itself): no grid barrier in the head.
 // Applicable when every CTA's tiles fit its TMEM (tiles <= 2 x CTAs, widths <= 128, K multiples of 32); otherwise the
 // per-layer kernels are used.
 #include "encoder_internal.cuh"
@@ -664,10 +667,10 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     if (warp == 16) cs_tmem_dealloc(tmem0, 512);
 
     // ================================================================================================================
-    // Fused tail: max-pool finalise + FC head (samplenet.py:97-104) on ALL CTAs of the grid.  Each FC layer's output
-    // channels are spread over the CTAs (BatchNorm over the batch stays inside one warp: lane = batch row), activations go
-    // through a few-KB global scratch that lives in L2, and the layers are separated by the same grid barrier.  Versus the
-    // 16-CTA cluster kernel this removes a launch and spreads each layer's latency chain over 9x more SMs.
+    // Fused tail: max-pool finalise + FC head (samplenet.py:97-104) on the CTAs of the grid.  Each FC layer's output channels
+    // are spread over the CTAs, 8 per CTA (BatchNorm over the batch stays inside one warp: lane = batch row); activations go
+    // through a few-KB global scratch that lives in L2 as self-validating words (cs_xchg_*), so the layers need no barrier.
+    // Versus the 16-CTA cluster kernel this removes a launch and spreads each layer's latency chain over more SMs.
     // ================================================================================================================
     if (!P.fuse_head) return;
     const HeadParams &H = P.H;

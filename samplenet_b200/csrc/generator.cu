@@ -1,17 +1,20 @@
-// generator.cu -- orchestration of the whole SampleNet generator (samplenet.py:90-104) and its fused FC head.
+// generator.cu -- orchestration of the whole SampleNet generator (samplenet.py:90-104): path selection, workspace layout, and the
+// stand-alone FC-head kernel of the non-fused paths.
 //
-//   training step at the headline size, tensor-core path:            launches
-//     cudaMemsetAsync(statistics)                                     (memset node)
-//     x_moments_kernel            input moments -> BN1 statistics      1
-//     tc_layer_kernel x4          layers 2..5 (layer 1 fused in #2)    4
-//     fc_head_cluster_kernel      max-pool finalise + fc1..fc4         1
+//   path (training step at the headline size)                                          launches
+//   default        cudaMemsetAsync(statistics, barrier word, FC exchange buffers)         (memset node)
+//                  conv_stack_kernel   conv 1..5 + pool + fc1..fc4, persistent cooperative   1      (conv_stack.cu)
+//   per-layer      memset; x_moments_kernel; tc_layer_kernel x4; fc_head_cluster_kernel      6      (encoder_tc.cu, here)
+//   exact fp32     memset; conv_layer_kernel x5; fc_head_cluster_kernel                      6      (encoder.cu, here)
+//   The default applies when the batch has at most 2 tiles of 128 points per SM and the conv widths are 32/64/128
+//   (conv_stack_supported); everything else falls through to the per-layer tensor-core path, then to exact fp32.
 //
-// The FC head (samplenet.py:99-104: 128->256->256->256->3M on B rows, BatchNorm over the batch) is tiny (7 MFLOP, 0.86 MB of
-// weights) but has four layer-to-layer dependencies; as separate launches it cost 4 x 17 us.  Here ONE thread-block
-// cluster runs all of it: every CTA owns a slice of the output channels of each layer (so BatchNorm over the batch never
-// leaves a warp: lane = batch row), activations are exchanged through a 32 KB global scratch that stays in L2, and layers
-// are separated by cluster barriers.  The same kernel first turns the last conv layer's per-tile extrema into the pooled
-// feature and applies every BatchNorm running-statistics update exactly once.
+// fc_head_cluster_kernel: the FC head (samplenet.py:99-104: 128->256->256->256->3M on B rows, BatchNorm over the batch) is tiny
+// (7 MFLOP, 0.86 MB of weights) but has four layer-to-layer dependencies.  ONE thread-block cluster of 16 CTAs runs all of it:
+// every CTA owns a slice of the output channels of each layer (so BatchNorm over the batch never leaves a warp: lane = batch
+// row), activations are exchanged through a 32 KB global scratch that stays in L2, and layers are separated by cluster
+// barriers.  The same kernel first turns the last conv layer's per-tile extrema into the pooled feature and applies every
+// BatchNorm running-statistics update exactly once.  (The default path runs the head inside conv_stack_kernel instead.)
 #include "encoder_internal.cuh"
 #include <cooperative_groups.h>
 #include <string.h>
