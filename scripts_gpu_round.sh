@@ -12,4 +12,5 @@ tail -5 gpurun_out/${TAG}_smoke.log; tail -40 gpurun_out/${TAG}_pytest.log; cat 
 # ncu --set full of the two step kernels (same bench command, eager launches) and the secondary configurations
 SNB200_NO_GRAPH=1 timeout -k 10 900 ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k 'regex:conv_stack|tail_fused' -s 8 -c 4 -o gpurun_out/${TAG}_prof -f python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout -k 10 600 python tools/bench_configs.py > gpurun_out/${TAG}_configs.jsonl 2> gpurun_out/${TAG}_configs.err; echo "configs rc=$?"
+timeout -k 10 600 ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k 'regex:approxmatch|matchcost' -s 5 -c 5 -o gpurun_out/${TAG}_emd -f python tools/run_emd.py > gpurun_out/${TAG}_ncu_emd.log 2>&1; echo "ncu emd rc=$?"
 
