@@ -672,6 +672,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // through a few-KB global scratch that lives in L2 as self-validating words (cs_xchg_*), so the layers need no barrier.
     // Versus the 16-CTA cluster kernel this removes a launch and spreads each layer's latency chain over more SMs.
     // ================================================================================================================
+    // Programmatic dependent launch: a kernel queued behind this one with the PDL attribute (the fused tail) may be scheduled onto
+    // SMs as this grid's CTAs exit; it synchronises on this grid's completion itself (griddepcontrol.wait) before touching our output.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!P.fuse_head) return;
     const HeadParams &H = P.H;
     // shared memory of the head (the conv stack's buffers are dead): input row group | partial sums | first weight rows of every layer

@@ -34,6 +34,9 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     // first wave; the short Chamfer tiles fill in behind them.  The projection role also IS the generated->input Chamfer
     // direction: the nearest neighbour of a query is lane 0 of its top-k list (same arithmetic, same lowest-index tie rule), so
     // dist1 / idx1 and their loss reductions come out of it for free and only the input->generated direction is scanned separately.
+    // Programmatic dependent launch: this grid may be scheduled while the producer of `samp` (the generator kernel) is still
+    // draining -- its launch latency and CTA start-up are hidden -- and waits here until that grid has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int n_knn = P.b * P.knn_ctas;
     const int ntiles = P.knn_ctas + P.ch.d[1].tiles;      // partial slots per cloud: projection CTAs, then direction-1 tiles
     float my_sum = 0.f, my_max = -INFINITY;
@@ -155,8 +158,15 @@ int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, con
         cudaFuncSetAttribute(tail_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     dim3 grid((unsigned)((long long)b * (P.knn_ctas + P.ch.d[1].tiles)));
-    if (flags & SNB200_DIST_UNFUSED) tail_fused_kernel<false><<<grid, 256, smem, stream>>>(P);
-    else tail_fused_kernel<true><<<grid, 256, smem, stream>>>(P);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // may start before the previous kernel of the stream has drained
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = (flags & SNB200_DIST_UNFUSED) ? cudaLaunchKernelEx(&cfg, tail_fused_kernel<false>, P) : cudaLaunchKernelEx(&cfg, tail_fused_kernel<true>, P);
+    if (e != cudaSuccess) { set_error("project_and_simplification_loss: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SNB200_ECUDA; }
     return check_launch("project_and_simplification_loss");
 }
 
