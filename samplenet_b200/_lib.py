@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsamplenet_b200.so")
 BNC, BCN = 0, 1
 DIST_FMA, DIST_UNFUSED = 0, 1
 GEN_EXACT_FP32 = 1
+GEN_WORKSPACE_PRIMED = 32
 SIGMA_VALUE, SIGMA_FROM_T_REG, SIGMA_FROM_T_CLS, SIGMA_FROM_T_REC = 0, 1, 2, 3
 
 _c_float_p = ctypes.c_void_p  # raw device pointers travel as integers

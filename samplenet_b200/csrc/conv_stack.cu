@@ -58,6 +58,11 @@ struct CsParams {
     float *tile_max, *tile_min;         // (tiles, c_last)
     int fuse_head;                      // run the pool + FC head as the tail of this launch
     HeadParams H;
+    // self-cleaning workspace (SNB200_GEN_WORKSPACE_PRIMED): the caller guarantees moments / barrier word / exit word are zero; the
+    // kernel zeroes [clean_ptr, clean_ptr + clean_bytes) itself before its first grid barrier and leaves the three words zero again
+    int self_clean;
+    char *clean_ptr;
+    unsigned clean_bytes;
 };
 
 // ---- tcgen05 helpers (same encodings as encoder_tc.cu, validated against fp64 in tests/test_gpu_parity.py::test_tc_gemm_3xtf32)
@@ -411,9 +416,15 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     unsigned barrier_epoch = 0;
     const double cnt = (double)P.b * (double)P.n, inv_cnt = 1.0 / cnt;
     CS_TS(1);
+    const bool need_stats = P.training != 0;
+    if (P.self_clean) {   // statistics accumulators and FC exchange words: zero before anybody adds to them (ordered by the first grid barrier)
+        float4 *z = reinterpret_cast<float4 *>(P.clean_ptr);
+        const unsigned n16 = P.clean_bytes >> 4;
+        for (unsigned e = blockIdx.x * kCsThreadsAll + tid; e < n16; e += G * kCsThreadsAll) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(need_stats && L1.has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // (no phase-0 barrier on this path)
+    }
 
     // ---- phase 0: input moments (training + BN after layer 1): 9 sums over this CTA's points, fp64 atomics, grid barrier
-    const bool need_stats = P.training != 0;
     if (need_stats && L1.has_bn) {
         if (producer) {
             float a9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -963,6 +974,17 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             base = (base + H.ru_c[l]) % gn;
         }
     }
+    if (P.self_clean) {   // the last CTA to leave puts the moments, the barrier word and the exit word back to zero for the next launch
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(P.barrier + 1, 1u) == G - 1) {
+                for (int j = 0; j < 16; j++) P.mom[j] = 0.0;
+                P.barrier[0] = 0u;
+                P.barrier[1] = 0u;
+            }
+        }
+    }
 }
 
 int debug_conv_stack_timestamps(long long *host_out64)
@@ -988,11 +1010,12 @@ bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
 
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
                       double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, const HeadParams *head,
-                      cudaStream_t stream)
+                      char *clean_ptr, size_t clean_bytes, cudaStream_t stream)
 {
     CsParams P;
     memset(&P, 0, sizeof(P));
     if (head) { P.fuse_head = 1; P.H = *head; }
+    if (head && clean_ptr) { P.self_clean = 1; P.clean_ptr = clean_ptr; P.clean_bytes = (unsigned)clean_bytes; }
     P.x = x; P.layout = layout; P.b = b; P.n = n;
     P.tiles_per_cloud = (n + kCsM - 1) / kCsM;
     P.tiles = b * P.tiles_per_cloud;

@@ -81,6 +81,6 @@ struct HeadParams {
 bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv);
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
                       double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, const HeadParams *head,
-                      cudaStream_t stream);
+                      char *clean_ptr, size_t clean_bytes, cudaStream_t stream);
 
 }  // namespace snb

@@ -463,7 +463,18 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     GenWorkspace W = carve_gen_ws(workspace, b, n, nconv, conv, nfc, fc);
     const bool coop = !(flags & (SNB200_GEN_EXACT_FP32 | SNB200_GEN_PER_LAYER_KERNELS | SNB200_GEN_PROFILE_SKIP_CONV)) && tc_stack_supported(nconv, conv) &&
                       conv_stack_supported(b, n, nconv, conv);
-    if (training || coop) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);   // statistics, moments, grid-barrier counter
+    // SNB200_GEN_WORKSPACE_PRIMED: the caller keeps this workspace for this call sequence and its first 256 bytes (moments, barrier
+    // and exit words) are zero -- freshly zeroed, or as the previous PRIMED call left them.  The persistent kernel then cleans the
+    // rest itself (no memset node in front of it); every other path memsets as usual and re-zeroes those 256 bytes at the end.
+    bool fuse_head_pre = !(flags & (SNB200_GEN_PROFILE_SKIP_HEAD | SNB200_GEN_SEPARATE_HEAD)) && b <= 256;
+    for (int l = 0; l < nfc; l++) fuse_head_pre = fuse_head_pre && fc[l].c_in <= 1024;
+    const bool primed = (flags & SNB200_GEN_WORKSPACE_PRIMED) != 0;
+    const bool self_clean = primed && coop && fuse_head_pre;
+    if ((training || coop) && !self_clean) cudaMemsetAsync(W.stats_base, 0, W.stats_bytes, stream);   // statistics, moments, grid-barrier counter
+    struct Rezero {   // non-self-cleaning paths leave the head of a PRIMED workspace as they found it
+        bool on; char *p; cudaStream_t s;
+        ~Rezero() { if (on) cudaMemsetAsync(p, 0, 256, s); }
+    } rezero{primed && !self_clean, W.stats_base, stream};
     const bool use_tc = !(flags & SNB200_GEN_EXACT_FP32) && tc_stack_supported(nconv, conv);
     int tpc = 0;
     if (flags & SNB200_GEN_PROFILE_SKIP_CONV) {
@@ -475,7 +486,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
         for (int l = 0; l < nfc; l++) fuse_head = fuse_head && fc[l].c_in <= 1024;
         if (fuse_head) fill_head_params(H, b, n, (n + 127) / 128, nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
         int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc,
-                                   fuse_head ? &H : nullptr, stream);
+                                   fuse_head ? &H : nullptr, (self_clean && fuse_head) ? W.stats_base + 256 : nullptr, W.stats_bytes - 256, stream);
         if (rc) return rc;
         if (fuse_head) return SNB200_OK;
     } else if (use_tc) {

@@ -13,7 +13,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 
 class PipelinedHostStep:
@@ -92,8 +92,11 @@ class GraphedStep:
         self.stream = torch.cuda.Stream(device=dev)
         m = net.num_out_points
 
+        self._pw = ops.PrimedWorkspaces()   # this step's persistent generator scratch: no memset node in front of the kernel
+
         def body():
-            simp, proj = net(self.x)
+            with ops.primed_workspaces(self._pw):
+                simp, proj = net(self.x)
             ref_bnc = self.x if net.input_shape == "bnc" else self.x.permute(0, 2, 1).contiguous()
             simp_bnc = simp if net.output_shape == "bnc" else simp.permute(0, 2, 1).contiguous()
             loss = net.get_simplification_loss(ref_bnc, simp_bnc, m, gamma, delta)
@@ -168,9 +171,12 @@ class GraphedTrainStep:
         self.x = torch.zeros(batch_size, num_points, 3, device=dev)
         m = net.num_out_points
 
+        self._pw = ops.PrimedWorkspaces()
+
         def body():
             self.ddp.zero_grad()
-            simp, proj = self.ddp(self.x)
+            with ops.primed_workspaces(self._pw):
+                simp, proj = self.ddp(self.x)
             loss = alpha * net.get_simplification_loss(self.x, simp, m, gamma, delta) + lmbda * net.get_projection_loss()
             if extra_loss is not None:
                 loss = loss + extra_loss(simp, proj)

@@ -5,6 +5,8 @@ CUDA graphs.  CPU tensors are rejected: there is no fallback path.
 """
 import ctypes
 
+import threading
+
 import torch
 
 from . import _lib
@@ -432,6 +434,41 @@ def make_layers(specs):
     return arr, keep
 
 
+class PrimedWorkspaces:
+    """Generator workspaces that persist across calls (one per size), zero-initialised once.  With one of these active
+    (`with primed_workspaces(pw): ...`) `generator_forward` passes SNB200_GEN_WORKSPACE_PRIMED: the persistent kernel cleans its own
+    scratch, so no memset is issued in front of it.  The owner promises the calls that share a buffer are stream-ordered
+    (GraphedStep / GraphedTrainStep own one each); plain calls outside such a context allocate and memset per call as before."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, dev, nbytes):
+        key = (dev.index, int(nbytes))
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.zeros(max(int(nbytes), 256), device=dev, dtype=torch.uint8)
+            self.bufs[key] = t
+        return t
+
+
+_ACTIVE_PW = threading.local()
+
+
+class primed_workspaces:
+    def __init__(self, pw):
+        self.pw = pw
+
+    def __enter__(self):
+        self.prev = getattr(_ACTIVE_PW, "pw", None)
+        _ACTIVE_PW.pw = self.pw
+        return self.pw
+
+    def __exit__(self, *exc):
+        _ACTIVE_PW.pw = self.prev
+        return False
+
+
 def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0, exact_fp32=False, _profile_flags=0, per_layer_kernels=False, separate_head=False):
     """x (B,N,3)/(B,3,N) -> (out (B, c_out_last), feat (B, c_conv_last)): conv stack + max-pool + FC head in ONE C-ABI call.
     Default: conv layers on the tensor cores (tcgen05, 3xTF32) + cluster-fused FC head; exact_fp32=True: CUDA-core conv stack."""
@@ -447,11 +484,17 @@ def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_i
     fc, keep2 = make_layers(fc_specs)
     with torch.cuda.device(dev):
         wsb = int(lib().snb200_generator_workspace_bytes(b, n, len(conv_specs), conv, len(fc_specs), fc))
-        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        pw = getattr(_ACTIVE_PW, "pw", None)
+        primed = 0
+        if pw is not None and not _profile_flags:
+            ws = pw.get(dev, wsb)
+            primed = _lib.GEN_WORKSPACE_PRIMED
+        else:
+            ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
         feat = torch.empty(b, conv[len(conv_specs) - 1].c_out, device=dev)
         out = torch.empty(b, fc[len(fc_specs) - 1].c_out, device=dev)
         check(lib().snb200_generator_forward(b, n, lay, _p(x), len(conv_specs), conv, len(fc_specs), fc, int(bool(training)), _p(out),
-                                             int(out_transpose_inner), _p(feat), (_lib.GEN_EXACT_FP32 if exact_fp32 else 0) | (8 if per_layer_kernels else 0) | (16 if separate_head else 0) | int(_profile_flags), _p(ws), wsb,
+                                             int(out_transpose_inner), _p(feat), (_lib.GEN_EXACT_FP32 if exact_fp32 else 0) | (8 if per_layer_kernels else 0) | (16 if separate_head else 0) | int(_profile_flags) | primed, _p(ws), wsb,
                                              _stream()), "generator_forward")
     del keep1, keep2
     return out, feat

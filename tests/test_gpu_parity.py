@@ -550,6 +550,27 @@ def test_graphed_step_and_host_pipeline_agree_with_eager(sb):
         pipe.finish()
 
 
+def test_primed_generator_workspace_is_self_cleaning(sb):
+    """SNB200_GEN_WORKSPACE_PRIMED: the persistent kernel cleans its own scratch, so repeated calls on one kept workspace give exactly
+    the per-call-memset results -- also after a call that took a non-self-cleaning path on the same workspace."""
+    torch.manual_seed(0)
+    net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda().train()
+    conv, fc = net._layer_specs()
+    g = torch.Generator().manual_seed(3)
+    xs = [(torch.rand(32, 1024, 3, generator=g) - 0.5).cuda() for _ in range(3)]
+    with torch.no_grad():
+        want = [sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)[0].clone() for x in xs]
+        pw = sb.ops.PrimedWorkspaces()
+        with sb.ops.primed_workspaces(pw):
+            got = [sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)[0].clone() for x in xs]
+            sb.ops.generator_forward(xs[0], "bnc", conv, fc, True, 64, per_layer_kernels=True)       # dirties, then re-zeroes the head
+            again = sb.ops.generator_forward(xs[1], "bnc", conv, fc, True, 64)[0].clone()
+        assert len(pw.bufs) == 1
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert torch.equal(again, want[1])
+
+
 def test_graphed_train_step_matches_eager_step(sb):
     """One captured training step (forward, losses, backward, Adam) == the same step issued eagerly: same loss, same updated weights."""
     def make():
