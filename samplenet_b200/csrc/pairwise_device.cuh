@@ -42,7 +42,7 @@ __device__ __forceinline__ float ld_coord(const float *base, int npts, int p, in
 // `tile_cap`), bar: an mbarrier in shared memory (initialised here).
 template <int kLayout, bool kFma>
 __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int bx, int bi, float *s_pts, uint64_t *barp,
-                                                  float *acc_sum = nullptr, float *acc_max = nullptr)
+                                                  float *acc_sum = nullptr, float *acc_max = nullptr, bool pdl = false)
 {
     uint64_t &bar = *barp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,6 +62,20 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
 
     uint32_t phase = 0;
     const int ntiles = (n + kSpTile - 1) / kSpTile;
+    // Programmatic dependent launch (fused tail): the cloud does not depend on the producer of the queries, so its tile is requested
+    // BEFORE this grid synchronises on the previous one; the queries are only read after griddepcontrol.wait.
+    bool preissued = false;
+    if (pdl) {
+        const bool tma_ok = kLayout == SNB200_BNC && ntiles == 1 && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0) && (((n * 3) & 3) == 0) && n > 0;
+        if (tma_ok) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, (uint32_t)n * 12u);
+                tma_load_1d(s_pts, pts, (uint32_t)n * 12u, &bar);
+            }
+            preissued = true;
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     // With a single tile (the common case: n <= 4096) the cloud is staged once and reused for all queries of the CTA.
     // With several tiles each query walks the tiles in order; the CTA restages per (query round, tile).
@@ -83,7 +97,10 @@ __device__ __forceinline__ void knn_softproj_body(const SoftProjParams &P, int b
             const int pn = min(kSpTile, n - p0);
             if (ntiles > 1 || qr == 0) {
                 if (!(t == 0 && qr == 0)) __syncthreads();
-                if (kLayout == SNB200_BNC) {
+                if (preissued && t == 0 && qr == 0) {
+                    mbar_wait(&bar, phase);   // the tile requested before griddepcontrol.wait
+                    phase ^= 1;
+                } else if (kLayout == SNB200_BNC) {
                     stage_floats(s_pts, pts + (size_t)p0 * 3, pn * 3, &bar, phase);
                 } else {
                     // three rows; issue them back to back on the same barrier when TMA-eligible

@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     // direction: the nearest neighbour of a query is lane 0 of its top-k list (same arithmetic, same lowest-index tie rule), so
     // dist1 / idx1 and their loss reductions come out of it for free and only the input->generated direction is scanned separately.
     // Programmatic dependent launch: this grid may be scheduled while the producer of `samp` (the generator kernel) is still
-    // draining -- its launch latency and CTA start-up are hidden -- and waits here until that grid has completed and flushed.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // draining -- its launch latency, CTA start-up and the staging of the input cloud are hidden -- and each role executes
+    // griddepcontrol.wait (previous grid complete and flushed) right before its first read of `samp`.
     const int n_knn = P.b * P.knn_ctas;
     const int ntiles = P.knn_ctas + P.ch.d[1].tiles;      // partial slots per cloud: projection CTAs, then direction-1 tiles
     float my_sum = 0.f, my_max = -INFINITY;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
     if ((int)blockIdx.x < n_knn) {   // ---- role A: projection + direction 0
         bi = (int)blockIdx.x / P.knn_ctas;
         slot = (int)blockIdx.x % P.knn_ctas;
-        knn_softproj_body<SNB200_BNC, kFma>(P.sp, slot, bi, s_dyn, &bar, &my_sum, &my_max);
+        knn_softproj_body<SNB200_BNC, kFma>(P.sp, slot, bi, s_dyn, &bar, &my_sum, &my_max, true);   // waits on the previous grid itself
     } else {                         // ---- role B: one tile of direction 1
         bi = ((int)blockIdx.x - n_knn) / P.ch.d[1].tiles;
         const int cx = ((int)blockIdx.x - n_knn) % P.ch.d[1].tiles;
@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(const __grid_constant__
             fence_mbar_init();
         }
         __syncthreads();
+        asm volatile("griddepcontrol.wait;" ::: "memory");     // the candidates ARE the previous grid's output
         chamfer_dir<kTailQ, kFma>(P.ch.d[1], cx, bi, s_dyn, &bar, &my_sum, &my_max);
     }
     // CTA partials (fixed order: warp shuffle tree, then warps in index order)
