@@ -42,6 +42,34 @@ def test_library_is_sm100a_with_tma_bulk_copies(sb):
     sass = subprocess.run(["cuobjdump", "-sass", sb._lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "UBLKCP" in sass  # cp.async.bulk (TMA) staging of the point tiles
+    assert "UTCHMMA" in sass and "LDTM" in sass  # tcgen05.mma kind::tf32 with the accumulators read back from tensor memory
+    assert "ACQBULK" in sass and "PREEXIT" in sass  # griddepcontrol.wait / launch_dependents (programmatic dependent launch)
+
+
+def test_primed_workspace_context_is_scoped_and_nestable(sb):
+    """Host logic of the self-cleaning-workspace opt-in (no launch): the provider is thread-local, scoped, and restored on exit."""
+    ops = sb.ops
+    assert getattr(ops._ACTIVE_PW, "pw", None) is None
+    a, b = ops.PrimedWorkspaces(), ops.PrimedWorkspaces()
+    with ops.primed_workspaces(a) as got:
+        assert got is a and ops._ACTIVE_PW.pw is a
+        with ops.primed_workspaces(b):
+            assert ops._ACTIVE_PW.pw is b
+        assert ops._ACTIVE_PW.pw is a
+        with pytest.raises(RuntimeError):
+            with ops.primed_workspaces(b):
+                raise RuntimeError("boom")
+        assert ops._ACTIVE_PW.pw is a
+    assert ops._ACTIVE_PW.pw is None
+    import threading
+    seen = []
+    with ops.primed_workspaces(a):
+        t = threading.Thread(target=lambda: seen.append(getattr(ops._ACTIVE_PW, "pw", None)))
+        t.start(); t.join()
+    assert seen == [None]
+    assert sb._lib.GEN_WORKSPACE_PRIMED == 32
+    hdr = open(os.path.join(ROOT, "include", "samplenet_b200.h")).read()
+    assert re.search(r"#define\s+SNB200_GEN_WORKSPACE_PRIMED\s+32", hdr)
 
 
 def test_samplenet_constructor_contract(sb):
