@@ -4,13 +4,16 @@
 // runs ONE CTA of 512 threads per cloud on a fixed grid of 32 CTAs (so at most 32 of the 148 SMs ever work), keeps the
 // remain/ratio vectors in global scratch, zeroes `match` and then read-modify-writes it once per level (10 sweeps).
 //
-// B200 design: a thread-block CLUSTER owns one cloud, so a batch of 50 clouds fills the chip.  The row dimension of every
-// phase is split over the cluster's CTAs and, inside a CTA, a row is shared by S lanes that each take the columns
-// j == lane (mod S) and merge their partial sums by shuffles; the opposite side (xyz + its per-point weight, as float4) is
-// staged through shared memory in tiles.  The four per-point vectors live in a small global scratch that stays in L2;
-// phases are separated by cluster barriers (release/acquire).  `match` is written (not accumulated) at the first level,
-// which removes the zero-fill sweep and one read sweep.  exp() is evaluated as ex2(level*log2e * d2) with the exact-range
-// intrinsic exp2f (not the reference's __expf), so values agree with the CPU oracle to fp32 rounding.
+// B200 design (approx_match): a persistent cooperative grid (two 512-thread CTAs per SM) walks the flat (cloud, row) index space
+// in equal chunks, so every SM works whatever the batch size is; inside a CTA a row is shared by S lanes that each take the
+// columns j == lane (mod S) and merge by shuffles; the opposite side (xyz + its per-point weight, as float4) is staged through
+// shared memory in tiles, for up to two consecutive clouds at once (a chunk that straddles a cloud boundary still costs one sweep).
+// The per-point vectors live in a small global scratch that stays in L2; the 30 phases are separated by a hand-written grid
+// barrier.  The ten levels only update those vectors (the per-level ratios are kept), and `match` is written ONCE by a final pass
+// that re-evaluates the ten weights of a pair in registers in level order -- no zero-fill, no read-modify-write sweeps.
+// exp(level*d) is evaluated as ex2(level*log2e * d) with one MUFU.EX2 (ex2.approx.ftz; the argument is <= 0, results below the
+// normal range flush to zero), so values agree with the CPU oracle to fp32 rounding (not the reference's __expf).
+// match_cost / match_cost_grad are streaming kernels that read `match` exactly once with 16-byte loads, eight in flight per thread.
 #include "common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
