@@ -3,8 +3,11 @@
 //
 // In the reference these are knn_cuda.KNN + grouping + ~8 torch ops (samplenet.py:114), then -- when the trainer asks for the
 // loss -- two Chamfer launches and four reductions (samplenet.py:175-180).  The projection and the Chamfer distances depend
-// only on (x, simp), not on each other, so they run as different CTA roles of one grid; the per-CTA partial sums / maxima are
-// combined by the last CTA to finish (ticket counter) in a fixed order, which keeps the loss bit-reproducible.
+// only on (x, simp), not on each other, so they run as different CTA roles of one grid: the projection CTAs also deliver the
+// generated->input Chamfer direction (the nearest neighbour is the head of the top-k list), the other CTAs scan input->generated;
+// the per-CTA partial sums / maxima are combined by the last CTA to finish (ticket counter) in a fixed order, which keeps the
+// loss bit-reproducible.  Launched with the programmatic-dependent-launch attribute: each role waits for the producer of `simp`
+// (griddepcontrol.wait) only right before it first reads `simp`, after the input cloud's tile has been requested.
 #include "pairwise_device.cuh"
 
 namespace snb {
