@@ -44,17 +44,41 @@ class ReferenceGenerator(nn.Module):
         return y.view(-1, 3, self.num_out_points)
 
 
-def cpu_step(gen, x_bnc, k, sigma, gamma=1.0, delta=0.0):
-    """One forward (train mode) + simplification loss on the CPU.  x_bnc: torch (B,N,3) float32.  Returns (simp, proj, loss)."""
+_POOL = {}
+
+
+def _pool(workers):
+    from concurrent.futures import ThreadPoolExecutor
+    if workers not in _POOL:
+        _POOL[workers] = ThreadPoolExecutor(max_workers=workers)
+    return _POOL[workers]
+
+
+def _over_clouds(fn, workers, *arrays):
+    """Run fn(chunk of every array) over contiguous chunks of the batch on `workers` threads (the C calls release the GIL) and
+    concatenate the results -- clouds are independent, so this is how the CPU path uses all host threads."""
+    b = arrays[0].shape[0]
+    if workers <= 1 or b <= 1:
+        return fn(*arrays)
+    w = min(workers, b)
+    bounds = [(b * i) // w for i in range(w + 1)]
+    futs = [_pool(w).submit(fn, *[np.ascontiguousarray(a[bounds[i]:bounds[i + 1]]) for a in arrays]) for i in range(w)]
+    parts = [f.result() for f in futs]
+    return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(len(parts[0])))
+
+
+def cpu_step(gen, x_bnc, k, sigma, gamma=1.0, delta=0.0, workers=1):
+    """One forward (train mode) + simplification loss on the CPU.  x_bnc: torch (B,N,3) float32.  Returns (simp, proj, loss).
+    workers > 1: kNN / projection / Chamfer run cloud-parallel on that many threads (the layer stack uses torch's own threads)."""
     with torch.no_grad():
         simp = gen(x_bnc.permute(0, 2, 1)).permute(0, 2, 1).contiguous().numpy()
     x = x_bnc.numpy()
-    _, idx = orc.knn_point(k, x, simp, contract=False, tie_mode=0)
-    proj, _, _ = orc.soft_project(x, simp, idx, float(sigma))
+    _, idx = _over_clouds(lambda a, q: orc.knn_point(k, a, q, contract=False, tie_mode=0), workers, x, simp)
+    proj, _, _ = _over_clouds(lambda a, q, i: orc.soft_project(a, q, i, float(sigma)), workers, x, simp, idx)
     if orc.have_ref():
-        c12, _, c21, _ = orc.ref_chamfer_forward(simp, x)
+        c12, _, c21, _ = _over_clouds(lambda q, a: orc.ref_chamfer_forward(q, a), workers, simp, x)
     else:
-        c12, _, c21, _ = orc.nn_distance(simp, x)
+        c12, _, c21, _ = _over_clouds(lambda q, a: orc.nn_distance(q, a), workers, simp, x)
     m = simp.shape[1]
     loss = np.float32(c12.mean(dtype=np.float32) + c12.max(axis=1).mean(dtype=np.float32) + np.float32(gamma + delta * m) * c21.mean(dtype=np.float32))
     return simp, proj, loss
