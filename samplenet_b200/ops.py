@@ -276,7 +276,10 @@ _TICKETS = {}
 
 
 def _ticket(dev):
-    """One zero-initialised device counter per GPU for the last-CTA reduction of the fused tail (the kernel leaves it zero)."""
+    """One zero-initialised device counter per GPU for the last-CTA reduction of the fused tail (the kernel leaves it zero).
+    Limitation (documented in DESIGN.md section 7): the word is shared by every fused-tail launch on that GPU, so such launches must be
+    stream-ordered with respect to each other (they are inside one training loop / one graph); two of them running CONCURRENTLY on
+    different streams of one device would share it.  The C ABI itself takes the word as an argument and has no such restriction."""
     key = (dev.type, dev.index)
     t = _TICKETS.get(key)
     if t is None:
