@@ -27,6 +27,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv[1:]:
+    # CPU arm: the step alternates between torch's OpenMP pool (layer stack) and a cloud-parallel worker pool (kNN / Chamfer); idle OpenMP
+    # threads must sleep, not spin, or they steal the cores from the workers (2x on 8 cores).  torchrun pins OMP_NUM_THREADS=1: undo that.
+    os.environ["OMP_WAIT_POLICY"] = "PASSIVE"
+    os.environ["KMP_BLOCKTIME"] = "0"
+    os.environ["GOMP_SPINCOUNT"] = "0"
+    os.environ.pop("OMP_NUM_THREADS", None)
+    os.environ.pop("MKL_NUM_THREADS", None)
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -94,39 +103,116 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(steps, warmup, threads=None):
+def _numa_cores():
+    """The logical CPUs of ONE NUMA node that this process may run on (the largest such group): a 32x3x1024 layer stack spread over
+    two sockets with 128 OpenMP threads is ~50x slower than the same code on 8-16 cores of one node (round-1 BENCH: 11.8 clouds/s)."""
+    import glob
+
+    aff = set(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else set(range(os.cpu_count() or 1))
+    best = sorted(aff)
+    groups = []
+    for path in sorted(glob.glob("/sys/devices/system/node/node*/cpulist")):
+        try:
+            cpus = set()
+            for part in open(path).read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            g = sorted(cpus & aff)
+            if g:
+                groups.append(g)
+        except Exception:
+            pass
+    if groups:
+        best = max(groups, key=len)
+    return best
+
+
+def cpu_reference_arm(steps, warmup):
+    """The reference's CPU path for the step, tuned once: pinned to one NUMA node; torch intra-op threads for the layer stack and the
+    number of cloud-parallel workers for kNN / projection / Chamfer are each chosen by a short sweep in the warm-up (the two phases
+    are sequential, so the sweep is separable); then `steps` full B=32 steps are timed with the best pair."""
     from oracle import oracle as orc
-    from oracle.torch_reference import ReferenceGenerator, cpu_step
+    from oracle.torch_reference import ReferenceGenerator, cpu_generator, cpu_pairwise
 
     orc._lib()
-    # all the host threads the CPU path can use: torch's intra-op pool for the layer stack (torchrun pins OMP_NUM_THREADS=1, undo that)
-    # and one worker per core, cloud-parallel, for the kNN / projection / Chamfer calls
-    cores = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    torch.set_num_threads(cores)
-    workers = max(1, min(cores, B))
+    cores = _numa_cores()
+    if hasattr(os, "sched_setaffinity"):
+        try:
+            os.sched_setaffinity(0, cores)      # before the OpenMP / worker pools exist: their threads inherit it
+        except OSError:
+            pass
+    ncore = len(cores)
     torch.manual_seed(0)
     gen = ReferenceGenerator(M, BOTTLENECK).train()
     xs = [synth_batch(100 + i) for i in range(4)]
-    for i in range(warmup):
-        cpu_step(gen, xs[i % 4], K_NN, 1.0, workers=workers)
+
+    def best_of(fn, reps=3):
+        fn()
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); t.append(time.perf_counter() - t0)
+        return min(t)
+
+    cand_t = sorted({t for t in (1, 2, 4, 8, 16, 24, 32, 48, 64) if t <= ncore} | {min(ncore, 64)})
+    sweep_t = {}
+    for t in cand_t:
+        torch.set_num_threads(t)
+        sweep_t[t] = best_of(lambda: cpu_generator(gen, xs[0]))
+    threads = min(sweep_t, key=sweep_t.get)
+    torch.set_num_threads(threads)
+    simp0 = cpu_generator(gen, xs[0])
+    cand_w = sorted({w for w in (1, 2, 4, 8, 16, 32) if w <= min(ncore, B)} | {min(ncore, B)})
+    sweep_w = {w: best_of(lambda: cpu_pairwise(xs[0], simp0, K_NN, 1.0, workers=w)) for w in cand_w}
+    workers = min(sweep_w, key=sweep_w.get)
+
+    def step(x):
+        simp = cpu_generator(gen, x)
+        return cpu_pairwise(x, simp, K_NN, 1.0, workers=workers)
+
+    for i in range(max(warmup, 1)):
+        step(xs[i % 4])
     t0 = time.perf_counter()
     for i in range(steps):
-        cpu_step(gen, xs[i % 4], K_NN, 1.0, workers=workers)
+        step(xs[i % 4])
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3, cores, ("reference" if orc.have_ref() else "port")
+    info = {"numa_node_cpus": ncore, "host_cpus": os.cpu_count(), "torch_threads": threads, "pairwise_workers": workers,
+            "sweep_generator_ms": {str(k): round(v * 1e3, 2) for k, v in sweep_t.items()},
+            "sweep_pairwise_ms": {str(k): round(v * 1e3, 2) for k, v in sweep_w.items()}}
+    return B * steps / dt, dt / steps * 1e3, max(threads, workers), ("port+reference" if orc.have_ref() else "port"), info
+
+
+CPU_SAMPLE = ("%d full steps of B=32 pinned to one NUMA node: torch CPU layer stack (restated module, %d intra-op threads) + C-oracle kNN/soft-proj "
+              "(port) + the reference's own CPU Chamfer compiled from its sources (oracle/_ref), cloud-parallel on %d worker threads; thread "
+              "counts picked by a sweep in the warm-up")
+
+
+def cpu_arm_subprocess(steps, warmup):
+    """Run the CPU arm in a fresh interpreter (clean OpenMP pool and affinity, no CUDA context) and return its parsed JSON line."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup)],
+                       env=env, capture_output=True, text=True, timeout=900)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("CPU arm produced no JSON line: %s" % r.stderr[-400:])
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    val, ms, cores, kind = cpu_reference_arm(args.steps, args.warmup)
+    val, ms, cores, kind, info = cpu_reference_arm(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clouds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B, "note": "CPU arm: rank 0 only, one replica, every step a full B=32 batch"},
         "cpu_baseline": {"value": val, "unit": "clouds/s", "cores": cores, "kind": kind,
-                         "sample": "%d full steps of B=32: torch CPU layer stack (all threads) + C-oracle kNN/soft-proj and the reference's CPU "
-                                   "Chamfer from oracle/_ref, cloud-parallel on one worker thread per core" % args.steps},
+                         "sample": CPU_SAMPLE % (args.steps, info["torch_threads"], info["pairwise_workers"]), "tuning": info},
         "e2e": {"value": val, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -324,8 +410,15 @@ def run_ours(args, rank, world, local_rank):
         "note": "arithmetic intensity of the pair work is 3*N*M*8 flop / 22.5 KB = 70 flop/B per cloud before top-k bookkeeping: with the machine "
                 "full these kernels are FP32-issue bound, not HBM bound (SURVEY.md section 8(d) caveat)",
     }
-    # ---- CPU baseline beside it (bounded: a few full B=32 steps)
-    cpu_val, cpu_ms, cores, kind = cpu_reference_arm(6, 2)
+    # ---- CPU baseline beside it (N=1 only; bounded: a few full B=32 steps, in a fresh interpreter pinned to one NUMA node)
+    cpu_base = None
+    if world == 1:
+        try:
+            cl = cpu_arm_subprocess(10, 3)
+            cpu_base = cl["cpu_baseline"]
+            cpu_base["ms_per_step"] = cl["ms_per_step"]
+        except Exception as exc:
+            cpu_base = {"error": str(exc)[:300]}
     line = {
         "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -340,9 +433,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "roofline_pairwise": roofline_pairwise,
         "kernel_us": kt,
-        "cpu_baseline": {"value": cpu_val, "unit": "clouds/s", "cores": cores, "kind": kind,
-                         "sample": "6 full steps of B=32 on the host: torch CPU layer stack (%d threads) + C-oracle kNN/soft-proj and the reference's "
-                                   "CPU Chamfer (oracle/_ref), cloud-parallel on one worker thread per core" % cores, "ms_per_step": cpu_ms},
+        "cpu_baseline": cpu_base,
     }
     print(json.dumps(line), flush=True)
 

@@ -67,11 +67,15 @@ def _over_clouds(fn, workers, *arrays):
     return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(len(parts[0])))
 
 
-def cpu_step(gen, x_bnc, k, sigma, gamma=1.0, delta=0.0, workers=1):
-    """One forward (train mode) + simplification loss on the CPU.  x_bnc: torch (B,N,3) float32.  Returns (simp, proj, loss).
-    workers > 1: kNN / projection / Chamfer run cloud-parallel on that many threads (the layer stack uses torch's own threads)."""
+def cpu_generator(gen, x_bnc):
+    """The layer stack (torch CPU kernels, torch's intra-op threads): x (B,N,3) torch -> simp (B,M,3) numpy."""
     with torch.no_grad():
-        simp = gen(x_bnc.permute(0, 2, 1)).permute(0, 2, 1).contiguous().numpy()
+        return gen(x_bnc.permute(0, 2, 1)).permute(0, 2, 1).contiguous().numpy()
+
+
+def cpu_pairwise(x_bnc, simp, k, sigma, gamma=1.0, delta=0.0, workers=1):
+    """kNN + soft projection (C oracle) and Chamfer (the reference's CPU code when oracle/_ref exists) + the loss reductions,
+    cloud-parallel on `workers` threads.  Returns (proj, loss)."""
     x = x_bnc.numpy()
     _, idx = _over_clouds(lambda a, q: orc.knn_point(k, a, q, contract=False, tie_mode=0), workers, x, simp)
     proj, _, _ = _over_clouds(lambda a, q, i: orc.soft_project(a, q, i, float(sigma)), workers, x, simp, idx)
@@ -81,4 +85,12 @@ def cpu_step(gen, x_bnc, k, sigma, gamma=1.0, delta=0.0, workers=1):
         c12, _, c21, _ = _over_clouds(lambda q, a: orc.nn_distance(q, a), workers, simp, x)
     m = simp.shape[1]
     loss = np.float32(c12.mean(dtype=np.float32) + c12.max(axis=1).mean(dtype=np.float32) + np.float32(gamma + delta * m) * c21.mean(dtype=np.float32))
+    return proj, loss
+
+
+def cpu_step(gen, x_bnc, k, sigma, gamma=1.0, delta=0.0, workers=1):
+    """One forward (train mode) + simplification loss on the CPU.  x_bnc: torch (B,N,3) float32.  Returns (simp, proj, loss).
+    workers > 1: kNN / projection / Chamfer run cloud-parallel on that many threads (the layer stack uses torch's own threads)."""
+    simp = cpu_generator(gen, x_bnc)
+    proj, loss = cpu_pairwise(x_bnc, simp, k, sigma, gamma, delta, workers)
     return simp, proj, loss
