@@ -200,6 +200,12 @@ int snb200_fc_head_forward(int b, const float *in, int num_layers, const snb200_
 size_t snb200_approxmatch_workspace_bytes(int b, int n, int m);
 int snb200_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace,
                        size_t workspace_bytes, snb200_stream_t stream);
+/* flags & SNB200_EMD_EXACT: the parity mode -- exact exponential (exp in double, rounded to float), one float accumulator per row summed in
+ * index order, the reference's level order and per-level read-modify-write of `match`: operation-for-operation the arithmetic of the CPU
+ * oracle, so match values AND arg-max assignments are bit-identical to it (workspace unused).  Without the flag: the fast kernel. */
+#define SNB200_EMD_EXACT 1
+int snb200_approxmatch_mode(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, int flags, void *workspace,
+                            size_t workspace_bytes, snb200_stream_t stream);
 size_t snb200_matchcost_workspace_bytes(int b);
 int snb200_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *cost,
                      void *workspace, size_t workspace_bytes, snb200_stream_t stream);

@@ -13,6 +13,7 @@ BNC, BCN = 0, 1
 DIST_FMA, DIST_UNFUSED = 0, 1
 GEN_EXACT_FP32 = 1
 GEN_WORKSPACE_PRIMED = 32
+EMD_EXACT = 1
 SIGMA_VALUE, SIGMA_FROM_T_REG, SIGMA_FROM_T_CLS, SIGMA_FROM_T_REC = 0, 1, 2, 3
 
 _c_float_p = ctypes.c_void_p  # raw device pointers travel as integers
@@ -60,6 +61,7 @@ _SIGNATURES = {
     "snb200_fc_head_forward": (_int, [_int, _vp, _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _size, _vp]),
     "snb200_approxmatch_workspace_bytes": (_size, [_int, _int, _int]),
     "snb200_approxmatch": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _size, _vp]),
+    "snb200_approxmatch_mode": (_int, [_int, _int, _int, _vp, _vp, _vp, _int, _vp, _size, _vp]),
     "snb200_matchcost_workspace_bytes": (_size, [_int]),
     "snb200_matchcost": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _size, _vp]),
     "snb200_matchcostgrad": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -43,6 +43,7 @@ int launch_fc_head_forward(int b, const float *in, int num_layers, const snb200_
                            void *workspace, cudaStream_t stream);
 size_t approxmatch_workspace_bytes(int b, int n, int m);
 int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace, cudaStream_t stream);
+int launch_approxmatch_exact(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, cudaStream_t stream);
 int launch_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *cost, float *partial, cudaStream_t stream);
 int launch_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2, cudaStream_t stream);
 int launch_nn_matching(int b, int n, int t, int k, const float *full_pc, const int *nn_idx, int complete_fps, float *out, int *out_idx,
@@ -308,6 +309,16 @@ SNB_API int snb200_approxmatch(int b, int n, int m, const float *xyz1, const flo
         return SNB200_EWORKSPACE;
     }
     return launch_approxmatch(b, n, m, xyz1, xyz2, match, workspace, (cudaStream_t)stream);
+}
+
+SNB_API int snb200_approxmatch_mode(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, int flags, void *workspace,
+                                    size_t workspace_bytes, snb200_stream_t stream)
+{
+    if (!(flags & SNB200_EMD_EXACT)) return snb200_approxmatch(b, n, m, xyz1, xyz2, match, workspace, workspace_bytes, stream);
+    SNB_REQUIRE(b >= 0 && n >= 1 && m >= 1, "approxmatch: bad sizes b=%d n=%d m=%d", b, n, m);
+    if (b == 0) return SNB200_OK;
+    SNB_REQUIRE(xyz1 && xyz2 && match, "approxmatch: null pointer");
+    return launch_approxmatch_exact(b, n, m, xyz1, xyz2, match, (cudaStream_t)stream);
 }
 
 SNB_API size_t snb200_matchcost_workspace_bytes(int b) { return (size_t)b * 16 * sizeof(float); }

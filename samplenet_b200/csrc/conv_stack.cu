@@ -1,41 +1,43 @@
-// conv_stack.cu -- the whole per-point MLP (conv layers 1..L, samplenet.py:90-94) as ONE persistent cooperative kernel whose
-// activations never leave the SM.
+// conv_stack.cu -- the whole per-point MLP (conv layers 1..L, samplenet.py:90-94), the max-pool and the FC head as ONE persistent
+// cooperative kernel whose activations never leave the SM.
 //
-// Per-layer kernels (encoder_tc.cu) pay, per layer, a launch, a 8-17 MB activation write + read through L2 and a cold
-// prologue/epilogue; at B=32 that is 65 us for 2.1 GFLOP.  Here every CTA (one per SM) owns up to TWO 128-point tiles for the
-// whole stack:
-//   * the raw (pre-BatchNorm) output of layer l stays in TENSOR MEMORY (128 lanes x c_out columns per tile; two ping-pong
-//     regions per tile slot = 4 x 128 columns = the SM's 512 TMEM columns);
-//   * layer l+1's A operand is produced straight from TMEM: tcgen05.ld (thread = point row) -> BatchNorm + ReLU of layer l ->
-//     exact hi/lo TF32 split -> canonical K-major SWIZZLE_128B shared-memory tile (ring of two 32-wide K chunks), so operand
-//     preparation of chunk k+1 overlaps the tcgen05.mma of chunk k (3 MMAs per K-step: lo*hi, hi*lo, hi*hi);
-//   * the layer's weights are split and staged once per CTA per layer (while the previous layer's MMAs and the grid barrier
-//     are in flight);
-//   * training-mode BatchNorm needs batch statistics of layer l before layer l+1 can start: per-tile column sums are reduced
-//     with a halving shuffle network (31 shuffles per 32x32 block), combined per CTA and added to fp64 global accumulators,
-//     and a grid-wide barrier (cooperative launch, one atomic counter) separates the layers.  Layer 1 (3 -> 64) is evaluated
-//     on the fly from the cloud and its statistics follow analytically from the batch's 9 input moments (phase 0);
-//   * the last layer never materialises: only per-tile column max / min leave the SM (the max-pool commutes with the monotone
-//     BN+ReLU map).
+// Round-2 design: the GEMMs are TRANSPOSED.  Every CTA (one per SM) owns `ppc` consecutive points of the flattened batch
+// (ppc = ceil(B*N / #SMs) rounded up to 32: 224 at the headline size, so all 148 SMs carry the same load) for the whole stack and
+// computes, per layer,            D^T[c_out x ppc] = W[c_out x K] . A^T[K x ppc]
+//   * MMA A operand = the layer's weights, exact hi/lo TF32 split, held in TENSOR MEMORY (A-from-TMEM form of tcgen05.mma, columns
+//     256..511: no shared-memory traffic for the weights during the MMAs), M = 128 rows (zero rows above c_out);
+//   * MMA B operand = the activations: "N x K, K-major" SWIZZLE_128B tiles in shared memory, one 32-wide K chunk (hi + lo) per ring
+//     slot, ring of three slots; N = ppc: ONE instruction covers all of the CTA's points (3 MMAs per K step of 8: lo*hi, hi*lo, hi*hi);
+//   * the accumulator has TMEM lane = output channel, column = point.  A thread therefore owns ONE channel and ppc/4 points: the
+//     BatchNorm batch statistics, the pool's max / min and the BatchNorm scale / shift are plain per-thread register loops -- no
+//     shuffle networks, no per-channel tables in shared memory; the raw outputs of a layer are read from tensor memory ONCE
+//     (tcgen05.ld, bias added) and stay in registers across the statistics grid barrier until they are normalised, split and stored
+//     as the next layer's B operand (a warp's 32 lanes are the 32 consecutive k of one swizzled 128-byte row: conflict-free STS.32);
+//   * training-mode BatchNorm needs the batch statistics of layer l before layer l+1 can start: per-CTA partial sums go to fp64
+//     global accumulators and a grid-wide barrier (cooperative launch, one counter) separates the layers.  Layer 1 (3 -> C) is
+//     evaluated on CUDA cores and its statistics follow analytically from the batch's 9 input moments (phase 0);
+//   * the last layer never materialises: only per-(CTA, cloud) max / min leave the SM (the max-pool commutes with the monotone
+//     BN+ReLU map);
 //   * the max-pool finalise and the FC head (fc1..fc4 with BatchNorm over the batch) run as the tail of the same launch, 8 output
 //     channels per CTA; the 32 KB activation matrix of a layer travels between CTAs as self-validating words (a zeroed buffer,
 //     producers never store the bit pattern 0, consumers spin on the data itself): no grid barrier in the head.
-// Applicable when every CTA's tiles fit its TMEM (tiles <= 2 x CTAs, widths <= 128, K multiples of 32); otherwise the
-// per-layer kernels are used.
+// Applicable when B*N <= 256 x #SMs, widths <= 128 and K in {32, 64, 128}; otherwise the per-layer kernels are used.
 #include "encoder_internal.cuh"
 #include <cooperative_groups.h>
 #include <string.h>
 
 namespace snb {
 
-constexpr int kCsThreads = 256;
-constexpr int kCsM = 128;
 constexpr int kCsMaxLayers = SNB200_MAX_CONV_LAYERS;
-constexpr int kCsSlots = 2;           // tiles per CTA
-constexpr int kCsRegion = 128;        // TMEM columns per (slot, parity) region
-constexpr int kCsProducers = 512;     // 16 producer warps = 2 groups of 8; group (warp >> 3) prepares the K chunks of its parity
-constexpr int kCsGroup = 256;
-constexpr int kCsThreadsAll = kCsProducers + 32;
+constexpr int kCsProducers = 512;     // 16 producer warps: warp & 3 = TMEM lane quarter (32 channels), warp >> 2 = column (point) group
+constexpr int kCsThreadsAll = kCsProducers;        // (17 warps would cap the kernel at 96 registers: 5 warps on one scheduler)
+constexpr int kCsIssuerWarp = 15;     // the producer warp whose lane 0 also issues the MMAs (q = 3: it owns a K chunk only in 128-wide layers)
+constexpr int kCsMaxPts = 256;        // points per CTA = MMA N
+constexpr int kCsMinPts = 64;
+constexpr int kCsNPT = kCsMaxPts / 4; // points per thread (register array)
+constexpr int kCsRing = 3;            // ring slots of one 32-wide K chunk (hi + lo)
+constexpr int kCsMaxSeg = 8;          // clouds a CTA's point range may touch
+constexpr uint32_t kCsColWhi = 256, kCsColWlo = 384;   // tensor-memory columns of the weight operand (D occupies 0..255)
 
 struct CsLayer {
     int c_in, c_out;
@@ -49,13 +51,16 @@ struct CsLayer {
 
 struct CsParams {
     const float *x; int layout;
-    int b, n, tiles, tiles_per_cloud;
+    int b, n;
+    long long total;                    // b * n points
+    int ppc, npt;                       // points per CTA (multiple of 32), points per thread = ppc / 4
+    int slots_per_cloud;                // pool partials: (cloud, slot) with slot = CTA index - first CTA touching the cloud
     int num_layers;                     // including layer 1
     CsLayer L[kCsMaxLayers];
     int training;
     double *mom;                        // [9] input moments (zeroed by the caller)
     unsigned *barrier;                  // grid barrier counter (zeroed by the caller)
-    float *tile_max, *tile_min;         // (tiles, c_last)
+    float *tile_max, *tile_min;         // (b, slots_per_cloud, c_last)
     int fuse_head;                      // run the pool + FC head as the tail of this launch
     HeadParams H;
     // self-cleaning workspace (SNB200_GEN_WORKSPACE_PRIMED): the caller guarantees moments / barrier word / exit word are zero; the
@@ -77,42 +82,9 @@ __device__ __forceinline__ void cs_tmem_dealloc(uint32_t taddr, uint32_t ncols)
 }
 __device__ __forceinline__ void cs_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void cs_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void cs_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void cs_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cs_ld16(uint32_t taddr, float *v)
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void cs_ld16_issue(uint32_t taddr, uint32_t *r)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
 }
 __device__ __forceinline__ void cs_ld8_issue(uint32_t taddr, uint32_t *r)
 {
@@ -122,23 +94,6 @@ __device__ __forceinline__ void cs_ld8_issue(uint32_t taddr, uint32_t *r)
                  : "memory");
 }
 __device__ __forceinline__ void cs_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cs_ld32(uint32_t taddr, float *v)
-{
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-          "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
 __host__ __device__ constexpr uint32_t cs_idesc(int M, int N)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -147,17 +102,6 @@ constexpr unsigned kCsDescHi = (64u) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint64_t cs_sdesc(uint32_t smem_addr)
 {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)kCsDescHi << 32);
-}
-__device__ __forceinline__ uint32_t cs_sw128(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
-__device__ __forceinline__ void cs_split_store(unsigned char *hi_base, unsigned char *lo_base, uint32_t off, float4 v)
-{
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-    *reinterpret_cast<float4 *>(hi_base + off) = h;
-    *reinterpret_cast<float4 *>(lo_base + off) = l;
 }
 
 // bounded waits: a protocol bug must not hang the GPU box -- trap instead (surfaces as a launch failure in the next API call)
@@ -228,75 +172,6 @@ __device__ __forceinline__ uint4 cs_xchg_load4(const float *p)   // four consecu
     return v;
 }
 
-// Column reduction of a 32x32 block held one row per lane: after the 5 halving steps lane i holds the combined value of
-// column i (31 shuffles instead of 160).  OP: 0 = sum, 1 = max, 2 = min.
-template <int OP>
-__device__ __forceinline__ float cs_colreduce(float *s, int lane)
-{
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool up = (lane & half) != 0;
-#pragma unroll
-        for (int j = 0; j < half; j++) {
-            const float send = up ? s[j] : s[j + half];
-            const float keep = up ? s[j + half] : s[j];
-            const float recv = __shfl_xor_sync(kFullMask, send, half);
-            s[j] = OP == 0 ? keep + recv : (OP == 1 ? fmaxf(keep, recv) : fminf(keep, recv));
-        }
-    }
-    return s[0];
-}
-
-// Split + swizzled staging of one layer's whole weight matrix (all K) into shared memory, by the 256 producer threads.
-// Only legal once every MMA that reads the previous layer's weights has completed.
-__device__ __forceinline__ void cs_stage_weights(const CsLayer &Lc, unsigned char *sWhi, float *sBias, int tid)
-{
-    const int K = Lc.c_in, N = Lc.c_out;
-    const int npad = N <= 64 ? 64 : 128;
-    const uint32_t atomB = (uint32_t)npad * 128u;
-    unsigned char *sWlo = sWhi + (size_t)(K >> 5) * atomB;
-    const int sh4 = (K == 32) ? 3 : (K == 64 ? 4 : 5);   // log2(K / 4); K is 32, 64 or 128 on this path
-    const int q4m = (1 << sh4) - 1, total = npad << sh4;
-    for (int e0 = tid; e0 < total; e0 += kCsProducers * 8) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int e = e0 + u * kCsProducers;
-            const int nrow = e >> sh4, kq = e & q4m;
-            v[u] = (e < total && nrow < N) ? __ldg(reinterpret_cast<const float4 *>(Lc.weight + (size_t)nrow * K) + kq) : make_float4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int e = e0 + u * kCsProducers;
-            if (e < total) {
-                const int nrow = e >> sh4, kq = e & q4m;
-                cs_split_store(sWhi, sWlo, (uint32_t)(kq >> 3) * atomB + cs_sw128(nrow, kq & 7), v[u]);
-            }
-        }
-    }
-    for (int c = tid; c < npad; c += kCsProducers) sBias[c] = (c < N && Lc.bias) ? __ldg(Lc.bias + c) : 0.f;
-    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
-}
-
-// 32 rows x 16 columns held one row per lane: after the five steps lanes 2c and 2c+1 both hold the combined value of column c.
-template <int OP>
-__device__ __forceinline__ float cs_colreduce16(float *s, int lane)
-{
-#pragma unroll
-    for (int half = 8; half >= 1; half >>= 1) {
-        const bool up = (lane & (half * 2)) != 0;
-#pragma unroll
-        for (int j = 0; j < half; j++) {
-            const float send = up ? s[j] : s[j + half];
-            const float keep = up ? s[j + half] : s[j];
-            const float recv = __shfl_xor_sync(kFullMask, send, half * 2);
-            s[j] = OP == 0 ? keep + recv : (OP == 1 ? fmaxf(keep, recv) : fminf(keep, recv));
-        }
-    }
-    const float o = __shfl_xor_sync(kFullMask, s[0], 1);
-    return OP == 0 ? s[0] + o : (OP == 1 ? fmaxf(s[0], o) : fminf(s[0], o));
-}
-
 // 8 weight rows (output channels cb..cb+nch-1) of an FC layer into shared memory, row-major as in HBM
 __device__ __forceinline__ void cs_head_stage_weights(const HeadLayer &L, int cb, int nch, float *s_wh, int tid, bool producer)
 {
@@ -326,6 +201,27 @@ __device__ __forceinline__ void cs_head_stage_weights(const HeadLayer &L, int cb
     }
 }
 
+
+// A-from-TMEM form: D[tmem] (+)= A[tmem, 128 lanes x 8 columns] . B[smem descriptor]
+__device__ __forceinline__ void cs_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void cs_st8(uint32_t taddr, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void cs_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ long long g_cs_ts[64];
 #define CS_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_cs_ts[(i)] = clock64(); } while (0)
 
@@ -335,75 +231,142 @@ __device__ __forceinline__ void cs_mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Thread roles: warps 0..7 (256 threads) are PRODUCERS (operand preparation, weight staging, epilogues); warp 8 is the MMA
-// ISSUER (lane 0 issues tcgen05.mma / tcgen05.commit, the warp only waits on mbarriers).  Producers and issuer walk the
-// same (layer, slot, chunk) sequence and meet through mbarriers, never through __syncthreads inside the main loop:
-//   bar_full[rb]  producers -> issuer : ring buffer rb holds a prepared 32-wide K chunk   (256 arrivals)
-//   bar_ring[rb]  tensor core -> producers : the MMAs that read ring buffer rb have completed (tcgen05.commit)
-//   bar_acc[s]    tensor core -> producers : every MMA of tile slot s of this layer has completed
+// One layer's weight row `ch`, columns [g*K/4, (g+1)*K/4), global -> registers (zero rows above c_out).  w holds up to 32 values.
+__device__ __forceinline__ void cs_load_w(const CsLayer &L, int ch, int g, float *w)
+{
+    const int K4 = L.c_in >> 2;
+    const bool valid = ch < L.c_out;
+    const float4 *src = reinterpret_cast<const float4 *>(L.weight + (size_t)(valid ? ch : 0) * L.c_in + g * K4);
+#pragma unroll
+    for (int i4 = 0; i4 < 8; i4++) {
+        if (i4 * 4 < K4) {
+            const float4 t = valid ? __ldg(src + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[i4 * 4 + 0] = t.x; w[i4 * 4 + 1] = t.y; w[i4 * 4 + 2] = t.z; w[i4 * 4 + 3] = t.w;
+        }
+    }
+}
+// ... registers -> tensor memory (hi at kCsColWhi + k, lo at kCsColWlo + k; lane = output channel), exact hi/lo TF32 split
+__device__ __forceinline__ void cs_store_w(uint32_t tmem_lane_base, int g, int K4, const float *w)
+{
+#pragma unroll
+    for (int i8 = 0; i8 < 4; i8++) {
+        if (i8 * 8 < K4) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float v = w[i8 * 8 + i];
+                const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                hi[i] = __float_as_uint(h);
+                lo[i] = __float_as_uint(v - h);
+            }
+            cs_st8(tmem_lane_base + kCsColWhi + (uint32_t)(g * K4 + i8 * 8), hi);
+            cs_st8(tmem_lane_base + kCsColWlo + (uint32_t)(g * K4 + i8 * 8), lo);
+        }
+    }
+    cs_st_wait();
+}
 
+// (B) of the layer loop: this thread's channel = column k of the B operand: normalise, split and store its npt points into ring slot `slot`
+__device__ __forceinline__ void cs_write_chunk(const uint32_t (&v)[kCsNPT], float sc, float sh, bool relu, int npt, int nvalid, unsigned char *hi_base,
+                                               unsigned char *lo_base, const uint32_t (&swz)[8])
+{
+#pragma unroll
+    for (int j = 0; j < kCsNPT; j++) {
+        if (j < npt) {
+            float t = fmaf(__uint_as_float(v[j]), sc, sh);
+            if (relu) t = fmaxf(t, 0.f);
+            if (j >= nvalid) t = 0.f;
+            const float h = __uint_as_float(__float_as_uint(t) & 0xffffe000u);
+            const uint32_t off = (uint32_t)j * 128u + swz[j & 7];
+            *reinterpret_cast<float *>(hi_base + off) = h;
+            *reinterpret_cast<float *>(lo_base + off) = t - h;
+        }
+    }
+}
+
+// MMA issue for K chunk c of the current layer (whole warp waits, lane 0 issues): 4 K steps x 3 MMAs (3xTF32), then the commits
+__device__ __forceinline__ void cs_issue_chunk(unsigned char *smem_raw, uint32_t slot_bytes, int ppc, uint32_t tmem0, uint32_t idesc, uint32_t gchunk,
+                                               int c, int nchunks, uint64_t *bar_full, uint64_t *bar_ring, uint64_t *bar_acc, int lane)
+{
+    const uint32_t gi = gchunk + (uint32_t)c, slot = gi % kCsRing, use = gi / kCsRing;
+    cs_mbar_wait(&bar_full[slot], use & 1u);
+    cs_fence_after();
+    if (lane == 0) {
+        const uint32_t sb = smem_u32(smem_raw) + slot * slot_bytes;
+        const uint64_t b_hi = cs_sdesc(sb), b_lo = cs_sdesc(sb + (uint32_t)ppc * 128u);
+        const uint32_t a_hi = tmem0 + kCsColWhi + (uint32_t)(c * 32), a_lo = tmem0 + kCsColWlo + (uint32_t)(c * 32);
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {   // K = 8 tf32 per step: +8 TMEM columns (A), +32 bytes = +2 in the 16-byte address field (B)
+            const uint64_t o = (uint64_t)(ks * 2);
+            const uint32_t ka = (uint32_t)(ks * 8);
+            cs_umma_ts(tmem0, a_lo + ka, b_hi + o, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            cs_umma_ts(tmem0, a_hi + ka, b_lo + o, idesc, 1u);
+            cs_umma_ts(tmem0, a_hi + ka, b_hi + o, idesc, 1u);
+        }
+        cs_commit(&bar_ring[slot]);
+        if (c == nchunks - 1) cs_commit(bar_acc);
+    }
+    __syncwarp();
+}
+
+// Thread roles: warps 0..15 (512 threads) are PRODUCERS: warp & 3 = q selects the TMEM lane quarter = 32 output channels (thread: channel
+// ch = 32 q + lane), warp >> 2 = g selects npt = ppc/4 consecutive points (accumulator columns).  Warp 15 is ALSO the MMA ISSUER: lane 0 issues
+// tcgen05.mma / tcgen05.commit for the K chunks in order (its own chunk, number 3, exists only in 128-wide layers and is prepared after
+// chunks 0..2 have been issued -- the tensor pipe is busy with them for thousands of cycles by then).  Everything meets through mbarriers:
+//   bar_w          producers -> issuer : the layer's weights are in tensor memory                          (512 arrivals)
+//   bar_full[s]    producers -> issuer : ring slot s holds a prepared 32-wide K chunk of the B operand      (128 arrivals: one quarter)
+//   bar_ring[s]    tensor core -> producers : the MMAs that read ring slot s have completed (tcgen05.commit)
+//   bar_acc        tensor core -> producers : every MMA of this layer has completed
 __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // shared-memory map (dynamic): [A ring: 2 x (hi 16 KB + lo 16 KB)] [W hi | W lo : 2 x c_in x c_out x 4 B]
-    unsigned char *sA[2][2];  // [ring][hi/lo]
-    sA[0][0] = smem_raw;             sA[0][1] = smem_raw + 16384;
-    sA[1][0] = smem_raw + 32768;     sA[1][1] = smem_raw + 49152;
-    unsigned char *sWhi = smem_raw + 65536;
-    __shared__ __align__(16) float sScale[128];
-    __shared__ __align__(16) float sShift[128];
-    __shared__ float sBias[128];
-    __shared__ float sX[kCsSlots][kCsM * 3];
+    // dynamic shared memory: ring of kCsRing slots x [hi: ppc x 128 B | lo: ppc x 128 B]; reused by the pool partials and by the head
+    __shared__ float sX[kCsMaxPts * 3];
     __shared__ float sW1[128 * 3], sB1[128];
-    __shared__ float sRedA[4][128], sRedB[4][128];
-    __shared__ uint64_t bar_full[2], bar_ring[2], bar_acc[kCsSlots];
+    __shared__ float sRedS[4][128], sRedQ[4][128];
+    __shared__ uint64_t bar_full[kCsRing], bar_ring[kCsRing], bar_acc, bar_w;
     __shared__ uint32_t tmem_base_smem;
     __shared__ double sMom[9];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool producer = warp < 16;
-    const int q = warp & 3, hsel = (warp >> 2) & 3;     // TMEM lane quarter, column group (epilogue: 4 groups of 16 columns)
-    const int grp = (warp >> 3) & 1, hs2 = (warp >> 2) & 1; // main loop: producer group, column half inside the chunk
-    const int row = q * 32 + lane;                      // the point row this producer thread owns in every tile
+    const bool producer = true;                          // every warp prepares operands; warp kCsIssuerWarp also issues the MMAs
+    const bool issuer = warp == kCsIssuerWarp;
+    const int q = warp & 3, g = (warp >> 2) & 3;
+    const int ch = q * 32 + lane;                       // the channel (TMEM lane) this producer thread owns in every layer
     const int G = gridDim.x;
-    int tile_of[kCsSlots], np_of[kCsSlots];
-    int nslots = 0;
-#pragma unroll
-    for (int s = 0; s < kCsSlots; s++) {
-        const int t = blockIdx.x + s * G;
-        tile_of[s] = t;
-        np_of[s] = 0;
-        if (t < P.tiles) {
-            nslots = s + 1;
-            const int p0 = (t % P.tiles_per_cloud) * kCsM;
-            np_of[s] = min(kCsM, P.n - p0);
-        }
-    }
+    const int ppc = P.ppc, npt = P.npt, n = P.n;
+    const long long P0 = (long long)blockIdx.x * ppc;   // first point (flattened batch) of this CTA
+    const int npts = (int)min((long long)ppc, P.total - P0);
+    const int col0 = g * npt;                           // first accumulator column of this thread
+    const int nvalid = max(0, min(npt, npts - col0));   // its columns [0, nvalid) are real points
+    const uint32_t slot_bytes = (uint32_t)ppc * 256u;
 
     CS_TS(0);
-    if (warp == 16) cs_tmem_alloc(&tmem_base_smem, 512);
+    if (warp == 0) cs_tmem_alloc(&tmem_base_smem, 512);
     if (tid == 0) {
-        mbar_init(&bar_full[0], kCsGroup); mbar_init(&bar_full[1], kCsGroup);
-        mbar_init(&bar_ring[0], 1); mbar_init(&bar_ring[1], 1);
-        mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
+        for (int s = 0; s < kCsRing; s++) { mbar_init(&bar_full[s], 128); mbar_init(&bar_ring[s], 1); }
+        mbar_init(&bar_acc, 1);
+        mbar_init(&bar_w, kCsProducers);
         fence_mbar_init();
     }
     if (tid < 9) sMom[tid] = 0.0;
-    // the cloud tiles of this CTA and layer 1's weights
+    // the points of this CTA and layer 1's weights
     const CsLayer &L1 = P.L[0];
     if (producer) {
-        for (int s = 0; s < nslots; s++) {
-            const int t = tile_of[s], cloud = t / P.tiles_per_cloud, p0 = (t % P.tiles_per_cloud) * kCsM;
-            const float *xc = P.x + (size_t)cloud * P.n * 3;
-            if (P.layout == SNB200_BNC) {
-                const float *src = xc + (size_t)p0 * 3;
-                const int nf = np_of[s] * 3;
-                for (int e = tid; e < kCsM * 3; e += kCsProducers) sX[s][e] = (e < nf) ? __ldg(src + e) : 0.f;
-            } else {
-                for (int e = tid; e < kCsM * 3; e += kCsProducers) {
-                    const int c = e / kCsM, r = e % kCsM;    // coalesced along points
-                    sX[s][r * 3 + c] = (r < np_of[s]) ? __ldg(xc + (size_t)c * P.n + p0 + r) : 0.f;
+        if (P.layout == SNB200_BNC) {   // (b, n, 3): the flattened batch is contiguous
+            const float *src = P.x + P0 * 3;
+            const int nf = npts * 3;
+            for (int e = tid; e < ppc * 3; e += kCsProducers) sX[e] = (e < nf) ? __ldg(src + e) : 0.f;
+        } else {
+            for (int e = tid; e < ppc * 3; e += kCsProducers) {
+                const int c = e / ppc, r = e - c * ppc;    // coalesced along points
+                float v = 0.f;
+                if (r < npts) {
+                    const long long gp = P0 + r;
+                    const int cloud = (int)(gp / n), pi = (int)(gp - (long long)cloud * n);
+                    v = __ldg(P.x + ((size_t)cloud * 3 + c) * n + pi);
                 }
+                sX[r * 3 + c] = v;
             }
         }
         for (int e = tid; e < L1.c_out * 3; e += kCsProducers) sW1[e] = __ldg(L1.weight + e);
@@ -413,8 +376,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     __syncthreads();
     cs_fence_after();
     const uint32_t tmem0 = tmem_base_smem;
+    const uint32_t tmem_lane = tmem0 + ((uint32_t)(q * 32) << 16);
     unsigned barrier_epoch = 0;
-    const double cnt = (double)P.b * (double)P.n, inv_cnt = 1.0 / cnt;
+    const double cnt = (double)P.total, inv_cnt = 1.0 / cnt;
     CS_TS(1);
     const bool need_stats = P.training != 0;
     if (P.self_clean) {   // statistics accumulators and FC exchange words: zero before anybody adds to them (ordered by the first grid barrier)
@@ -424,258 +388,233 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         if (!(need_stats && L1.has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);   // (no phase-0 barrier on this path)
     }
 
+    // ---- the first tensor layer's weights: global -> registers now, tensor memory below (overlaps the phase-0 barrier)
+    float wreg[32];
+    if (producer) cs_load_w(P.L[1], ch, g, wreg);
+
     // ---- phase 0: input moments (training + BN after layer 1): 9 sums over this CTA's points, fp64 atomics, grid barrier
     if (need_stats && L1.has_bn) {
         if (producer) {
             float a9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if (tid < kCsM * nslots) {
-                const int s = tid / kCsM, r = tid % kCsM;
-                if (r < np_of[s]) {
-                    const float px = sX[s][r * 3 + 0], py = sX[s][r * 3 + 1], pz = sX[s][r * 3 + 2];
-                    a9[0] = px; a9[1] = py; a9[2] = pz;
-                    a9[3] = px * px; a9[4] = px * py; a9[5] = px * pz; a9[6] = py * py; a9[7] = py * pz; a9[8] = pz * pz;
-                }
+            if (tid < npts) {
+                const float px = sX[tid * 3 + 0], py = sX[tid * 3 + 1], pz = sX[tid * 3 + 2];
+                a9[0] = px; a9[1] = py; a9[2] = pz;
+                a9[3] = px * px; a9[4] = px * py; a9[5] = px * pz; a9[6] = py * py; a9[7] = py * pz; a9[8] = pz * pz;
             }
+            if (warp * 32 < npts) {
 #pragma unroll
-            for (int j = 0; j < 9; j++) {
-                float v = a9[j];
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-                if (lane == 0) atomicAdd(&sMom[j], (double)v);
+                for (int j = 0; j < 9; j++) {
+                    float v = a9[j];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+                    if (lane == 0) atomicAdd(&sMom[j], (double)v);
+                }
             }
         }
         __syncthreads();
         if (tid < 9) atomicAdd(P.mom + tid, sMom[tid]);
         __syncthreads();
         if (tid == 0) cs_grid_arrive(P.barrier);
-        if (producer) cs_stage_weights(P.L[1], sWhi, sBias, tid);     // overlaps the barrier latency
+    }
+    if (producer) {   // weights of the first tensor layer into tensor memory
+        cs_store_w(tmem_lane, g, P.L[1].c_in >> 2, wreg);
+        cs_fence_before();
+        cs_mbar_arrive(&bar_w);
+    }
+    if (need_stats && L1.has_bn) {
         if (tid == 0) cs_grid_wait(P.barrier, ++barrier_epoch * G);
         __syncthreads();
         if (tid < 9) sMom[tid] = __ldcg(P.mom + tid);
         __syncthreads();
-    } else {
-        if (producer) cs_stage_weights(P.L[1], sWhi, sBias, tid);
-        __syncthreads();
     }
     CS_TS(2);
 
-    uint32_t g = 0;                     // global chunk counter (same sequence in producers and issuer)
-    uint32_t acc_phase[kCsSlots] = {0, 0};
-    int parity = 0;                     // TMEM region parity holding the CURRENT layer's input (previous layer's raw output)
+    // ---- layer 1 (3 -> C1) on CUDA cores: this thread's channel at its npt points (raw, with bias), kept in registers
+    uint32_t v[kCsNPT];   // (float bit patterns: tcgen05.ld writes straight into this array)
+    if (producer && q * 32 < L1.c_out) {
+        const bool cv = ch < L1.c_out;
+        const float w0 = cv ? sW1[ch * 3 + 0] : 0.f, w1 = cv ? sW1[ch * 3 + 1] : 0.f, w2 = cv ? sW1[ch * 3 + 2] : 0.f, b1 = cv ? sB1[ch] : 0.f;
+#pragma unroll
+        for (int j = 0; j < kCsNPT; j++) {
+            if (j < npt) {
+                const float *xr = sX + (col0 + j) * 3;
+                v[j] = __float_as_uint(fmaf(w2, xr[2], fmaf(w1, xr[1], w0 * xr[0])) + b1);
+            }
+        }
+    }
+
+    uint32_t gchunk = 0;                // global K-chunk counter (same sequence in producers and issuer): slot = gchunk % kCsRing
+    // swizzle: point p's 128-byte row holds its 16-byte group c at position c ^ (p & 7); col0 is a multiple of 8, so p & 7 = j & 7
+    uint32_t swz[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) swz[i] = (uint32_t)(((lane >> 2) ^ i) << 4) + (uint32_t)((lane & 3) << 2);
 
     for (int l = 1; l < P.num_layers; l++) {
-        const CsLayer &Lp = P.L[l - 1];   // producer of this layer's input (its BN+ReLU is applied on load)
+        const CsLayer &Lp = P.L[l - 1];   // producer of this layer's input (its BN+ReLU is applied when the registers are stored)
         const CsLayer &Lc = P.L[l];
         const int K = Lc.c_in, N = Lc.c_out;
-        const int npad = N <= 64 ? 64 : 128;
-        const uint32_t idesc = cs_idesc(kCsM, npad);
-        const uint32_t atomB = (uint32_t)npad * 128u;
         const int nchunks = K >> 5;
-        unsigned char *sWlo = sWhi + (size_t)nchunks * atomB;
         const bool last = (l == P.num_layers - 1);
         const bool want_stats = need_stats && Lc.has_bn;
-        const uint32_t in_region = (uint32_t)(parity * kCsRegion), out_region = (uint32_t)((parity ^ 1) * kCsRegion);
 
-        if (!producer) {
-            // =============================== MMA issuer warp ===============================
-            for (int s = 0; s < nslots; s++) {
-                const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-                for (int kc = 0; kc < nchunks; kc++, g++) {
-                    const int rb = g & 1;
-                    cs_mbar_wait(&bar_full[rb], (g >> 1) & 1);
-                    cs_fence_after();
-                    if (lane == 0) {
-                        const uint64_t a_hi = cs_sdesc(smem_u32(sA[rb][0])), a_lo = cs_sdesc(smem_u32(sA[rb][1]));
-                        const uint64_t b_hi = cs_sdesc(smem_u32(sWhi) + (uint32_t)kc * atomB), b_lo = cs_sdesc(smem_u32(sWlo) + (uint32_t)kc * atomB);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {   // 32 bytes (K = 8 tf32) per step: +2 in the 16-byte address field
-                            const uint64_t o = (uint64_t)(ks * 2);
-                            cs_umma(t_out, a_lo + o, b_hi + o, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                            cs_umma(t_out, a_hi + o, b_lo + o, idesc, 1u);
-                            cs_umma(t_out, a_hi + o, b_hi + o, idesc, 1u);
-                        }
-                        cs_commit(&bar_ring[rb]);
-                        if (kc == nchunks - 1) cs_commit(&bar_acc[s]);
-                    }
-                    __syncwarp();
-                }
-            }
-        } else {
+        {
             // =============================== producer warps ===============================
             CS_TS(3 + (l - 1) * 8 + 0);
+            // (A) BatchNorm (+ReLU) of the producer layer for this thread's channel: two registers
+            float sc = 1.f, sh = 0.f;
+            if (Lp.has_bn && ch < K) {
+                float mean, var;
+                if (P.training) {
+                    double m, vv;
+                    if (l == 1) {   // analytic statistics of layer 1 from the input moments
+                        const double mx = sMom[0] * inv_cnt, my = sMom[1] * inv_cnt, mz = sMom[2] * inv_cnt;
+                        const double cxx = sMom[3] * inv_cnt - mx * mx, cxy = sMom[4] * inv_cnt - mx * my, cxz = sMom[5] * inv_cnt - mx * mz;
+                        const double cyy = sMom[6] * inv_cnt - my * my, cyz = sMom[7] * inv_cnt - my * mz, czz = sMom[8] * inv_cnt - mz * mz;
+                        const double a0 = sW1[ch * 3 + 0], a1 = sW1[ch * 3 + 1], a2 = sW1[ch * 3 + 2];
+                        m = a0 * mx + a1 * my + a2 * mz + (double)sB1[ch];
+                        vv = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
+                        if (vv < 0) vv = 0;
+                        if (blockIdx.x == 0 && g == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
+                            Lp.stats[ch] = cnt * m;
+                            Lp.stats[K + ch] = cnt * (vv + m * m);
+                        }
+                    } else {
+                        m = __ldcg(Lp.stats + ch) * inv_cnt;
+                        vv = __ldcg(Lp.stats + K + ch) * inv_cnt - m * m;
+                        if (vv < 0) vv = 0;
+                    }
+                    mean = (float)m; var = (float)vv;
+                } else {
+                    mean = Lp.run_mean[ch]; var = Lp.run_var[ch];
+                }
+                const float invstd = 1.0f / sqrtf(var + Lp.eps);
+                sc = Lp.gamma[ch] * invstd;
+                sh = Lp.beta[ch] - mean * sc;
+            }
             CS_TS(3 + (l - 1) * 8 + 1);
-            // BatchNorm (+ReLU) of the producer layer as a per-channel affine map
-            for (int c = tid; c < K; c += kCsProducers) {
-                float sc = 1.f, sh = 0.f;
-                if (Lp.has_bn) {
-                    float mean, var;
-                    if (P.training) {
-                        double m, v;
-                        if (l == 1) {   // analytic statistics of layer 1 from the input moments
-                            const double mx = sMom[0] * inv_cnt, my = sMom[1] * inv_cnt, mz = sMom[2] * inv_cnt;
-                            const double cxx = sMom[3] * inv_cnt - mx * mx, cxy = sMom[4] * inv_cnt - mx * my, cxz = sMom[5] * inv_cnt - mx * mz;
-                            const double cyy = sMom[6] * inv_cnt - my * my, cyz = sMom[7] * inv_cnt - my * mz, czz = sMom[8] * inv_cnt - mz * mz;
-                            const double a0 = sW1[c * 3 + 0], a1 = sW1[c * 3 + 1], a2 = sW1[c * 3 + 2];
-                            m = a0 * mx + a1 * my + a2 * mz + (double)sB1[c];
-                            v = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
-                            if (v < 0) v = 0;
-                            if (blockIdx.x == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
-                                Lp.stats[c] = cnt * m;
-                                Lp.stats[K + c] = cnt * (v + m * m);
-                            }
-                        } else {
-                            m = __ldcg(Lp.stats + c) * inv_cnt;
-                            v = __ldcg(Lp.stats + K + c) * inv_cnt - m * m;
-                            if (v < 0) v = 0;
-                        }
-                        mean = (float)m; var = (float)v;
-                    } else {
-                        mean = Lp.run_mean[c]; var = Lp.run_var[c];
-                    }
-                    const float invstd = 1.0f / sqrtf(var + Lp.eps);
-                    sc = Lp.gamma[c] * invstd;
-                    sh = Lp.beta[c] - mean * sc;
-                }
-                // tensor memory holds W.a WITHOUT the producer's bias (layer 1 is evaluated with its bias): fold it into the shift
-                if (l >= 2 && Lp.bias) sh = fmaf(Lp.bias[c], sc, sh);
-                sScale[c] = sc;
-                sShift[c] = sh;
+            // (B) MMA issue (warp kCsIssuerWarp, chunks in order) around the operand preparation (every warp that owns a K chunk)
+            const uint32_t idesc = cs_idesc(128, ppc);
+            if (issuer) {
+                cs_mbar_wait(&bar_w, (uint32_t)(l - 1) & 1u);   // every thread's slice of this layer's weights is in tensor memory
+                cs_fence_after();
+                for (int c = 0; c < min(nchunks, 3); c++)        // (this warp owns chunk 3)
+                    cs_issue_chunk(smem_raw, slot_bytes, ppc, tmem0, idesc, gchunk, c, nchunks, bar_full, bar_ring, &bar_acc, lane);
             }
-            cs_named_sync(1, kCsProducers);
+            if (q < nchunks) {
+                const uint32_t gi = gchunk + (uint32_t)q, slot = gi % kCsRing, use = gi / kCsRing;
+                if (use > 0) {   // the MMAs that read this ring slot last time must have completed
+                    cs_mbar_wait(&bar_ring[slot], (use - 1) & 1u);
+                    cs_fence_after();
+                }
+                unsigned char *hi_base = smem_raw + slot * slot_bytes + (uint32_t)col0 * 128u;
+                cs_write_chunk(v, sc, sh, Lp.relu != 0, npt, nvalid, hi_base, hi_base + (uint32_t)ppc * 128u, swz);
+                cs_fence_before();     // this thread's tcgen05.ld of the previous accumulator are complete (wait::ld) and ordered
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
+                cs_mbar_arrive(&bar_full[slot]);
+            }
+            if (issuer && nchunks > 3) cs_issue_chunk(smem_raw, slot_bytes, ppc, tmem0, idesc, gchunk, 3, nchunks, bar_full, bar_ring, &bar_acc, lane);
+            gchunk += (uint32_t)nchunks;
             CS_TS(3 + (l - 1) * 8 + 2);
-
-            // ---- operand preparation: chunk g+1 is prepared while the tensor core works on chunk g; inside a thread the
-            //      tensor-memory load of the NEXT chunk is in flight while the current chunk is normalised, split and stored
-            {
-                // Producer group `grp` prepares the chunks whose global index has its parity (= ring buffer grp): while one group
-                // is inside its fence / arrive latency chain the other one is already normalising the next chunk.
-                const int total_chunks = nslots * nchunks;
-                const uint32_t g0 = g;
-                for (int ci = 0; ci < total_chunks; ci++) {
-                    const uint32_t gg = g0 + (uint32_t)ci;
-                    if ((int)(gg & 1) != grp) continue;
-                    const int s = ci / nchunks, kc = ci - s * nchunks;
-                    const int np = (s == 0) ? np_of[0] : np_of[1];
-                    const int kb = kc * 32 + hs2 * 16;
-                    float v[16];
-                    if (l == 1) {
-                        const float *xr = (s == 0 ? sX[0] : sX[1]) + row * 3;
-                        const float px = xr[0], py = xr[1], pz = xr[2];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const int c = kb + j;
-                            v[j] = fmaf(sW1[c * 3 + 2], pz, fmaf(sW1[c * 3 + 1], py, sW1[c * 3 + 0] * px)) + sB1[c];
-                        }
-                    } else {
-                        cs_ld16(tmem0 + (uint32_t)(s * 2 * kCsRegion) + in_region + ((uint32_t)(q * 32) << 16) + (uint32_t)kb, v);
-                    }
-                    const bool pv = row < np;
-                    float4 tq[4];
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        const float4 sc = *reinterpret_cast<const float4 *>(sScale + kb + c4 * 4);
-                        const float4 sh = *reinterpret_cast<const float4 *>(sShift + kb + c4 * 4);
-                        float4 t;
-                        t.x = fmaf(v[c4 * 4 + 0], sc.x, sh.x); t.y = fmaf(v[c4 * 4 + 1], sc.y, sh.y);
-                        t.z = fmaf(v[c4 * 4 + 2], sc.z, sh.z); t.w = fmaf(v[c4 * 4 + 3], sc.w, sh.w);
-                        if (Lp.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-                        if (!pv) t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        tq[c4] = t;
-                    }
-                    if (gg >= 2) {   // the MMAs of chunk gg-2 (same ring buffer) must have completed before its operands are overwritten
-                        cs_mbar_wait(&bar_ring[grp], ((gg >> 1) - 1) & 1);
-                        cs_fence_after();
-                    }
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) cs_split_store(sA[grp][0], sA[grp][1], cs_sw128(row, hs2 * 4 + c4), tq[c4]);
-                    cs_fence_before();
-                    fence_proxy_async();
-                    cs_mbar_arrive(&bar_full[grp]);
-                }
-                g = g0 + (uint32_t)total_chunks;
-            }
-            CS_TS(3 + (l - 1) * 8 + 3);
-
-            // ---- epilogue: wait for the accumulators, then batch statistics and / or per-tile extrema
-            for (int s = 0; s < nslots; s++) {
-                cs_mbar_wait(&bar_acc[s], acc_phase[s]);
-                acc_phase[s] ^= 1;
-            }
+            // (C) while the tensor core works: this layer's bias and the NEXT layer's weight row into registers
+            const float bias = (ch < N && Lc.bias) ? __ldg(Lc.bias + ch) : 0.f;
+            if (!last) cs_load_w(P.L[l + 1], ch, g, wreg);
+            // (D) every MMA of this layer has completed
+            cs_mbar_wait(&bar_acc, (uint32_t)(l - 1) & 1u);
             cs_fence_after();
-            CS_TS(3 + (l - 1) * 8 + 4);
-            if (want_stats) {   // sums over BOTH tile slots first (same columns, different rows), one reduction per 16-column block
-                for (int cb = hsel * 16; cb < npad; cb += 64) {
-                    float v[16], w[16], t[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) { v[j] = 0.f; w[j] = 0.f; }
-                    for (int s = 0; s < nslots; s++) {
-                        const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-                        cs_ld16(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, t);
-                        if (row < (s == 0 ? np_of[0] : np_of[1])) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const float u = t[j] + sBias[cb + j];
-                                v[j] += u;
-                                w[j] = fmaf(u, u, w[j]);
-                            }
-                        }
-                    }
-                    const float sm = cs_colreduce16<0>(v, lane);
-                    const float sq = cs_colreduce16<0>(w, lane);
-                    if (!(lane & 1)) { sRedA[q][cb + (lane >> 1)] = sm; sRedB[q][cb + (lane >> 1)] = sq; }
-                }
-                cs_named_sync(1, kCsProducers);
-                if (tid < N) {
-                    const float sm = (sRedA[0][tid] + sRedA[1][tid]) + (sRedA[2][tid] + sRedA[3][tid]);
-                    const float sq = (sRedB[0][tid] + sRedB[1][tid]) + (sRedB[2][tid] + sRedB[3][tid]);
-                    atomicAdd(Lc.stats + tid, (double)sm);
-                    atomicAdd(Lc.stats + N + tid, (double)sq);
-                }
-                cs_named_sync(1, kCsProducers);
+            CS_TS(3 + (l - 1) * 8 + 3);
+            // (E) the next layer's weights replace this layer's in tensor memory
+            if (!last) {
+                cs_store_w(tmem_lane, g, P.L[l + 1].c_in >> 2, wreg);
+                cs_fence_before();
+                cs_mbar_arrive(&bar_w);
             }
-            if (last) {   // extrema for the max-pool, per tile
-                for (int s = 0; s < nslots; s++) {
-                    const bool pv = row < (s == 0 ? np_of[0] : np_of[1]);
-                    const uint32_t t_out = tmem0 + (uint32_t)(s * 2 * kCsRegion) + out_region;
-                    for (int cb = hsel * 16; cb < npad; cb += 64) {
-                        float v[16], w[16];
-                        cs_ld16(t_out + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+            // (F) the accumulator: lane = channel, this thread's npt columns -> registers (+bias); statistics / extrema on the way
+            float sum = 0.f, sq = 0.f;
+            if (q * 32 < N) {
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const float u = v[j] + sBias[cb + j];
-                            v[j] = pv ? u : -INFINITY;
-                            w[j] = pv ? u : INFINITY;
+                for (int jb = 0; jb < kCsNPT / 8; jb++)
+                    if (jb * 8 < npt) cs_ld8_issue(tmem_lane + (uint32_t)(col0 + jb * 8), v + jb * 8);
+                cs_ld_wait();
+#pragma unroll
+                for (int j = 0; j < kCsNPT; j++) {
+                    if (j < npt) {
+                        const float u = __uint_as_float(v[j]) + bias;
+                        v[j] = __float_as_uint(u);
+                        if (j < nvalid) { sum += u; sq = fmaf(u, u, sq); }
+                    }
+                }
+                if (want_stats) { sRedS[g][ch] = sum; sRedQ[g][ch] = sq; }
+            }
+            float *sPmax = reinterpret_cast<float *>(smem_raw);                       // [4 groups][kCsMaxSeg][128]
+            float *sPmin = sPmax + 4 * kCsMaxSeg * 128;
+            const int cl_first = (int)(P0 / n);
+            const int nseg = (int)((P0 + npts - 1) / n) - cl_first + 1;
+            if (last && q * 32 < N) {   // per-cloud extrema of this thread's columns (the ring is dead: every MMA has completed)
+                for (int s = 0; s < nseg; s++) { sPmax[(g * kCsMaxSeg + s) * 128 + ch] = -INFINITY; sPmin[(g * kCsMaxSeg + s) * 128 + ch] = INFINITY; }
+                const long long gp0 = P0 + col0;
+                const int cl = (int)(gp0 / n);
+                int seg = cl - cl_first;
+                int nb = (int)((long long)(cl + 1) * n - gp0);   // column at which the next cloud starts
+                float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+                for (int j = 0; j < kCsNPT; j++) {
+                    if (j < nvalid) {
+                        if (j == nb) {
+                            sPmax[(g * kCsMaxSeg + seg) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + seg) * 128 + ch] = mn;
+                            seg++; nb += n; mx = -INFINITY; mn = INFINITY;
                         }
-                        const float mx = cs_colreduce16<1>(v, lane);
-                        const float mn = cs_colreduce16<2>(w, lane);
-                        if (!(lane & 1)) { sRedA[q][cb + (lane >> 1)] = mx; sRedB[q][cb + (lane >> 1)] = mn; }
+                        mx = fmaxf(mx, __uint_as_float(v[j])); mn = fminf(mn, __uint_as_float(v[j]));
                     }
-                    cs_named_sync(1, kCsProducers);
-                    if (tid < N) {
-                        const int tile = (s == 0) ? tile_of[0] : tile_of[1];
-                        P.tile_max[(size_t)tile * N + tid] = fmaxf(fmaxf(sRedA[0][tid], sRedA[1][tid]), fmaxf(sRedA[2][tid], sRedA[3][tid]));
-                        P.tile_min[(size_t)tile * N + tid] = fminf(fminf(sRedB[0][tid], sRedB[1][tid]), fminf(sRedB[2][tid], sRedB[3][tid]));
+                }
+                if (nvalid > 0 && seg < nseg) { sPmax[(g * kCsMaxSeg + seg) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + seg) * 128 + ch] = mn; }
+            }
+            CS_TS(3 + (l - 1) * 8 + 4);
+            if (want_stats || last) cs_named_sync(1, kCsProducers);
+            if (want_stats && g == 0 && ch < N) {
+                const float sm = (sRedS[0][ch] + sRedS[1][ch]) + (sRedS[2][ch] + sRedS[3][ch]);
+                const float sqq = (sRedQ[0][ch] + sRedQ[1][ch]) + (sRedQ[2][ch] + sRedQ[3][ch]);
+                atomicAdd(Lc.stats + ch, (double)sm);
+                atomicAdd(Lc.stats + N + ch, (double)sqq);
+            }
+            if (last) {   // (cloud, slot) partial extrema; slot = this CTA's rank among the CTAs that touch the cloud
+                const int S = P.slots_per_cloud;
+                for (int e = tid; e < nseg * N; e += kCsProducers) {
+                    const int s = e / N, c = e - s * N;
+                    const int cl = cl_first + s;
+                    const int slot = (int)blockIdx.x - (int)(((long long)cl * n) / ppc);
+                    float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+                    for (int gg = 0; gg < 4; gg++) {
+                        mx = fmaxf(mx, sPmax[(gg * kCsMaxSeg + s) * 128 + c]);
+                        mn = fminf(mn, sPmin[(gg * kCsMaxSeg + s) * 128 + c]);
                     }
-                    cs_named_sync(1, kCsProducers);
+                    P.tile_max[((size_t)cl * S + slot) * N + c] = mx;
+                    P.tile_min[((size_t)cl * S + slot) * N + c] = mn;
+                    // the CTA that holds a cloud's last point also fills the slots no CTA owns
+                    if ((int)((((long long)cl + 1) * n - 1) / ppc) == (int)blockIdx.x)
+                        for (int s2 = slot + 1; s2 < S; s2++) {
+                            P.tile_max[((size_t)cl * S + s2) * N + c] = -INFINITY;
+                            P.tile_min[((size_t)cl * S + s2) * N + c] = INFINITY;
+                        }
                 }
             }
             CS_TS(3 + (l - 1) * 8 + 5);
+            if (want_stats) {   // grid barrier: every CTA's statistics (and, last layer, extrema) are in
+                cs_named_sync(1, kCsProducers);
+                if (tid == 0) {
+                    cs_grid_arrive(P.barrier);
+                    cs_grid_wait(P.barrier, (barrier_epoch + 1) * G);
+                }
+                cs_named_sync(1, kCsProducers);
+            }
+            CS_TS(3 + (l - 1) * 8 + 6);
         }
-        parity ^= 1;
-        cs_fence_before();
-        __syncthreads();                                         // this CTA's statistics atomics are issued, its MMAs are done
-        if (want_stats && tid == 0) cs_grid_arrive(P.barrier);
-        if (producer && l + 1 < P.num_layers) cs_stage_weights(P.L[l + 1], sWhi, sBias, tid);   // overlaps the barrier latency
-        if (want_stats && tid == 0) cs_grid_wait(P.barrier, (barrier_epoch + 1) * G);   // every tile's statistics are in
         if (want_stats) barrier_epoch++;
-        __syncthreads();
-        cs_fence_after();
-        CS_TS(3 + (l - 1) * 8 + 6);
     }
 
     // every commit has been observed through bar_acc; release tensor memory
     cs_fence_before();
     __syncthreads();
-    if (warp == 16) cs_tmem_dealloc(tmem0, 512);
+    if (warp == 0) cs_tmem_dealloc(tmem0, 512);
 
     // ================================================================================================================
     // Fused tail: max-pool finalise + FC head (samplenet.py:97-104) on the CTAs of the grid.  Each FC layer's output channels
@@ -993,19 +932,47 @@ int debug_conv_stack_timestamps(long long *host_out64)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+static int cs_num_sms()
+{
+    static int sms[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (!sms[dev]) {
+        int v = 0;
+        sms[dev] = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : kNumSMs;
+    }
+    return sms[dev];
+}
+
+// points per CTA: the batch spread evenly over the SMs, a multiple of 32 (4 column groups x 8-column tensor-memory loads)
+static int cs_points_per_cta(long long total)
+{
+    const int sms = cs_num_sms();
+    long long ppc = (total + sms - 1) / sms;
+    ppc = (ppc + 31) / 32 * 32;
+    if (ppc < kCsMinPts) ppc = kCsMinPts;
+    return (int)ppc;
+}
+
+int conv_stack_slots_per_cloud(int b, int n)
+{
+    const int ppc = cs_points_per_cta((long long)b * n);
+    return (n - 1) / ppc + 2;
+}
+
 bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
 {
     if (nconv < 2 || nconv > kCsMaxLayers || conv[0].c_in != 3) return false;
     if (conv[0].c_out % 32 != 0 || conv[0].c_out > 128) return false;
-    size_t wmax = 0;
     for (int l = 1; l < nconv; l++) {
         if ((conv[l].c_in != 32 && conv[l].c_in != 64 && conv[l].c_in != 128) || conv[l].c_out > 128 || conv[l].c_out < 8) return false;
-        const size_t npad = conv[l].c_out <= 64 ? 64 : 128;
-        wmax = max(wmax, 2 * (size_t)conv[l].c_in * npad * 4);
+        if (reinterpret_cast<uintptr_t>(conv[l].weight) & 15) return false;   // 16-byte row loads
     }
-    if (65536 + wmax > 200 * 1024) return false;
-    const long long tiles = (long long)b * ((n + kCsM - 1) / kCsM);
-    return tiles <= (long long)kCsSlots * kNumSMs;
+    const long long total = (long long)b * n;
+    const int ppc = cs_points_per_cta(total);
+    if (ppc > kCsMaxPts) return false;
+    if ((ppc - 1) / n + 2 > kCsMaxSeg) return false;   // clouds one CTA may touch
+    return true;
 }
 
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
@@ -1017,20 +984,21 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     if (head) { P.fuse_head = 1; P.H = *head; }
     if (head && clean_ptr) { P.self_clean = 1; P.clean_ptr = clean_ptr; P.clean_bytes = (unsigned)clean_bytes; }
     P.x = x; P.layout = layout; P.b = b; P.n = n;
-    P.tiles_per_cloud = (n + kCsM - 1) / kCsM;
-    P.tiles = b * P.tiles_per_cloud;
+    P.total = (long long)b * n;
+    P.ppc = cs_points_per_cta(P.total);
+    P.npt = P.ppc / 4;
+    P.slots_per_cloud = (n - 1) / P.ppc + 2;
     P.num_layers = nconv; P.training = training;
     P.mom = mom; P.barrier = barrier; P.tile_max = tile_max; P.tile_min = tile_min;
-    size_t wmax = 0;
     for (int l = 0; l < nconv; l++) {
         CsLayer &D = P.L[l];
         D.c_in = conv[l].c_in; D.c_out = conv[l].c_out; D.weight = conv[l].weight; D.bias = conv[l].bias;
         D.gamma = conv[l].bn_weight; D.beta = conv[l].bn_bias; D.run_mean = conv[l].bn_running_mean; D.run_var = conv[l].bn_running_var;
         D.eps = conv[l].bn_eps; D.has_bn = conv[l].bn_weight != nullptr; D.relu = conv[l].relu; D.stats = stats[l];
-        if (l >= 1) wmax = max(wmax, 2 * (size_t)conv[l].c_in * (conv[l].c_out <= 64 ? 64 : 128) * 4);
     }
-    if (tiles_per_cloud_out) *tiles_per_cloud_out = P.tiles_per_cloud;
-    size_t smem = 65536 + wmax + 1024;
+    if (tiles_per_cloud_out) *tiles_per_cloud_out = P.slots_per_cloud;
+    if (head) P.H.tiles_per_cloud = P.slots_per_cloud;
+    size_t smem = (size_t)kCsRing * P.ppc * 256 + 1024;
     if (head) {   // the fused tail reuses the same dynamic shared memory: input tile + partial sums + 8 weight rows
         int hcmax = head->c_feat;
         for (int l = 0; l < head->num_fc; l++) hcmax = max(hcmax, head->fc[l].c_in);
@@ -1041,8 +1009,8 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
         smem = max(smem, hs);
     }
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
-    int grid = min(P.tiles, kNumSMs);
+    if (once.first()) cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    const int grid = (int)((P.total + P.ppc - 1) / P.ppc);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kCsThreadsAll); cfg.dynamicSmemBytes = smem; cfg.stream = stream;

@@ -282,6 +282,87 @@ int launch_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Exact mode (SNB200_EMD_EXACT): the parity path.  The fast kernel above evaluates exp as one MUFU.EX2 and sums a row with S lanes x 4
+// accumulators; the level schedule then amplifies those roundings wherever `remain` runs towards zero, so its `match` agrees with the
+// CPU oracle to ~1e-3 absolute only and arg-max assignments can flip at near-ties.  This kernel reproduces the oracle's arithmetic
+// operation by operation (oracle/samplenet_oracle.c:orc_approxmatch, itself a restatement of tf_approxmatch_g.cu:21-160 in the
+// reference's level order 7 ... -2): one thread owns a row and accumulates over the columns IN INDEX ORDER in one float accumulator,
+// no FMA contraction, exp(d) evaluated in double and rounded to float (both sides obtain the correctly rounded float exponential),
+// `match` zero-filled and read-modify-written per level like the reference.  One CTA per cloud, per-point vectors in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kEmdExactThreads = 1024;
+
+__device__ __forceinline__ float emd_exact_exp(float level, float x1, float y1, float z1, float x2, float y2, float z2)
+{
+    const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return (float)exp((double)__fmul_rn(level, s));
+}
+
+__global__ void __launch_bounds__(kEmdExactThreads) approxmatch_exact_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                                            float *__restrict__ match)
+{
+    extern __shared__ float s_vec[];   // remainL[n] remainR[m] ratioL[n] ratioR[m]
+    float *remainL = s_vec, *remainR = s_vec + n, *ratioL = s_vec + n + m, *ratioR = s_vec + 2 * n + m;
+    const int bi = blockIdx.x, tid = threadIdx.x;
+    const float *p1 = xyz1 + (size_t)bi * n * 3, *p2 = xyz2 + (size_t)bi * m * 3;
+    float *mt = match + (size_t)bi * n * m;
+    float multiL, multiR;   // tf_approxmatch_g.cu:4-10 (integer division)
+    if (n >= m) { multiL = 1.f; multiR = (float)(n / m); } else { multiL = (float)(m / n); multiR = 1.f; }
+    for (size_t j = tid; j < (size_t)n * m; j += kEmdExactThreads) mt[j] = 0.f;
+    for (int j = tid; j < n; j += kEmdExactThreads) remainL[j] = multiL;
+    for (int j = tid; j < m; j += kEmdExactThreads) remainR[j] = multiR;
+    __syncthreads();
+    for (int j = 7; j >= -2; j--) {
+        float level = 0.f;
+        if (j != -2) { level = 1.f; for (int e = 0; e < (j < 0 ? -j : j); e++) level = (j < 0) ? level * 0.25f : level * 4.f; level = -level; }   // -4^j, exact
+        for (int k = tid; k < n; k += kEmdExactThreads) {
+            const float x1 = p1[k * 3 + 0], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+            float suml = 1e-9f;
+            for (int l = 0; l < m; l++)
+                suml = __fadd_rn(suml, __fmul_rn(emd_exact_exp(level, x1, y1, z1, p2[l * 3 + 0], p2[l * 3 + 1], p2[l * 3 + 2]), remainR[l]));
+            ratioL[k] = __fdiv_rn(remainL[k], suml);
+        }
+        __syncthreads();
+        for (int l = tid; l < m; l += kEmdExactThreads) {
+            const float x2 = p2[l * 3 + 0], y2 = p2[l * 3 + 1], z2 = p2[l * 3 + 2];
+            float sumr = 0.f;
+            for (int k = 0; k < n; k++)
+                sumr = __fadd_rn(sumr, __fmul_rn(emd_exact_exp(level, p1[k * 3 + 0], p1[k * 3 + 1], p1[k * 3 + 2], x2, y2, z2), ratioL[k]));
+            const float rr = remainR[l];
+            sumr = __fmul_rn(sumr, rr);
+            const float consumption = fminf(__fdiv_rn(rr, __fadd_rn(sumr, 1e-9f)), 1.0f);
+            ratioR[l] = __fmul_rn(consumption, rr);
+            remainR[l] = fmaxf(0.0f, __fsub_rn(rr, sumr));
+        }
+        __syncthreads();
+        for (int k = tid; k < n; k += kEmdExactThreads) {
+            const float x1 = p1[k * 3 + 0], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+            const float rl = ratioL[k];
+            float suml = 0.f;
+            for (int l = 0; l < m; l++) {
+                const float w = __fmul_rn(__fmul_rn(emd_exact_exp(level, x1, y1, z1, p2[l * 3 + 0], p2[l * 3 + 1], p2[l * 3 + 2]), rl), ratioR[l]);
+                mt[(size_t)l * n + k] = __fadd_rn(mt[(size_t)l * n + k], w);
+                suml = __fadd_rn(suml, w);
+            }
+            remainL[k] = fmaxf(0.0f, __fsub_rn(remainL[k], suml));
+        }
+        __syncthreads();
+    }
+}
+
+int launch_approxmatch_exact(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, cudaStream_t stream)
+{
+    if (b == 0) return SNB200_OK;
+    const size_t smem = (size_t)2 * (n + m) * sizeof(float);
+    if (smem > 200 * 1024) { set_error("approxmatch (exact mode): %d + %d points exceed the shared-memory vectors", n, m); return SNB200_EUNSUPPORTED; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(approxmatch_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    approxmatch_exact_kernel<<<b, kEmdExactThreads, smem, stream>>>(n, m, xyz1, xyz2, match);
+    return check_launch("approxmatch exact");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // match_cost (:183-225): cost[b] = sum_{k,l} match[b][l][k] * ||xyz1[k] - xyz2[l]||.
 // Streaming kernels: `match` is read exactly once, 16 bytes per thread and load (k runs fastest in memory), several loads in
 // flight per thread; per-CTA partials are combined in slab order by a second tiny kernel (deterministic).

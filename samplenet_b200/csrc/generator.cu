@@ -387,7 +387,7 @@ static GenWorkspace carve_gen_ws(void *base, int b, int n, int nconv, const snb2
     W.stats_bytes = sb;
     off += sb;
     const int c_last = conv[nconv - 1].c_out;
-    const int tpc = (n + 127) / 128;  // upper bound over both paths (128- or 256-point tiles)
+    const int tpc = max((n + 127) / 128, (n + 63) / 64 + 1);  // upper bound over all paths (128- / 256-point tiles; conv-stack (cloud, CTA) slots)
     const size_t tb = align_up((size_t)b * tpc * c_last * sizeof(float), 256);
     W.tile_max = reinterpret_cast<float *>(p + off); off += tb;
     W.tile_min = reinterpret_cast<float *>(p + off); off += tb;
@@ -478,13 +478,13 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
     const bool use_tc = !(flags & SNB200_GEN_EXACT_FP32) && tc_stack_supported(nconv, conv);
     int tpc = 0;
     if (flags & SNB200_GEN_PROFILE_SKIP_CONV) {
-        tpc = use_tc ? tc_tiles_per_cloud(n) : (n + (conv[nconv - 1].c_out > 64 ? 128 : 256) - 1) / (conv[nconv - 1].c_out > 64 ? 128 : 256);
+        tpc = (use_tc && conv_stack_supported(b, n, nconv, conv)) ? conv_stack_slots_per_cloud(b, n) : use_tc ? tc_tiles_per_cloud(n) : (n + (conv[nconv - 1].c_out > 64 ? 128 : 256) - 1) / (conv[nconv - 1].c_out > 64 ? 128 : 256);
     } else if (use_tc && !(flags & SNB200_GEN_PER_LAYER_KERNELS) && conv_stack_supported(b, n, nconv, conv)) {
         // one persistent cooperative launch for the conv stack AND (unless profiling flags split them) the pool + FC head
         HeadParams H;
         bool fuse_head = !(flags & (SNB200_GEN_PROFILE_SKIP_HEAD | SNB200_GEN_SEPARATE_HEAD)) && b <= 256;
         for (int l = 0; l < nfc; l++) fuse_head = fuse_head && fc[l].c_in <= 1024;
-        if (fuse_head) fill_head_params(H, b, n, (n + 127) / 128, nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
+        if (fuse_head) fill_head_params(H, b, n, conv_stack_slots_per_cloud(b, n), nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
         int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc,
                                    fuse_head ? &H : nullptr, (self_clean && fuse_head) ? W.stats_base + 256 : nullptr, W.stats_bytes - 256, stream);
         if (rc) return rc;

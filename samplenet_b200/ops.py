@@ -4,7 +4,7 @@ Every function launches on torch's CURRENT CUDA stream and never synchronises, s
 CUDA graphs.  CPU tensors are rejected: there is no fallback path.
 """
 import ctypes
-
+import os
 import threading
 
 import torch
@@ -529,7 +529,11 @@ def generator_forward_unfused(x, layout, conv_specs, fc_specs, training, out_tra
 
 
 # ----------------------------------------------------------------------------------------------------- EMD
-def approx_match(xyz1, xyz2):
+def approx_match(xyz1, xyz2, exact=None):
+    """exact=True (or SNB200_EMD_EXACT_EXP=1 in the environment): the parity kernel -- exact exponential, index-order float sums, the
+    reference's level order; bit-identical to the CPU oracle.  Default: the fast kernel (ex2.approx, blocked sums)."""
+    if exact is None:
+        exact = os.environ.get("SNB200_EMD_EXACT_EXP", "0") == "1"
     xyz1, xyz2 = _req(xyz1, "xyz1"), _req(xyz2, "xyz2")
     if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[2] != 3 or xyz2.shape[2] != 3 or xyz1.shape[0] != xyz2.shape[0]:
         raise ValueError("ApproxMatch expects (batch_size,num_points,3) xyz1 and xyz2 with equal batch sizes")
@@ -540,7 +544,7 @@ def approx_match(xyz1, xyz2):
         match = torch.empty(b, m, n, device=dev)
         wsb = int(lib().snb200_approxmatch_workspace_bytes(b, n, m))
         ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
-        check(lib().snb200_approxmatch(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(ws), wsb, _stream()), "approxmatch")
+        check(lib().snb200_approxmatch_mode(b, n, m, _p(xyz1), _p(xyz2), _p(match), _lib.EMD_EXACT if exact else 0, _p(ws), wsb, _stream()), "approxmatch")
     return match
 
 

@@ -21,10 +21,11 @@ def nn_distance(xyz1, xyz2):
     return ops.NNDistanceFunction.apply(xyz1, xyz2)
 
 
-def approx_match(xyz1, xyz2):
-    """xyz1 (B, #dataset, 3), xyz2 (B, #query, 3) -> match (B, #query, #dataset).  No gradient."""
+def approx_match(xyz1, xyz2, exact=None):
+    """xyz1 (B, #dataset, 3), xyz2 (B, #query, 3) -> match (B, #query, #dataset).  No gradient.
+    exact=True / SNB200_EMD_EXACT_EXP=1: the parity kernel (bit-identical to the CPU oracle); default: the fast kernel."""
     with torch.no_grad():
-        return ops.approx_match(xyz1.detach(), xyz2.detach())
+        return ops.approx_match(xyz1.detach(), xyz2.detach(), exact=exact)
 
 
 def match_cost(xyz1, xyz2, match):

@@ -73,12 +73,31 @@ def install_stubs():
     sys.modules["pointnet2.utils"] = pn2u
     sys.modules["pointnet2.utils.pointnet2_utils"] = pn2uu
 
-    # kornia is imported (never called on this path) by src/qdataset.py:4-5 via src/__init__.py
+    # kornia (unpinned, registration/Dockerfile:6) is imported by src/qdataset.py:4-5; the only function on the registration step's path
+    # is conversions.quaternion_to_rotation_matrix((x, y, z, w)) (qdataset.py:74-75): restated here as kornia <= 0.4 defines it
+    # (normalise, then the standard unit-quaternion rotation matrix).  PARITY UNPINNED for this one function (source not in the tree).
     for name in ("kornia", "kornia.geometry", "kornia.geometry.conversions", "kornia.geometry.linalg"):
         sys.modules[name] = types.ModuleType(name)
     sys.modules["kornia"].geometry = sys.modules["kornia.geometry"]
     sys.modules["kornia.geometry"].conversions = sys.modules["kornia.geometry.conversions"]
     sys.modules["kornia.geometry"].linalg = sys.modules["kornia.geometry.linalg"]
+
+    def quaternion_to_rotation_matrix(quaternion):
+        q = torch.nn.functional.normalize(quaternion, p=2, dim=-1, eps=1e-12)
+        x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+        tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+        twx, twy, twz = tx * w, ty * w, tz * w
+        txx, txy, txz = tx * x, ty * x, tz * x
+        tyy, tyz, tzz = ty * y, tz * y, tz * z
+        one = torch.ones_like(x)
+        m = torch.stack([one - (tyy + tzz), txy - twz, txz + twy,
+                         txy + twz, one - (txx + tzz), tyz - twx,
+                         txz - twy, tyz + twx, one - (txx + tyy)], dim=-1)
+        return m.view(quaternion.shape[:-1] + (3, 3))
+
+    sys.modules["kornia.geometry.conversions"].quaternion_to_rotation_matrix = quaternion_to_rotation_matrix
+    # registration/main.py also imports h5py (through data/modelnet_loader_torch.py:12; never called here)
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
 
 
 def unit_cube(x):
@@ -201,7 +220,111 @@ def main():
     np.savez_compressed(os.path.join(OUT, "chamfer_reg.npz"), xyz1=a.detach().numpy(), xyz2=b.detach().numpy(),
                         dist1=d1.detach().numpy(), dist2=d2.detach().numpy(), w1=w1.numpy(), w2=w2.numpy(),
                         grad_xyz1=a.grad.numpy(), grad_xyz2=b.grad.numpy())
+    headline_and_registration(SampleNet, state0)
     print("golden fixtures written to", OUT)
+
+
+def perturbed_samplenet(SampleNet, m=64, temperature=0.35):
+    """The SampleNet of fixture 1: default init under torch.manual_seed(0), BN affine parameters perturbed with Generator(seed 1)."""
+    torch.manual_seed(0)
+    net = SampleNet(m, 128, group_size=8, initial_temperature=1.0, input_shape="bnc", output_shape="bnc")
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.startswith("bn") and name.endswith("weight"):
+                p.copy_(1.0 + 0.25 * torch.randn(p.shape, generator=g))
+            if name.startswith("bn") and name.endswith("bias"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+        net.project._temperature.fill_(temperature)
+    return net
+
+
+def headline_and_registration(SampleNet, state0):
+    import copy
+
+    # ---------------- fixture 4: the HEADLINE size -- B=32, N=1024 -> 64, k=8: forward, both losses, every parameter gradient.
+    # The weights are those of fixture 1 (same seeds; asserted), so only the batch and the outputs are stored.
+    net = perturbed_samplenet(SampleNet)
+    for k, v in net.state_dict().items():
+        assert np.array_equal(v.detach().numpy(), state0[k]), k
+    x = unit_cube(torch.rand(32, 1024, 3, generator=torch.Generator().manual_seed(5)) - 0.5)
+    net.train()
+    simp, proj = net(x)
+    simp.retain_grad()
+    loss_s = net.get_simplification_loss(x, simp, 64, 1, 0)
+    loss_p = net.get_projection_loss()
+    rw = torch.randn(proj.shape, generator=torch.Generator().manual_seed(6))
+    (0.01 * loss_s + 0.01 * loss_p + (proj * rw).sum()).backward()
+    gnorm = {("gnorm_" + k): np.float64(p.grad.double().norm().item()) for k, p in net.named_parameters()}
+    net64 = copy.deepcopy(net).double()
+    net64.load_state_dict({k: (torch.from_numpy(v).double() if torch.from_numpy(v).is_floating_point() else torch.from_numpy(v)) for k, v in state0.items()})
+    net64.train()
+    with torch.no_grad():
+        simp64, proj64 = net64(x.double())
+        d64 = ((simp64[:, :, None, :] - x.double()[:, None, :, :]) ** 2).sum(-1)   # (the reference Chamfer extension is float-only)
+        c12, c21 = d64.min(dim=2)[0], d64.min(dim=1)[0]
+        loss64 = c12.mean() + c12.max(dim=1)[0].mean() + c21.mean()
+    np.savez_compressed(
+        os.path.join(OUT, "samplenet_reg_b32.npz"),
+        x=x.numpy(), simp=simp.detach().numpy(), proj=proj.detach().numpy(), rw=rw.numpy(), simp_fp64=simp64.numpy(), proj_fp64=proj64.numpy(),
+        loss_simplification=loss_s.detach().numpy(), loss_projection=loss_p.detach().numpy(), loss_simplification_fp64=loss64.numpy(),
+        grad_fc4_bias=net.fc4.bias.grad.numpy(), grad_conv1_weight=net.conv1.weight.grad.numpy(), grad_conv5_bias=net.conv5.bias.grad.numpy(),
+        grad_bn3_weight=net.bn3.weight.grad.numpy(), grad_fc2_weight_rows=net.fc2.weight.grad[:4].numpy(), grad_conv4_weight_rows=net.conv4.weight.grad[:4].numpy(),
+        grad_temperature=net.project._temperature.grad.numpy(), grad_simp=simp.grad.numpy(),
+        after_bn5_running_mean=net.bn5.running_mean.numpy(), after_bn5_running_var=net.bn5.running_var.numpy(),
+        after_bn_fc3_running_var=net.bn_fc3.running_var.numpy(), **gnorm,
+    )
+
+    # ---------------- fixture 5: one registration training step's loss assembly through the reference's own `Action`
+    # (registration/main.py:221-247, 500-598): compute_samplenet_loss + compute_pcrnet_loss on a synthetic (template, source, igt) batch.
+    # PCRNet (4.4 M parameters) is default-initialised under torch.manual_seed(11); a consumer rebuilds it from the same seed.
+    sys.modules.setdefault("data", types.ModuleType("data"))
+    mlt = types.ModuleType("data.modelnet_loader_torch")
+    mlt.ModelNetCls = object
+    sys.modules["data.modelnet_loader_torch"] = mlt
+    argv_keep = sys.argv
+    sys.argv = ["main.py"]
+    import main as refmain  # noqa: E402  (registration/main.py, unmodified)
+    sys.argv = argv_keep
+    from src import sputils as ref_sputils  # noqa: E402
+    from src.qdataset import QuaternionTransform  # noqa: E402
+    import src.quaternion as Q  # noqa: E402
+
+    args = refmain.options(["-o", "/tmp/x", "--datafolder", "none", "--sampler", "samplenet", "--train-samplenet", "--num-sampled-clouds", "2",
+                            "--device", "cpu"], parser=ref_sputils.get_parser())
+    for ncl in (1, 2):
+        args.num_sampled_clouds = ncl
+        act = refmain.Action(args)
+        torch.manual_seed(11)
+        model = act.create_model()
+        model.sampler.load_state_dict({k: torch.from_numpy(v) for k, v in state0.items()})
+        model.sampler.train()
+        gb = torch.Generator().manual_seed(12)
+        B = 4
+        p0 = unit_cube(torch.rand(B, 1024, 3, generator=gb) - 0.5)
+        rot = (torch.rand(B, 3, generator=gb) - 0.5) * (np.pi / 2)
+        quat = torch.from_numpy(Q.euler_to_quaternion(rot.numpy(), "xyz").astype(np.float32))
+        vec = torch.cat([quat, torch.zeros(B, 3)], dim=1)
+        igt = {"vec": vec, "inversion": torch.tensor([False])}
+        p1 = QuaternionTransform(vec).rotate(p0)
+        data = (p0, p1, igt)
+        sl, sampled, info = act.compute_samplenet_loss(model, data, "cpu")
+        pl, pinfo = act.compute_pcrnet_loss(model, sampled, "cpu", 0)
+        cons = act.compute_sampling_consistency(sampled, "cpu")
+        if ncl == 2:   # the whole step of train_1 (main.py:340-352): task loss + sampling losses, backward into the sampler
+            model.zero_grad()
+            (pl + sl).backward()
+            gn = {("gnorm_" + k): np.float64(p.grad.double().norm().item()) for k, p in model.sampler.named_parameters()}
+        else:
+            gn = {}
+        np.savez_compressed(
+            os.path.join(OUT, "registration_step_c%d.npz" % ncl), p0=p0.numpy(), p1=p1.detach().numpy(), igt_vec=vec.numpy(),
+            samplenet_loss=sl.detach().numpy(), simplification_loss=info["simplification_loss"].detach().numpy(),
+            projection_loss=info["projection_loss"].detach().numpy(), p0_out=sampled[0].detach().numpy(), p1_out=sampled[1].detach().numpy(),
+            pcrnet_loss=pl.detach().numpy(), chamfer_loss=pinfo["chamfer_loss"].detach().numpy(), qnorm_loss=pinfo["qnorm_loss"].detach().numpy(),
+            rot_err=np.float32(pinfo["rot_err"].detach().numpy()), norm_err=pinfo["norm_err"].detach().numpy(), trans_err=pinfo["trans_err"].detach().numpy(),
+            twist=pinfo["est_transform"].vec.detach().numpy(), consistency=cons.detach().numpy(), alpha=np.float32(args.alpha), lmbda=np.float32(args.lmbda), **gn,
+        )
 
 
 if __name__ == "__main__":
