@@ -410,6 +410,21 @@ def run_ours(args, rank, world, local_rank):
         "note": "arithmetic intensity of the pair work is 3*N*M*8 flop / 22.5 KB = 70 flop/B per cloud before top-k bookkeeping: with the machine "
                 "full these kernels are FP32-issue bound, not HBM bound (SURVEY.md section 8(d) caveat)",
     }
+    # ---- the reference's GPU path on this box (row G0), N=1 only: stock torch layer stack + the reference's Chamfer kernels for sm_100
+    gpu_ref = None
+    if world == 1:
+        try:
+            from oracle import ref_cuda
+            from oracle.torch_reference import time_gpu_reference
+
+            if ref_cuda.available():
+                gpu_ref = time_gpu_reference(dev_pool, M, BOTTLENECK, K_NN, steps=100, warmup=10)
+                gpu_ref["clouds_per_s"] = B / (gpu_ref["step_us"] * 1e-6)
+                gpu_ref["ours_over_reference_gpu"] = gpu_ref["step_us"] / (ms_val / args.steps * 1e3)
+            else:
+                gpu_ref = {"unavailable": "oracle/_ref/libsamplenet_ref_cuda.so not built"}
+        except Exception as exc:
+            gpu_ref = {"error": str(exc)[:300]}
     # ---- CPU baseline beside it (N=1 only; bounded: a few full B=32 steps, in a fresh interpreter pinned to one NUMA node)
     cpu_base = None
     if world == 1:
@@ -434,6 +449,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline_pairwise": roofline_pairwise,
         "kernel_us": kt,
         "cpu_baseline": cpu_base,
+        "gpu_reference": gpu_ref,
     }
     print(json.dumps(line), flush=True)
 

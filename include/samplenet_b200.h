@@ -174,6 +174,28 @@ int snb200_generator_forward(int b, int n, int layout, const float *x, int num_c
                              const snb200_layer *fc, int training, float *out, int out_transpose_inner, float *feat, int flags,
                              void *workspace, size_t workspace_bytes, snb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Generator TRAINING step: forward that keeps what the backward needs, and the backward itself
+ * (replaces `loss.backward()` through registration/src/samplenet.py:90-104 -- stock cuDNN / cuBLAS / ATen kernels in the reference).
+ *   snb200_generator_backward_supported(...) != 0 : shapes covered (the persistent conv-stack envelope, 2 <= b <= 64, BN + ReLU layers)
+ *   snb200_generator_train_forward : snb200_generator_forward + `zsave`: per conv layer l a (b*n, c_out_l) float buffer that receives
+ *                                    the layer's raw output; `workspace` must stay untouched until the backward has run
+ *   snb200_generator_backward      : grad_out (b, c_out_last) in the layout snb200_generator_forward stores `out` -> gradients of
+ *                                    every weight / bias / BatchNorm weight / BatchNorm bias (null pointers are skipped)
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct snb200_layer_grad {
+    float *weight, *bias, *bn_weight, *bn_bias;
+} snb200_layer_grad;
+int snb200_generator_backward_supported(int b, int n, int num_conv, const snb200_layer *conv, int num_fc, const snb200_layer *fc);
+int snb200_generator_train_forward(int b, int n, int layout, const float *x, int num_conv, const snb200_layer *conv, int num_fc,
+                                   const snb200_layer *fc, float *out, int out_transpose_inner, float *feat, float *const *zsave, int flags,
+                                   void *workspace, size_t workspace_bytes, snb200_stream_t stream);
+size_t snb200_generator_backward_workspace_bytes(int b, int n, int num_conv, const snb200_layer *conv, int num_fc, const snb200_layer *fc);
+int snb200_generator_backward(int b, int n, int layout, const float *x, int num_conv, const snb200_layer *conv, int num_fc,
+                              const snb200_layer *fc, float *const *zsave, void *forward_workspace, const float *grad_out,
+                              int out_transpose_inner, const snb200_layer_grad *conv_grads, const snb200_layer_grad *fc_grads,
+                              void *workspace, size_t workspace_bytes, snb200_stream_t stream);
+
 /* Bring-up / unit-test hook of the tcgen05 layer kernel (csrc/encoder_tc.cu): D (rows, c_out) = A (rows, c_in) * W (c_out, c_in)^T + bias
  * as 3xTF32 on the tensor cores.  desc_hi / k_adv16 / swizzle override the shared-memory descriptor encoding (0,0,0 = defaults);
  * they exist so that one GPU session can sweep encodings.  c_in % 8 == 0, 8 <= c_in, c_out <= 256. */

@@ -34,6 +34,12 @@ class Layer(ctypes.Structure):
     ]
 
 
+class LayerGrad(ctypes.Structure):
+    """Mirror of `snb200_layer_grad`."""
+
+    _fields_ = [("weight", _vp), ("bias", _vp), ("bn_weight", _vp), ("bn_bias", _vp)]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "snb200_last_error": (ctypes.c_char_p, []),
@@ -54,6 +60,12 @@ _SIGNATURES = {
     "snb200_encoder_forward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, _vp, _vp, _size, _vp]),
     "snb200_generator_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer)]),
     "snb200_generator_forward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _int, _vp, _size, _vp]),
+    "snb200_generator_backward_supported": (_int, [_int, _int, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer)]),
+    "snb200_generator_train_forward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer), _vp, _int, _vp,
+                                              ctypes.POINTER(_vp), _int, _vp, _size, _vp]),
+    "snb200_generator_backward_workspace_bytes": (_size, [_int, _int, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer)]),
+    "snb200_generator_backward": (_int, [_int, _int, _int, _vp, _int, ctypes.POINTER(Layer), _int, ctypes.POINTER(Layer), ctypes.POINTER(_vp), _vp, _vp, _int,
+                                         ctypes.POINTER(LayerGrad), ctypes.POINTER(LayerGrad), _vp, _size, _vp]),
     "snb200_debug_head_timestamps": (_int, [_vp]),
     "snb200_debug_conv_stack_timestamps": (_int, [_vp]),
     "snb200_debug_tc_gemm": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, ctypes.c_uint, _int, _int, _vp]),

@@ -55,7 +55,13 @@ bool tc_layer_supported(int c_in, int c_out);
 
 size_t generator_workspace_bytes(int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc);
 int launch_generator_forward(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc,
-                             int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream);
+                             int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream,
+                             float *const *zsave = nullptr);
+bool generator_backward_supported(int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc);
+size_t generator_backward_workspace_bytes(int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc);
+int launch_generator_backward(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc,
+                              float *const *zsave, void *fwd_workspace, const float *grad_out, int out_transpose_inner,
+                              const snb200_layer_grad *gconv, const snb200_layer_grad *gfc, void *workspace, cudaStream_t stream);
 
 int debug_head_timestamps(long long *host_out64);
 int debug_conv_stack_timestamps(long long *host_out64);
@@ -258,6 +264,59 @@ SNB_API int snb200_generator_forward(int b, int n, int layout, const float *x, i
     if (!workspace || workspace_bytes < need) { set_error("generator_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
     return launch_generator_forward(b, n, layout, x, num_conv, conv, num_fc, fc, training, out, out_transpose_inner, feat, flags, workspace,
                                     (cudaStream_t)stream);
+}
+
+SNB_API int snb200_generator_backward_supported(int b, int n, int num_conv, const snb200_layer *conv, int num_fc, const snb200_layer *fc)
+{
+    if (check_layers("generator_backward_supported", num_conv, conv, SNB200_MAX_CONV_LAYERS) || check_layers("generator_backward_supported", num_fc, fc, SNB200_MAX_FC_LAYERS) ||
+        b < 1 || n < 1)
+        return 0;
+    return generator_backward_supported(b, n, num_conv, conv, num_fc, fc) ? 1 : 0;
+}
+
+SNB_API int snb200_generator_train_forward(int b, int n, int layout, const float *x, int num_conv, const snb200_layer *conv, int num_fc,
+                                           const snb200_layer *fc, float *out, int out_transpose_inner, float *feat, float *const *zsave, int flags,
+                                           void *workspace, size_t workspace_bytes, snb200_stream_t stream)
+{
+    SNB_REQUIRE(zsave != nullptr, "generator_train_forward: zsave is null");
+    int rc = check_layers("generator_train_forward", num_conv, conv, SNB200_MAX_CONV_LAYERS);
+    if (rc) return rc;
+    rc = check_layers("generator_train_forward", num_fc, fc, SNB200_MAX_FC_LAYERS);
+    if (rc) return rc;
+    SNB_REQUIRE(b >= 1 && n >= 1 && x && out, "generator_train_forward: bad arguments");
+    SNB_REQUIRE(layout == SNB200_BNC || layout == SNB200_BCN, "generator_train_forward: unknown layout %d", layout);
+    SNB_REQUIRE(generator_backward_supported(b, n, num_conv, conv, num_fc, fc), "generator_train_forward: shape outside the CUDA backward's envelope (b=%d n=%d)", b, n);
+    SNB_REQUIRE(!(flags & (SNB200_GEN_EXACT_FP32 | SNB200_GEN_PER_LAYER_KERNELS | SNB200_GEN_SEPARATE_HEAD | SNB200_GEN_PROFILE_SKIP_CONV | SNB200_GEN_PROFILE_SKIP_HEAD)),
+                "generator_train_forward: flags 0x%x select a path that does not keep activations", flags);
+    for (int l = 0; l < num_conv; l++) SNB_REQUIRE(zsave[l] != nullptr, "generator_train_forward: zsave[%d] is null", l);
+    const size_t need = generator_workspace_bytes(b, n, num_conv, conv, num_fc, fc);
+    if (!workspace || workspace_bytes < need) { set_error("generator_train_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
+    return launch_generator_forward(b, n, layout, x, num_conv, conv, num_fc, fc, 1, out, out_transpose_inner, feat, flags, workspace, (cudaStream_t)stream, zsave);
+}
+
+SNB_API size_t snb200_generator_backward_workspace_bytes(int b, int n, int num_conv, const snb200_layer *conv, int num_fc, const snb200_layer *fc)
+{
+    if (check_layers("generator_backward_workspace_bytes", num_conv, conv, SNB200_MAX_CONV_LAYERS) || check_layers("generator_backward_workspace_bytes", num_fc, fc, SNB200_MAX_FC_LAYERS) ||
+        b < 1 || n < 1)
+        return 0;
+    return generator_backward_workspace_bytes(b, n, num_conv, conv, num_fc, fc);
+}
+
+SNB_API int snb200_generator_backward(int b, int n, int layout, const float *x, int num_conv, const snb200_layer *conv, int num_fc,
+                                      const snb200_layer *fc, float *const *zsave, void *forward_workspace, const float *grad_out,
+                                      int out_transpose_inner, const snb200_layer_grad *conv_grads, const snb200_layer_grad *fc_grads,
+                                      void *workspace, size_t workspace_bytes, snb200_stream_t stream)
+{
+    int rc = check_layers("generator_backward", num_conv, conv, SNB200_MAX_CONV_LAYERS);
+    if (rc) return rc;
+    rc = check_layers("generator_backward", num_fc, fc, SNB200_MAX_FC_LAYERS);
+    if (rc) return rc;
+    SNB_REQUIRE(x && zsave && forward_workspace && grad_out && conv_grads && fc_grads, "generator_backward: null pointer");
+    SNB_REQUIRE(generator_backward_supported(b, n, num_conv, conv, num_fc, fc), "generator_backward: shape outside the CUDA backward's envelope (b=%d n=%d)", b, n);
+    const size_t need = generator_backward_workspace_bytes(b, n, num_conv, conv, num_fc, fc);
+    if (!workspace || workspace_bytes < need) { set_error("generator_backward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
+    return launch_generator_backward(b, n, layout, x, num_conv, conv, num_fc, fc, zsave, forward_workspace, grad_out, out_transpose_inner, conv_grads,
+                                     fc_grads, workspace, (cudaStream_t)stream);
 }
 
 SNB_API int snb200_debug_head_timestamps(long long *host_out64) { return debug_head_timestamps(host_out64); }

@@ -47,6 +47,7 @@ struct CsLayer {
     float eps;
     int has_bn, relu;
     double *stats;                      // [2][c_out] sum, sumsq (training) -- written here, read by the next layer and the head
+    float *zsave;                       // optional (total points, c_out): this layer's raw output (with bias) kept for the backward pass
 };
 
 struct CsParams {
@@ -440,6 +441,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 v[j] = __float_as_uint(fmaf(w2, xr[2], fmaf(w1, xr[1], w0 * xr[0])) + b1);
             }
         }
+        if (L1.zsave && cv) {   // a warp stores 32 consecutive channels of one point: 128 contiguous bytes
+            float *zs = L1.zsave + (size_t)(P0 + col0) * L1.c_out + ch;
+#pragma unroll
+            for (int j = 0; j < kCsNPT; j++)
+                if (j < nvalid) zs[(size_t)j * L1.c_out] = __uint_as_float(v[j]);
+        }
     }
 
     uint32_t gchunk = 0;                // global K-chunk counter (same sequence in producers and issuer): slot = gchunk % kCsRing
@@ -543,6 +550,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     }
                 }
                 if (want_stats) { sRedS[g][ch] = sum; sRedQ[g][ch] = sq; }
+                if (Lc.zsave && ch < N) {   // training with gradients: the raw outputs go to HBM / L2 as well (coalesced 128-byte rows)
+                    float *zs = Lc.zsave + (size_t)(P0 + col0) * N + ch;
+#pragma unroll
+                    for (int j = 0; j < kCsNPT; j++)
+                        if (j < nvalid) zs[(size_t)j * N] = __uint_as_float(v[j]);
+                }
             }
             float *sPmax = reinterpret_cast<float *>(smem_raw);                       // [4 groups][kCsMaxSeg][128]
             float *sPmin = sPmax + 4 * kCsMaxSeg * 128;
@@ -977,7 +990,7 @@ bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
 
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
                       double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, const HeadParams *head,
-                      char *clean_ptr, size_t clean_bytes, cudaStream_t stream)
+                      char *clean_ptr, size_t clean_bytes, cudaStream_t stream, float *const *zsave)
 {
     CsParams P;
     memset(&P, 0, sizeof(P));
@@ -995,6 +1008,7 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
         D.c_in = conv[l].c_in; D.c_out = conv[l].c_out; D.weight = conv[l].weight; D.bias = conv[l].bias;
         D.gamma = conv[l].bn_weight; D.beta = conv[l].bn_bias; D.run_mean = conv[l].bn_running_mean; D.run_var = conv[l].bn_running_var;
         D.eps = conv[l].bn_eps; D.has_bn = conv[l].bn_weight != nullptr; D.relu = conv[l].relu; D.stats = stats[l];
+        D.zsave = zsave ? zsave[l] : nullptr;
     }
     if (tiles_per_cloud_out) *tiles_per_cloud_out = P.slots_per_cloud;
     if (head) P.H.tiles_per_cloud = P.slots_per_cloud;

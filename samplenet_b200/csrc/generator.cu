@@ -457,8 +457,22 @@ static bool tc_stack_supported(int nconv, const snb200_layer *conv)
     return true;
 }
 
+struct GenWorkspaceView {
+    const double *stats[SNB200_MAX_CONV_LAYERS];
+    const float *ll[SNB200_MAX_FC_LAYERS + 1];
+};
+GenWorkspaceView generator_workspace_view(void *fwd_workspace, int b, int n, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc)
+{
+    GenWorkspace W = carve_gen_ws(fwd_workspace, b, n, nconv, conv, nfc, fc);
+    GenWorkspaceView V;
+    for (int l = 0; l < SNB200_MAX_CONV_LAYERS; l++) V.stats[l] = l < nconv ? W.stats[l] : nullptr;
+    for (int l = 0; l <= SNB200_MAX_FC_LAYERS; l++) V.ll[l] = W.ll[l];
+    return V;
+}
+
 int launch_generator_forward(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int nfc, const snb200_layer *fc,
-                             int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream)
+                             int training, float *out, int out_transpose_inner, float *feat_out, int flags, void *workspace, cudaStream_t stream,
+                             float *const *zsave)
 {
     GenWorkspace W = carve_gen_ws(workspace, b, n, nconv, conv, nfc, fc);
     const bool coop = !(flags & (SNB200_GEN_EXACT_FP32 | SNB200_GEN_PER_LAYER_KERNELS | SNB200_GEN_PROFILE_SKIP_CONV)) && tc_stack_supported(nconv, conv) &&
@@ -486,7 +500,7 @@ int launch_generator_forward(int b, int n, int layout, const float *x, int nconv
         for (int l = 0; l < nfc; l++) fuse_head = fuse_head && fc[l].c_in <= 1024;
         if (fuse_head) fill_head_params(H, b, n, conv_stack_slots_per_cloud(b, n), nconv, conv, nfc, fc, training, out, out_transpose_inner, feat_out, W);
         int rc = launch_conv_stack(b, n, layout, x, nconv, conv, training, W.stats, W.mom, W.counter, W.tile_max, W.tile_min, &tpc,
-                                   fuse_head ? &H : nullptr, (self_clean && fuse_head) ? W.stats_base + 256 : nullptr, W.stats_bytes - 256, stream);
+                                   fuse_head ? &H : nullptr, (self_clean && fuse_head) ? W.stats_base + 256 : nullptr, W.stats_bytes - 256, stream, zsave);
         if (rc) return rc;
         if (fuse_head) return SNB200_OK;
     } else if (use_tc) {

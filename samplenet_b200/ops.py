@@ -10,7 +10,7 @@ import threading
 import torch
 
 from . import _lib
-from ._lib import BCN, BNC, DIST_FMA, DIST_UNFUSED, Layer, check, lib
+from ._lib import BCN, BNC, DIST_FMA, DIST_UNFUSED, Layer, LayerGrad, check, lib
 
 _LAYOUTS = {"bnc": BNC, "bcn": BCN}
 
@@ -454,6 +454,15 @@ class PrimedWorkspaces:
             self.bufs[key] = t
         return t
 
+    def get_named(self, dev, name, shapes):
+        """Persistent float buffers (e.g. the activations kept for the backward pass), one list per (device, name, shapes)."""
+        key = (dev.index, name, tuple(tuple(s) for s in shapes))
+        t = self.bufs.get(key)
+        if t is None:
+            t = [torch.empty(*s, device=dev) for s in shapes]
+            self.bufs[key] = t
+        return t
+
 
 _ACTIVE_PW = threading.local()
 
@@ -501,6 +510,84 @@ def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_i
                                              _stream()), "generator_forward")
     del keep1, keep2
     return out, feat
+
+
+def generator_backward_supported(x, layout, conv_specs, fc_specs):
+    """True when the CUDA backward (csrc/generator_bwd.cu) covers this shape: the persistent conv-stack envelope, 2 <= B <= 64,
+    BatchNorm + ReLU on every conv layer."""
+    lay = _layout(layout)
+    b = x.shape[0]
+    n = x.shape[1] if lay == BNC else x.shape[2]
+    conv, keep1 = make_layers(conv_specs)
+    fc, keep2 = make_layers(fc_specs)
+    return bool(lib().snb200_generator_backward_supported(b, n, len(conv_specs), conv, len(fc_specs), fc))
+
+
+def generator_train_forward(x, layout, conv_specs, fc_specs, out_transpose_inner=0):
+    """Training-mode forward that keeps what the CUDA backward needs.  Returns (out, feat, saved) with saved = (zsave list, workspace)."""
+    lay = _layout(layout)
+    x = _req(x, "x")
+    b = x.shape[0]
+    n = x.shape[1] if lay == BNC else x.shape[2]
+    dev = x.device
+    conv, keep1 = make_layers(conv_specs)
+    fc, keep2 = make_layers(fc_specs)
+    with torch.cuda.device(dev):
+        wsb = int(lib().snb200_generator_workspace_bytes(b, n, len(conv_specs), conv, len(fc_specs), fc))
+        pw = getattr(_ACTIVE_PW, "pw", None)
+        primed = 0
+        if pw is not None:
+            ws = pw.get(dev, wsb)
+            primed = _lib.GEN_WORKSPACE_PRIMED
+            zs = pw.get_named(dev, "zsave", [(b * n, conv[l].c_out) for l in range(len(conv_specs))])
+        else:
+            ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+            zs = [torch.empty(b * n, conv[l].c_out, device=dev) for l in range(len(conv_specs))]
+        zp = (ctypes.c_void_p * len(zs))(*[z.data_ptr() for z in zs])
+        feat = torch.empty(b, conv[len(conv_specs) - 1].c_out, device=dev)
+        out = torch.empty(b, fc[len(fc_specs) - 1].c_out, device=dev)
+        check(lib().snb200_generator_train_forward(b, n, lay, _p(x), len(conv_specs), conv, len(fc_specs), fc, _p(out), int(out_transpose_inner), _p(feat),
+                                                   zp, primed, _p(ws), wsb, _stream()), "generator_train_forward")
+    del keep1, keep2
+    return out, feat, (zs, ws)
+
+
+def generator_backward(x, layout, conv_specs, fc_specs, saved, grad_out, out_transpose_inner=0):
+    """Gradients of every generator parameter (hand-written CUDA; csrc/generator_bwd.cu).  Returns a list, in layer order (conv then fc), of
+    dicts {weight, bias, bn_weight, bn_bias} (bn_* None for layers without BatchNorm)."""
+    lay = _layout(layout)
+    x = _req(x, "x"); grad_out = _req(grad_out, "grad_out")
+    b = x.shape[0]
+    n = x.shape[1] if lay == BNC else x.shape[2]
+    dev = x.device
+    zs, fwd_ws = saved
+    conv, keep1 = make_layers(conv_specs)
+    fc, keep2 = make_layers(fc_specs)
+    grads = []
+
+    def grad_structs(specs):
+        arr = (LayerGrad * len(specs))()
+        for i, s in enumerate(specs):
+            w = s["weight"]
+            g = {"weight": torch.empty_like(w), "bias": torch.empty(w.shape[0], device=dev) if s.get("bias") is not None else None,
+                 "bn_weight": None, "bn_bias": None}
+            if s.get("bn") is not None:
+                g["bn_weight"] = torch.empty(w.shape[0], device=dev); g["bn_bias"] = torch.empty(w.shape[0], device=dev)
+            arr[i].weight, arr[i].bias = _p(g["weight"]), _p(g["bias"])
+            arr[i].bn_weight, arr[i].bn_bias = _p(g["bn_weight"]), _p(g["bn_bias"])
+            grads.append(g)
+        return arr
+
+    with torch.cuda.device(dev):
+        gconv = grad_structs(conv_specs)
+        gfc = grad_structs(fc_specs)
+        wsb = int(lib().snb200_generator_backward_workspace_bytes(b, n, len(conv_specs), conv, len(fc_specs), fc))
+        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        zp = (ctypes.c_void_p * len(zs))(*[z.data_ptr() for z in zs])
+        check(lib().snb200_generator_backward(b, n, lay, _p(x), len(conv_specs), conv, len(fc_specs), fc, zp, _p(fwd_ws), _p(grad_out), int(out_transpose_inner),
+                                              gconv, gfc, _p(ws), wsb, _stream()), "generator_backward")
+    del keep1, keep2
+    return grads
 
 
 def generator_forward_unfused(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0):

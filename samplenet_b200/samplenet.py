@@ -33,7 +33,14 @@ class _GeneratorFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, layout, training, out_inner, *params):
         conv_specs, fc_specs = net._layer_specs()
-        out, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, training, out_inner, exact_fp32=net.generator_precision == "fp32")
+        ctx.cuda_saved = None
+        if (training and net.generator_backward == "cuda" and net.generator_precision != "fp32" and not ctx.needs_input_grad[1]
+                and ops.generator_backward_supported(x, layout, conv_specs, fc_specs)):
+            # forward that keeps every conv layer's raw output (registers -> HBM while the CTA waits at the statistics barrier): the
+            # backward is then this library's own kernels (csrc/generator_bwd.cu), no recompute, no library GEMM
+            out, _, ctx.cuda_saved = ops.generator_train_forward(x, layout, conv_specs, fc_specs, out_inner)
+        else:
+            out, _ = ops.generator_forward(x, layout, conv_specs, fc_specs, training, out_inner, exact_fp32=net.generator_precision == "fp32")
         ctx.net = net
         ctx.layout = layout
         ctx.training = training
@@ -46,6 +53,15 @@ class _GeneratorFunction(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         net = ctx.net
         names = [n for n, _ in net._generator_named_parameters()]
+        if ctx.cuda_saved is not None:
+            conv_specs, fc_specs = net._layer_specs()
+            grads = ops.generator_backward(x, ctx.layout, conv_specs, fc_specs, ctx.cuda_saved, g.contiguous(), ctx.out_inner)
+            gp = []
+            for gl in grads:   # same order as _generator_named_parameters: w, b[, g, beta] per layer
+                gp += [gl["weight"].view_as(params[len(gp)]), gl["bias"]]
+                if gl["bn_weight"] is not None:
+                    gp += [gl["bn_weight"], gl["bn_bias"]]
+            return (None, None, None, None, None, *gp)
         # the recompute runs the reference layer stack in true fp32 (torch's cuDNN default would be plain TF32)
         tf32_c, tf32_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
@@ -119,6 +135,9 @@ class SampleNet(nn.Module):
         # "3xtf32": conv layers 2..5 on the tensor cores, error-compensated to fp32 accuracy (default);
         # "fp32":   exact-fp32 CUDA-core conv stack.  Not part of the reference signature; plain attribute.
         self.generator_precision = "3xtf32"
+        # "cuda": hand-written backward kernels (csrc/generator_bwd.cu) wherever they cover the shape; "torch": recompute the layer stack
+        # with stock torch ops and differentiate that (the round-1 path; also the fallback outside the CUDA backward's envelope)
+        self.generator_backward = "cuda"
         # project + Chamfer + loss reductions of (simp, x) in one launch when forward() runs in training mode ("bnc" in and out)
         self.fused_tail = True
         self._tail = None
