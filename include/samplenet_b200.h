@@ -214,6 +214,20 @@ int snb200_fc_head_forward(int b, const float *in, int num_layers, const snb200_
                            int out_transpose_inner, void *workspace, size_t workspace_bytes, snb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * SampleNetProgressive: the simplification loss summed over prefixes of an ORDERED sample set, one launch
+ * (replaces the per-prefix NnDistance ops + reductions of classification/train_samplenet_progressive.py:172-230).
+ *   ref (b,n,3), samp (b,m,3); sizes[num_prefix] ascending prefix lengths (<= m, <= 16 of them); weights[p] = gamma + delta * sizes[p]
+ *   dist1/idx1 (b,m): sample -> nearest input point (prefix p uses the slice [:sizes[p]])
+ *   dist2/idx2 (b,num_prefix,n): input point -> nearest of the first sizes[p] samples
+ *   terms (3*num_prefix + 1): per prefix [mean dist1[:s], mean_b max dist1[:s], mean dist2_p], then the total loss
+ *   ticket: one zero-initialised unsigned, left zero.  sizes / weights are HOST arrays.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t snb200_progressive_loss_workspace_bytes(int b, int n, int m, int num_prefix);
+int snb200_progressive_loss_forward(int b, int n, int m, const float *ref, const float *samp, int num_prefix, const int *sizes, const float *weights,
+                                    float *dist1, int *idx1, float *dist2, int *idx2, float *terms, void *workspace, size_t workspace_bytes,
+                                    unsigned *ticket, int flags, snb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * EMD.  xyz1 (b,n,3), xyz2 (b,m,3), match (b,m,n), cost (b), grad1 (b,n,3), grad2 (b,m,3).
  * Replace approxmatchLauncher / matchcostLauncher / matchcostgradLauncher
  * (classification/structural_losses/tf_approxmatch.cpp:141-143, tf_approxmatch_g.cu:181,227,293-294).

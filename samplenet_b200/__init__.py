@@ -12,4 +12,4 @@ from .chamfer_distance import ChamferDistance, ChamferDistanceFunction  # noqa: 
 from .samplenet import SampleNet  # noqa: F401
 from .soft_projection import SoftProjection, knn_point  # noqa: F401
 
-__all__ = ["SampleNet", "SoftProjection", "ChamferDistance", "ChamferDistanceFunction", "knn_point", "sputils", "tf_ops", "ops", "GraphedStep", "PipelinedHostStep"]
+__all__ = ["SampleNet", "SoftProjection", "ChamferDistance", "ChamferDistanceFunction", "knn_point", "sputils", "tf_ops", "ops", "GraphedStep", "PipelinedHostStep", "GraphedTrainStep"]

@@ -71,6 +71,9 @@ _SIGNATURES = {
     "snb200_debug_tc_gemm": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, ctypes.c_uint, _int, _int, _vp]),
     "snb200_fc_head_workspace_bytes": (_size, [_int, _int, ctypes.POINTER(Layer)]),
     "snb200_fc_head_forward": (_int, [_int, _vp, _int, ctypes.POINTER(Layer), _int, _vp, _int, _vp, _size, _vp]),
+    "snb200_progressive_loss_workspace_bytes": (_size, [_int, _int, _int, _int]),
+    "snb200_progressive_loss_forward": (_int, [_int, _int, _int, _vp, _vp, _int, ctypes.POINTER(_int), ctypes.POINTER(_float), _vp, _vp, _vp, _vp, _vp, _vp, _size,
+                                               _vp, _int, _vp]),
     "snb200_approxmatch_workspace_bytes": (_size, [_int, _int, _int]),
     "snb200_approxmatch": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _size, _vp]),
     "snb200_approxmatch_mode": (_int, [_int, _int, _int, _vp, _vp, _vp, _int, _vp, _size, _vp]),

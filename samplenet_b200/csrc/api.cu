@@ -67,6 +67,9 @@ int debug_head_timestamps(long long *host_out64);
 int debug_conv_stack_timestamps(long long *host_out64);
 
 size_t tail_workspace_bytes(int b, int n_samp, int n_ref);
+size_t progressive_workspace_bytes(int b, int n, int m, int np);
+int launch_progressive_loss(int b, int n, int m, const float *ref, const float *samp, int np, const int *sizes, const float *w21, float *dist1, int *idx1,
+                            float *dist2, int *idx2, float *terms, void *workspace, unsigned *ticket, int flags, cudaStream_t stream);
 int launch_tail_fused(int b, int n_ref, int n_samp, int k, const float *ref, const float *samp, const float *sigma, int sigma_mode, float sigma_floor,
                       float *proj, int *knn_idx, float *weights, float *dist_over_sigma, float *dist1, int *idx1, float *dist2, int *idx2,
                       float w21, float *out4, float *partial, unsigned *ticket, int flags, cudaStream_t stream);
@@ -353,6 +356,22 @@ SNB_API int snb200_fc_head_forward(int b, const float *in, int num_layers, const
     const size_t need = fc_head_workspace_bytes(b, num_layers, layers);
     if (!workspace || workspace_bytes < need) { set_error("fc_head_forward: workspace %zu < %zu bytes", workspace_bytes, need); return SNB200_EWORKSPACE; }
     return launch_fc_head_forward(b, in, num_layers, layers, training, out, out_transpose_inner, workspace, (cudaStream_t)stream);
+}
+
+SNB_API size_t snb200_progressive_loss_workspace_bytes(int b, int n, int m, int num_prefix) { return progressive_workspace_bytes(b, n, m, num_prefix); }
+
+SNB_API int snb200_progressive_loss_forward(int b, int n, int m, const float *ref, const float *samp, int num_prefix, const int *sizes, const float *weights,
+                                            float *dist1, int *idx1, float *dist2, int *idx2, float *terms, void *workspace, size_t workspace_bytes,
+                                            unsigned *ticket, int flags, snb200_stream_t stream)
+{
+    SNB_REQUIRE(b >= 1 && n >= 1 && m >= 1, "progressive_loss: bad sizes b=%d n=%d m=%d", b, n, m);
+    SNB_REQUIRE(num_prefix >= 1 && num_prefix <= 16 && sizes && weights, "progressive_loss: 1..16 prefixes expected, got %d", num_prefix);
+    SNB_REQUIRE(m <= 4096, "progressive_loss: at most 4096 ordered samples (one shared-memory tile), got %d", m);
+    for (int p = 0; p < num_prefix; p++)
+        SNB_REQUIRE(sizes[p] >= 1 && sizes[p] <= m && (p == 0 || sizes[p] > sizes[p - 1]), "progressive_loss: prefix sizes must be ascending in [1, m]");
+    SNB_REQUIRE(ref && samp && dist1 && idx1 && dist2 && idx2 && terms && ticket, "progressive_loss: null pointer");
+    if (!workspace || workspace_bytes < progressive_workspace_bytes(b, n, m, num_prefix)) { set_error("progressive_loss: workspace too small"); return SNB200_EWORKSPACE; }
+    return launch_progressive_loss(b, n, m, ref, samp, num_prefix, sizes, weights, dist1, idx1, dist2, idx2, terms, workspace, ticket, flags, (cudaStream_t)stream);
 }
 
 SNB_API size_t snb200_approxmatch_workspace_bytes(int b, int n, int m) { return approxmatch_workspace_bytes(b, n, m); }

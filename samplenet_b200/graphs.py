@@ -16,6 +16,27 @@ import torch
 from . import _lib, ops
 
 
+def _snapshot(module):
+    """Clones of every parameter and buffer (BatchNorm running statistics, num_batches_tracked): graph construction runs real warm-up
+    executions of the step on a placeholder batch, which must not leave a trace in the model."""
+    return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def _restore(module, snap):
+    with torch.no_grad():
+        for k, v in module.state_dict().items():
+            v.copy_(snap[k])           # in place: captured graphs keep pointing at the same storage
+
+
+def _reset_optimizer_state(opt):
+    """Zero the optimizer's per-parameter state in place (capturable Adam: step, exp_avg, exp_avg_sq) -- the state after construction."""
+    with torch.no_grad():
+        for st in opt.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
+
 class PipelinedHostStep:
     """End-to-end streaming of host batches through two `GraphedStep`s (double buffering): the pinned host batch of a later step
     crosses PCIe on a copy stream while an earlier step computes, and up to two steps are in flight so the GPU always has the next
@@ -103,10 +124,12 @@ class GraphedStep:
             return simp, proj, loss
 
         with torch.cuda.device(dev), torch.no_grad():
+            snap = _snapshot(net)          # warm-up forwards in train mode would move the BatchNorm running statistics
             self.stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self.stream):
                 for _ in range(warmup):
                     body()
+                _restore(net, snap)
             self.stream.synchronize()
             before = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()
@@ -190,10 +213,16 @@ class GraphedTrainStep:
 
         self.stream = torch.cuda.Stream(device=dev)
         with torch.cuda.device(dev):
+            # the warm-up executions are REAL optimizer steps on a placeholder batch: undo them (parameters, BatchNorm buffers, Adam
+            # moments and step counts) so that constructing the graphed step leaves the training trajectory untouched
+            snap = _snapshot(net)
             self.stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self.stream):
                 for _ in range(warmup):
                     body()
+                _restore(net, snap)
+                _reset_optimizer_state(self.optimizer)
+                self.ddp.zero_grad()
             self.stream.synchronize()
             before = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()

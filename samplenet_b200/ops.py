@@ -276,11 +276,10 @@ _TICKETS = {}
 
 
 def _ticket(dev):
-    """One zero-initialised device counter per GPU for the last-CTA reduction of the fused tail (the kernel leaves it zero).
-    Limitation (documented in DESIGN.md section 7): the word is shared by every fused-tail launch on that GPU, so such launches must be
-    stream-ordered with respect to each other (they are inside one training loop / one graph); two of them running CONCURRENTLY on
-    different streams of one device would share it.  The C ABI itself takes the word as an argument and has no such restriction."""
-    key = (dev.type, dev.index)
+    """One zero-initialised device counter per (GPU, stream) for the last-CTA reductions (fused tail, progressive loss); the kernels leave
+    it zero.  Launches that share a word are stream-ordered by construction; concurrent launches on different streams get different
+    words.  (A kernel that traps leaves the context unusable anyway.)  The C ABI takes the word as an argument."""
+    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)   # launches on different streams never share a word
     t = _TICKETS.get(key)
     if t is None:
         t = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -357,6 +356,63 @@ class ProjectAndLossFunction(torch.autograd.Function):
             if need[0]:
                 g_ref = gr_c if g_ref is None else g_ref + gr_c
         return (g_ref if need[0] else None), g_samp, g_t, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------- progressive loss
+def progressive_loss_forward(ref, samp, sizes, weights, unfused=False):
+    """One launch: dist1/idx1 (B,M), dist2/idx2 (B,P,N) for the P prefixes `sizes` of the ordered samples, terms (3P+1,)."""
+    ref, samp = _req(ref, "ref_pc"), _req(samp, "samp_pc")
+    b, n, _ = ref.shape
+    m = samp.shape[1]
+    npf = len(sizes)
+    dev = ref.device
+    csz = (ctypes.c_int * npf)(*[int(v) for v in sizes])
+    cw = (ctypes.c_float * npf)(*[float(v) for v in weights])
+    with torch.cuda.device(dev):
+        dist1 = torch.empty(b, m, device=dev); idx1 = torch.empty(b, m, device=dev, dtype=torch.int32)
+        dist2 = torch.empty(b, npf, n, device=dev); idx2 = torch.empty(b, npf, n, device=dev, dtype=torch.int32)
+        terms = torch.empty(3 * npf + 1, device=dev)
+        wsb = int(lib().snb200_progressive_loss_workspace_bytes(b, n, m, npf))
+        ws = torch.empty(max(wsb, 4), device=dev, dtype=torch.uint8)
+        check(lib().snb200_progressive_loss_forward(b, n, m, _p(ref), _p(samp), npf, csz, cw, _p(dist1), _p(idx1), _p(dist2), _p(idx2), _p(terms), _p(ws), wsb,
+                                                    _p(_ticket(dev)), DIST_UNFUSED if unfused else DIST_FMA, _stream()), "progressive_loss_forward")
+    return dist1, idx1, dist2, idx2, terms
+
+
+class ProgressiveLossFunction(torch.autograd.Function):
+    """sum over prefixes s of [mean(c12[:s]) + mean_b(max c12[:s]) + w_s mean(c21^(s))]  (train_samplenet_progressive.py:196-220) in one
+    forward launch; backward = one deterministic Chamfer-backward launch over the concatenated prefix index sets."""
+
+    @staticmethod
+    def forward(ctx, samp, ref, sizes, weights):
+        samp = samp.contiguous(); ref = ref.contiguous()
+        dist1, idx1, dist2, idx2, terms = progressive_loss_forward(ref, samp, sizes, weights)
+        ctx.save_for_backward(samp, ref, dist1, idx1, idx2)
+        ctx.sizes, ctx.weights = [int(v) for v in sizes], [float(v) for v in weights]
+        return terms[3 * len(sizes)].clone(), terms[:3 * len(sizes)].view(len(sizes), 3)
+
+    @staticmethod
+    def backward(ctx, g, g_terms):
+        samp, ref, dist1, idx1, idx2 = ctx.saved_tensors
+        b, m = dist1.shape
+        npf, n = idx2.shape[1], idx2.shape[2]
+        dev = samp.device
+        sizes = torch.tensor(ctx.sizes, device=dev)
+        w = torch.tensor(ctx.weights, device=dev)
+        gt = g_terms if g_terms is not None else torch.zeros(npf, 3, device=dev)
+        gg = g if g is not None else torch.zeros((), device=dev)
+        a0 = gg + gt[:, 0]; a1 = gg + gt[:, 1]; a2 = gg * w + gt[:, 2]           # d total / d term, per prefix
+        # mean(c12[:s]) : every j < s gets 1/(b s);  as a function of j: sum over prefixes with s > j
+        j = torch.arange(m, device=dev)
+        cover = (sizes[None, :] > j[:, None]).to(dist1.dtype)                     # (m, P)
+        g1 = (cover * (a0 / (b * sizes.to(dist1.dtype)))[None, :]).sum(1)[None, :].expand(b, m).clone()
+        # mean_b max(c12[:s]) : the running arg-max at position s-1
+        am = torch.cummax(dist1, dim=1).indices[:, sizes - 1]                     # (b, P)
+        g1.scatter_add_(1, am, (a1 / b)[None, :].expand(b, npf).contiguous())
+        g2 = (a2 / (b * n))[None, :, None].expand(b, npf, n).reshape(b, npf * n).contiguous()
+        ref_rep = ref[:, None].expand(b, npf, n, 3).reshape(b, npf * n, 3).contiguous()
+        gs, gr = nn_distance_backward(samp, ref_rep, g1.contiguous(), idx1, g2, idx2.reshape(b, npf * n).contiguous())
+        return gs, gr.view(b, npf, n, 3).sum(1), None, None
 
 
 def group_point(points, idx, layout="bnc"):

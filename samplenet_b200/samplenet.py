@@ -187,7 +187,16 @@ class SampleNet(nn.Module):
                 y = F.relu(y)
         return y
 
+    MAX_GENERATOR_BATCH = 256   # rows the FC head kernels hold per launch (snb200_generator_forward rejects more)
+
     def _generate(self, x, layout, out_inner):
+        if x.shape[0] > self.MAX_GENERATOR_BATCH:
+            if self.training:
+                raise RuntimeError("SampleNet: training-mode batches are limited to %d clouds per call (BatchNorm over the batch runs inside one "
+                                   "FC-head launch); got %d.  Split the batch (statistics are per call, as in the reference per GPU)." %
+                                   (self.MAX_GENERATOR_BATCH, x.shape[0]))
+            # eval mode: BatchNorm uses the running statistics, so the batch can be processed in chunks with identical results
+            return torch.cat([self._generate(xc.contiguous(), layout, out_inner) for xc in x.split(self.MAX_GENERATOR_BATCH, dim=0)], dim=0)
         params = [p for _, p in self._generator_named_parameters()]
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if need_grad:

@@ -63,9 +63,17 @@ def autoencoder_simplification_loss(ref_pc, samp_pc, pc_size, is_denoising=False
     return loss, cost_p1_p2, idx, cost_p2_p1, per_cloud
 
 
-def progressive_simplification_loss(ref_pc, ordered_samples, sizes, gamma=1, delta=0):
+def progressive_simplification_loss(ref_pc, ordered_samples, sizes, gamma=1, delta=0, one_pass=True):
     """SampleNetProgressive (classification/train_samplenet_progressive.py:196-220): the simplification loss summed over the
-    prefixes `ordered_samples[:, :s]` for s in `sizes`."""
+    prefixes `ordered_samples[:, :s]` for s in `sizes`.  one_pass=True (default): ONE launch evaluates every prefix (the sample -> input
+    distances of a prefix are a slice, the input -> sample distances a running prefix minimum: csrc/progressive.cu); one_pass=False: the
+    reference's structure, one Chamfer evaluation per prefix."""
+    sizes = [int(s) for s in sizes]
+    if one_pass and len(sizes) <= 16 and ordered_samples.shape[1] <= 4096 and sorted(set(sizes)) == sizes:
+        from . import ops
+
+        total, _ = ops.ProgressiveLossFunction.apply(ordered_samples, ref_pc, sizes, [gamma + delta * s for s in sizes])
+        return total
     total = torch.zeros((), device=ref_pc.device)
     for s in sizes:
         total = total + tf_ops.get_simplification_loss(ref_pc, ordered_samples[:, :s].contiguous(), s, gamma, delta)

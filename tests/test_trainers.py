@@ -71,3 +71,31 @@ def test_trainer_losses_match_reference_formulas():
     sizes = [8, 16, 32]
     prog = trainers.progressive_simplification_loss(p1, samp, sizes, 1, 0)
     np.testing.assert_allclose(float(prog), sum(float(simp_loss(p1, samp[:, :s].contiguous(), s, 1, 0)) for s in sizes), rtol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,n,m,sizes", [(4, 1024, 1024, [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]), (3, 500, 300, [7, 50, 299, 300]), (32, 1024, 1024, [8, 16, 32, 64, 128, 256, 512, 1024])])
+def test_progressive_one_pass_equals_per_prefix(b, n, m, sizes):
+    """csrc/progressive.cu: every prefix's Chamfer distances AND indices bit-identical to a stand-alone nn_distance on the sliced samples
+    (the reference's graph: one NnDistance per prefix, train_samplenet_progressive.py:196-220); loss and gradients within fp32 tolerance."""
+    import numpy as np
+    import samplenet_b200 as sb
+    from samplenet_b200 import ops, trainers
+
+    g = torch.Generator().manual_seed(b + n + m)
+    x = (torch.rand(b, n, 3, generator=g) - 0.5).cuda()
+    s = (torch.rand(b, m, 3, generator=g) - 0.5).cuda()
+    dist1, idx1, dist2, idx2, terms = ops.progressive_loss_forward(x, s, sizes, [1.0 + 0.01 * v for v in sizes])
+    for p, sz in enumerate(sizes):
+        d1, i1, d2, i2 = ops.nn_distance_forward(s[:, :sz].contiguous(), x)
+        assert torch.equal(dist1[:, :sz], d1) and torch.equal(idx1[:, :sz], i1)
+        assert torch.equal(dist2[:, p], d2) and torch.equal(idx2[:, p], i2)
+    s1 = s.clone().requires_grad_(True); x1 = x.clone().requires_grad_(True)
+    s2 = s.clone().requires_grad_(True); x2 = x.clone().requires_grad_(True)
+    l1 = trainers.progressive_simplification_loss(x1, s1, sizes, gamma=1, delta=0.01, one_pass=True)
+    l2 = trainers.progressive_simplification_loss(x2, s2, sizes, gamma=1, delta=0.01, one_pass=False)
+    np.testing.assert_allclose(float(l1), float(l2), rtol=2e-6)
+    np.testing.assert_allclose(float(terms[-1]), float(l2), rtol=2e-6)
+    l1.backward(); l2.backward()
+    np.testing.assert_allclose(s1.grad.cpu().numpy(), s2.grad.cpu().numpy(), rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), x2.grad.cpu().numpy(), rtol=1e-4, atol=1e-8)
