@@ -370,13 +370,14 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "conv_stack_kernel (the whole generator in one persistent cooperative launch: conv layers 1-5 on tcgen05.mma kind::tf32 "
-                  "(3xTF32) with activations resident in TMEM, max-pool, FC head; BatchNorm batch statistics via grid barriers)",
+        "kernel": "conv_stack_kernel (the whole generator in one persistent cooperative launch: conv layers 2-5 as TRANSPOSED GEMMs on tcgen05.mma "
+                  "kind::tf32 (3xTF32): weights = A operand in tensor memory, activations = B operand in swizzled shared memory, one channel per thread, "
+                  "224 points per CTA on all 148 SMs; max-pool; FC head; BatchNorm batch statistics via grid barriers)",
         "bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops"],
         "peak_source": pk["source"] + " cuBLAS bf16 burst. `achieved` counts the ALGORITHMIC fp32 flops (2*M*N*K over the 5 conv + 4 FC layers = %.2f GFLOP "
                        "per launch); the kernel issues 3 TF32 MMAs per product (error compensation to fp32 accuracy) and TF32 runs at half the "
-                       "bf16 rate, so the ceiling for this number is peak/6; at B=32 (256 tiles, < 2 per SM) the launch is a chain of 5 grid "
-                       "barriers + per-layer operand preparation + 4 dependent FC layers: latency-bound, tensor pipe active ~9%%" % (gen_flops / 1e9),
+                       "bf16 rate, so the ceiling for this number is peak/6; the launch is a dependent chain (5 BatchNorm statistics grid barriers, "
+                       "4 dependent FC layers on 32 rows): latency-bound, see profiles/ for the tensor-pipe share" % (gen_flops / 1e9),
         "frac_of_3xtf32_ceiling": ach_tf / (pk["bf16_tflops"] / 6.0), "traffic": traffic, "us_per_launch": kt["generator_us"],
         "algorithmic_flops_per_launch": gen_flops,
         "conv_phase_only": {"us": kt["conv_stack_us"], "achieved_tflops": conv_flops / (kt["conv_stack_us"] * 1e-6) / 1e12},

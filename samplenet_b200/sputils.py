@@ -26,6 +26,19 @@ def nn_matching(full_pc, idx, k, complete_fps=True):
     return out.cpu().numpy().astype(np.float64)
 
 
+def simple_projection_and_continued_fps(full_pc, gen_pc, idx):
+    """reconstruction/src/samplenet_pointnet_ae.py:535-549 on the GPU: per cloud, order-preserving unique of the nearest-neighbour indices
+    `idx` (B, k) of the generated points, completed to k points by farthest point sampling seeded with them
+    (`fps_from_given_indices`, :513-533).  full_pc (B,N,3) float32 CUDA, gen_pc (B,k,3) (only its k is used, as in the reference),
+    idx (B,k) int -> (out_pc (B,k,3), out_pc_idx (B,k) int32, n_unique_points (B,1))."""
+    k = gen_pc.shape[1]
+    ii = idx.to(torch.int32).contiguous()
+    out_pc, out_idx = ops.nn_matching(full_pc, ii, k, complete_fps=True, return_idx=True)
+    srt = torch.sort(ii.long(), dim=1)[0]
+    n_unique = 1 + (srt[:, 1:] != srt[:, :-1]).sum(dim=1, keepdim=True)
+    return out_pc, out_idx, n_unique
+
+
 # Flag table: (short/long names, type or action, default, help).  Produces exactly the parser of
 # registration/src/sputils.py:45-62 so that scripts written against the reference parse the same command lines.
 _FLAGS = (

@@ -78,3 +78,69 @@ def progressive_simplification_loss(ref_pc, ordered_samples, sizes, gamma=1, del
     for s in sizes:
         total = total + tf_ops.get_simplification_loss(ref_pc, ordered_samples[:, :s].contiguous(), s, gamma, delta)
     return total
+
+
+# ----------------------------------------------------------------------------------------------------- whole steps with task networks
+class ClassificationStep:
+    """One training step of classification/train_samplenet.py:154-199: sampler (generator + TF-flavoured soft projection, sigma = T^2) in
+    front of a FROZEN PointNet classifier; loss = loss_classifier + ALPHA * loss_simplification + LMBDA * loss_projection.
+    `sampler` is a SampleNet-like module returning (simplified, projected) on (B,N,3) input; `classifier` a tasknets.PointNetCls."""
+
+    def __init__(self, sampler, classifier, num_out_points, alpha=30.0, lmbda=1.0, gamma=1.0, delta=0.0):
+        self.sampler, self.classifier = sampler, classifier
+        self.M, self.alpha, self.lmbda, self.gamma, self.delta = num_out_points, alpha, lmbda, gamma, delta
+        classifier.requires_grad_(False)
+        classifier.eval()
+
+    def loss(self, point_clouds, labels):
+        simplified, projected = self.sampler(point_clouds)
+        pred, end_points = self.classifier(projected)
+        loss_classifier = self.classifier.get_loss(pred, labels, end_points)
+        loss_simplification = self.sampler.get_simplification_loss(point_clouds, simplified, self.M, self.gamma, self.delta)
+        loss_projection = self.sampler.get_projection_loss()
+        total = loss_classifier + self.alpha * loss_simplification + self.lmbda * loss_projection
+        return total, {"loss_classifier": loss_classifier, "loss_simplification": loss_simplification, "loss_projection": loss_projection, "pred": pred}
+
+
+class ProgressiveClassificationStep(ClassificationStep):
+    """classification/train_samplenet_progressive.py:156-230: ONE generator pass emits MAX ordered points; the classifier and the
+    simplification loss are evaluated on every power-of-two prefix and summed."""
+
+    def __init__(self, sampler, classifier, min_points, max_points, alpha=30.0, lmbda=1.0, gamma=1.0, delta=0.0):
+        super().__init__(sampler, classifier, max_points, alpha, lmbda, gamma, delta)
+        self.sizes = []
+        s = min_points
+        while s <= max_points:
+            self.sizes.append(s)
+            s *= 2
+
+    def loss(self, point_clouds, labels):
+        simplified, projected = self.sampler(point_clouds)
+        loss_classifier = 0.0
+        for s in self.sizes:
+            pred, end_points = self.classifier(projected[:, :s].contiguous())
+            loss_classifier = loss_classifier + self.classifier.get_loss(pred, labels, end_points)
+        loss_simplification = progressive_simplification_loss(point_clouds, simplified, self.sizes, self.gamma, self.delta)
+        loss_projection = self.sampler.get_projection_loss()
+        total = loss_classifier + self.alpha * loss_simplification + self.lmbda * loss_projection
+        return total, {"loss_classifier": loss_classifier, "loss_simplification": loss_simplification, "loss_projection": loss_projection}
+
+
+class ReconstructionStep:
+    """One training step of reconstruction/src/samplenet_pointnet_ae.py:46-189: sampler (rec widths, sigma = max(T, 1e-2)^2) in front of a
+    FROZEN auto-encoder; loss = AE loss(reconstruction of the projected points, input cloud) [Chamfer or EMD] + ALPHA * simplification
+    loss (weight pc_size / 64 on the input -> sample term) + LMBDA * projection loss."""
+
+    def __init__(self, sampler, ae, num_out_points, alpha=0.01, lmbda=1e-4, ae_loss="chamfer"):
+        self.sampler, self.ae, self.M, self.alpha, self.lmbda, self.ae_loss = sampler, ae, num_out_points, alpha, lmbda, ae_loss
+        ae.requires_grad_(False)
+        ae.eval()
+
+    def loss(self, point_clouds):
+        simplified, projected = self.sampler(point_clouds)
+        x_reconstr = self.ae(projected)
+        loss_ae = autoencoder_loss(x_reconstr, point_clouds, self.ae_loss)
+        loss_simplification, _, _, _, _ = autoencoder_simplification_loss(point_clouds, simplified, self.M)
+        loss_projection = self.sampler.get_projection_loss()
+        total = loss_ae + self.alpha * loss_simplification + self.lmbda * loss_projection
+        return total, {"loss_ae": loss_ae, "loss_simplification": loss_simplification, "loss_projection": loss_projection}

@@ -834,3 +834,35 @@ def test_fused_tail_matches_separate_kernels(sb, oracle):
     a = sb.ops.project_and_loss_forward(x, ss_t := simp.detach(), 8, net.project._temperature, 1, 1e-2, 1.0)[-1].clone()
     c = sb.ops.project_and_loss_forward(x, ss_t, 8, net.project._temperature, 1, 1e-2, 1.0)[-1].clone()
     assert torch.equal(a, c) and int(sb.ops._ticket(x.device)) == 0
+
+
+def test_rec_continued_fps_matches_reference_semantics(sb, oracle):
+    """reconstruction's inference matching `simple_projection_and_continued_fps` (samplenet_pointnet_ae.py:494-549): restated in numpy
+    line by line below (float64 distances, first-maximum arg-max, order-preserving unique) and compared exactly."""
+    r = _rng(77)
+    B, N, k = 5, 2048, 64
+    pc = r.random((B, N, 3)).astype(np.float32)
+    gen = (pc[:, r.permutation(N)[:k]] + 0.05 * r.standard_normal((B, k, 3))).astype(np.float32)
+    _, idx1, _, _ = sb.ops.nn_distance_forward(_t(gen), _t(pc))
+    idx = _n(idx1)
+    idx[:, 5] = idx[:, 3]; idx[:, 17] = idx[:, 0]            # force duplicates
+    out_pc, out_idx, nu = sb.sputils.simple_projection_and_continued_fps(_t(pc), _t(gen), _t(idx, torch.int32))
+
+    def calc(p0, pts):
+        return ((p0 - pts) ** 2).sum(axis=1)
+
+    for ii in range(B):
+        _, first = np.unique(idx[ii], return_index=True)
+        best = idx[ii][np.sort(first)]
+        t = best.size
+        far = np.zeros((k, 3)); sel = np.zeros(k, dtype=int)
+        far[:t] = pc[ii][best]; sel[:t] = best
+        d = calc(far[0], pc[ii].astype(np.float64))
+        for i in range(1, t):
+            d = np.minimum(d, calc(far[i], pc[ii].astype(np.float64)))
+        for i in range(t, k):
+            sel[i] = np.argmax(d); far[i] = pc[ii][sel[i]]
+            d = np.minimum(d, calc(far[i], pc[ii].astype(np.float64)))
+        assert int(nu[ii]) == t
+        assert np.array_equal(_n(out_idx[ii]), sel)
+        assert np.array_equal(_n(out_pc[ii]), far.astype(np.float32))

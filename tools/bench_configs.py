@@ -141,8 +141,19 @@ def cfg_progressive(dev):
                 tot = tot + tf_ops.get_simplification_loss(x, simp[:, :s].contiguous(), s)
             return proj, tot
         us = graph_us(fwd, reps=3, replays=10)
-    emit({"config": "progressive SampleNet fwd(train)+soft-proj(1024 queries, k=7)+simplification loss over prefixes 8..1024, B=32, N=1024->1024",
+    emit({"config": "progressive SampleNet fwd(train)+soft-proj(1024 queries, k=7)+simplification loss over prefixes 8..1024, B=32, N=1024->1024, one Chamfer launch per prefix",
           "us_per_step": us, "clouds_per_s": B / (us * 1e-6), "prefix_sizes": sizes})
+    from samplenet_b200 import trainers
+    with torch.no_grad():
+        def fwd1():
+            simp, proj = net(x)
+            return proj, trainers.progressive_simplification_loss(x, simp, sizes)
+        us1 = graph_us(fwd1, reps=3, replays=10)
+        simp, _ = net(x)
+        us_loss8 = graph_us(lambda: trainers.progressive_simplification_loss(x, simp, sizes, one_pass=False), reps=5, replays=10)
+        us_loss1 = graph_us(lambda: trainers.progressive_simplification_loss(x, simp, sizes, one_pass=True), reps=5, replays=10)
+    emit({"config": "progressive SampleNet fwd(train)+soft-proj(1024 queries, k=7)+ONE-PASS prefix loss (csrc/progressive.cu), B=32, N=1024->1024",
+          "us_per_step": us1, "clouds_per_s": B / (us1 * 1e-6), "prefix_sizes": sizes, "loss_only_us_one_pass": us_loss1, "loss_only_us_per_prefix_launches": us_loss8})
 
 
 def cfg_train(dev, rank, world):
@@ -207,7 +218,94 @@ def cfg_train(dev, rank, world):
     if rank == 0:
         emit({"config": "training step: SampleNet fwd + simplification/projection loss + backward + flat-bucket all-reduce (%d B) + Adam, 32 clouds/GPU, eager" % ddp.bucket_bytes(),
               "n_gpus": world, "ms_per_step": ms / steps, "clouds_per_s": world * B * steps / (ms * 1e-3),
-              "note": "generator backward recomputes through torch ops (cuBLAS, TF32 off); Chamfer / projection backward are this library's deterministic kernels; host-launch-bound"})
+              "note": "generator, Chamfer and projection backward are this library's kernels (csrc/generator_bwd.cu); eager launches, host-launch-bound"})
+
+
+def cfg_task_steps(dev):
+    """configs[1..3] END TO END with their (frozen) task networks: whole training steps -- sampler forward, task network forward, all losses,
+    backward into the sampler, Adam -- eager, as the reference trainers run them (samplenet_b200.trainers / .registration / .tasknets)."""
+    from samplenet_b200 import trainers, tasknets
+
+    def run(name, B, loss_fn, params, reps=20):
+        opt = torch.optim.Adam(params, lr=1e-3)
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn()
+            loss.backward()
+            opt.step()
+            return loss
+        us = time_us(one, reps=reps, warm=5)
+        emit({"config": name, "ms_per_step": us / 1e3, "clouds_per_s": B / (us * 1e-6), "loss": float(one())})
+
+    torch.manual_seed(0)
+    # classification: N=1024 -> 32, k=7, frozen PointNet classifier
+    B, N, M = 32, 1024, 32
+    net = sb.SampleNet(M, 128, group_size=7, input_shape="bnc", output_shape="bnc").to(dev).train()
+    cls = tasknets.PointNetCls().to(dev)
+    step = trainers.ClassificationStep(net, cls, M)
+    x = clouds(B, N, 11, dev); y = torch.randint(0, 40, (B,), device=dev)
+    run("cls training step end to end: SampleNet(1024->32,k=7) + frozen PointNet classifier, loss_cls + 30*simplification + projection, backward, Adam; B=32",
+        B, lambda: step.loss(x, y)[0], [p for p in net.parameters() if p.requires_grad])
+    # progressive classification: one generator pass, 8 prefixes
+    Mp = 1024
+    netp = sb.SampleNet(Mp, 128, group_size=7, input_shape="bnc", output_shape="bnc").to(dev).train()
+    stepp = trainers.ProgressiveClassificationStep(netp, cls, 8, Mp)
+    run("progressive cls training step end to end: SampleNet(1024->1024,k=7), classifier + one-pass prefix loss on 8 prefixes, backward, Adam; B=32",
+        B, lambda: stepp.loss(x, y)[0], [p for p in netp.parameters() if p.requires_grad], reps=10)
+    # reconstruction: N=2048 -> 64, k=16, frozen AE, Chamfer AE loss (EMD variant timed separately at the kernel level)
+    Br, Nr, Mr = 50, 2048, 64
+    netr = sb.SampleNet(Mr, 128, group_size=16, input_shape="bnc", output_shape="bnc").to(dev).train()
+    ae = tasknets.PointNetAE(Nr, 128).to(dev)
+    stepr = trainers.ReconstructionStep(netr, ae, Mr)
+    xr = clouds(Br, Nr, 12, dev)
+    run("rec training step end to end: SampleNet(2048->64,k=16) + frozen PointNet AE, Chamfer AE loss + simplification + projection, backward, Adam; B=50",
+        Br, lambda: stepr.loss(xr)[0], [p for p in netr.parameters() if p.requires_grad], reps=10)
+    stepe = trainers.ReconstructionStep(netr, ae, Mr, ae_loss="emd")
+    run("rec training step end to end with the EMD AE loss (approx_match + match_cost 2048x2048); B=50",
+        Br, lambda: stepe.loss(xr)[0], [p for p in netr.parameters() if p.requires_grad], reps=5)
+
+
+def cfg_registration_ddp(dev, rank, world):
+    """configs[4]: registration PCRNet + SampleNet, batch-sharded over the ranks (32 sample pairs per GPU: global B = 32 x world), the step of
+    registration/main.py:306-362 (train_1) through samplenet_b200.registration.RegistrationStep: two sampler passes (template + source),
+    frozen PCRNet, quaternion + Chamfer task loss, backward into the sampler, ONE flat-bucket NCCL all-reduce, Adam."""
+    from samplenet_b200.registration import RegistrationStep, QuaternionTransform
+
+    B, N = 32, 1024
+    act = RegistrationStep(num_sampled_clouds=2)
+    torch.manual_seed(0)
+    model = act.create_model().to(dev)
+    model.sampler.train()
+    ddp = act.wrap_data_parallel(model)
+    opt = torch.optim.Adam([p for p in model.sampler.parameters() if p.requires_grad], lr=1e-3)
+    g = torch.Generator().manual_seed(100 + rank)
+    p0 = clouds(B, N, 200 + rank, dev)
+    quat = torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=1).to(dev)
+    vec = torch.cat([quat, torch.zeros(B, 3, device=dev)], dim=1)
+    igt = {"vec": vec, "inversion": torch.tensor([False])}
+    p1 = QuaternionTransform(vec).rotate(p0)
+    data = (p0, p1, igt)
+    for _ in range(5):
+        act.train_step(model, data, opt, dev)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 30
+    a.record()
+    for _ in range(steps):
+        loss, rot, _ = act.train_step(model, data, opt, dev)
+    b.record(); b.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        emit({"config": "registration training step (PCRNet frozen + SampleNet, 2 sampled clouds, quaternion + Chamfer task loss), batch-sharded DDP, "
+                        "global B = %d, flat-bucket all-reduce %d B, eager" % (B * world, ddp.bucket_bytes()),
+              "n_gpus": world, "ms_per_step": ms / steps, "sample_pairs_per_s": world * B * steps / (ms * 1e-3), "loss": float(loss)})
 
 
 def main():
@@ -226,8 +324,12 @@ def main():
             cfg_rec(dev)
         if rank == 0 and args.only in ("all", "progressive"):
             cfg_progressive(dev)
+        if rank == 0 and args.only in ("all", "tasks"):
+            cfg_task_steps(dev)
         if args.only in ("all", "train"):
             cfg_train(dev, rank, world)
+        if args.only in ("all", "train", "registration"):
+            cfg_registration_ddp(dev, rank, world)
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()
