@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 for (int jb = 0; jb < kCsNPT / 8; jb++)
                     if (jb * 8 < npt) cs_ld8_issue(tmem_lane + (uint32_t)(col0 + jb * 8), v + jb * 8);
                 cs_ld_wait();
+                cs_fence_before();   // the next layer's first MMA overwrites these columns: ordered through the CTA barrier below
 #pragma unroll
                 for (int j = 0; j < kCsNPT; j++) {
                     if (j < npt) {
@@ -617,6 +618,10 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     cs_grid_arrive(P.barrier);
                     cs_grid_wait(P.barrier, (barrier_epoch + 1) * G);
                 }
+                cs_named_sync(1, kCsProducers);
+            } else if (!last) {
+                // no statistics barrier (eval mode / no BatchNorm): still, every warp must have read its accumulator columns before the
+                // next layer's MMAs (which need only K chunk 0) start overwriting them
                 cs_named_sync(1, kCsProducers);
             }
             CS_TS(3 + (l - 1) * 8 + 6);
