@@ -196,16 +196,6 @@ int snb200_generator_backward(int b, int n, int layout, const float *x, int num_
                               int out_transpose_inner, const snb200_layer_grad *conv_grads, const snb200_layer_grad *fc_grads,
                               void *workspace, size_t workspace_bytes, snb200_stream_t stream);
 
-/* Bring-up / unit-test hook of the tcgen05 layer kernel (csrc/encoder_tc.cu): D (rows, c_out) = A (rows, c_in) * W (c_out, c_in)^T + bias
- * as 3xTF32 on the tensor cores.  desc_hi / k_adv16 / swizzle override the shared-memory descriptor encoding (0,0,0 = defaults);
- * they exist so that one GPU session can sweep encodings.  c_in % 8 == 0, 8 <= c_in, c_out <= 256. */
-int snb200_debug_tc_gemm(int rows, int c_in, int c_out, const float *A, const float *W, const float *bias, float *D,
-                         unsigned desc_hi, int k_adv16, int swizzle, snb200_stream_t stream);
-
-/* Bring-up instrumentation: 64 SM-clock timestamps written by CTA 0 of the last FC-head launch (synchronous copy). */
-int snb200_debug_head_timestamps(long long *host_out64);
-int snb200_debug_conv_stack_timestamps(long long *host_out64);
-
 /* Fully connected head on the pooled feature: in (b, c_in0) -> out (b, c_out_last).  BatchNorm over the batch.
  * out_transpose_inner = M > 0: each output row, logically (c_out_last/M, M) -- the reference's y.view(-1, 3, M),
  * samplenet.py:104 -- is stored transposed as (M, c_out_last/M), i.e. directly in BNC order; 0 = stored as is (BCN). */

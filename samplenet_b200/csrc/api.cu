@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary of libsamplenet_b200.so (see include/samplenet_b200.h).
 // Argument validation + dispatch only; kernels live in chamfer.cu / softproj.cu / encoder.cu / emd.cu / matching.cu.
 #include "common.cuh"
+#include "../../include/samplenet_b200_debug.h"
 #include <string.h>
 
 namespace snb {
