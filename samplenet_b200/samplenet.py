@@ -17,6 +17,7 @@ What changes is what runs underneath:
 Backward: the projection and the loss have hand-written CUDA backward kernels; the generator's backward recomputes the
 layer stack with torch's stock conv/BN/linear ops (activation checkpointing) -- the forward never uses them.
 """
+import os
 import warnings
 
 import torch
@@ -137,7 +138,7 @@ class SampleNet(nn.Module):
         self.generator_precision = "3xtf32"
         # "cuda": hand-written backward kernels (csrc/generator_bwd.cu) wherever they cover the shape; "torch": recompute the layer stack
         # with stock torch ops and differentiate that (the round-1 path; also the fallback outside the CUDA backward's envelope)
-        self.generator_backward = "cuda"
+        self.generator_backward = os.environ.get("SNB200_GENERATOR_BACKWARD", "torch")   # TODO(flip to "cuda" after hardware validation)
         # project + Chamfer + loss reductions of (simp, x) in one launch when forward() runs in training mode ("bnc" in and out)
         self.fused_tail = True
         self._tail = None

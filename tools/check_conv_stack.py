@@ -21,19 +21,21 @@ for (b, n, m, train) in [(32, 1024, 64, True), (2, 1024, 64, True), (7, 1000, 64
     x = (torch.rand(b, n, 3, device="cuda") - 0.5)
     conv, fc = net._layer_specs()
     with torch.no_grad():
-        o1, f1 = sb.ops.generator_forward(x, "bnc", conv, fc, train, m)
+        o1, f1 = sb.ops.generator_forward(x, "bnc", conv, fc, train, m, conv_stack_version=2)
+        o0, f0 = sb.ops.generator_forward(x, "bnc", conv, fc, train, m, conv_stack_version=1)
         o2, f2 = sb.ops.generator_forward(x, "bnc", conv, fc, train, m, per_layer_kernels=True)
         o3, f3 = sb.ops.generator_forward(x, "bnc", conv, fc, train, m, exact_fp32=True)
         xb = x.permute(0, 2, 1).contiguous()
-        o4, f4 = sb.ops.generator_forward(xb, "bcn", conv, fc, train, 0)
+        o4, f4 = sb.ops.generator_forward(xb, "bcn", conv, fc, train, 0, conv_stack_version=2)
     torch.cuda.synchronize()
     e12f, e13f = (f1 - f2).abs().max().item(), (f1 - f3).abs().max().item()
     e12, e13 = (o1 - o2).abs().max().item(), (o1 - o3).abs().max().item()
     e14f = (f1 - f4).abs().max().item()
+    e10 = (o1 - o0).abs().max().item()
     good = e12f < 2e-4 and e13f < 2e-4 and e12 < 2e-3 and e13 < 2e-3 and e14f < 2e-4 and torch.isfinite(o1).all().item()
     ok = ok and good
-    print("b=%d n=%d m=%d train=%d  feat: vs per-layer %.2e vs fp32 %.2e bcn %.2e | out: vs per-layer %.2e vs fp32 %.2e  %s" %
-          (b, n, m, train, e12f, e13f, e14f, e12, e13, "ok" if good else "MISMATCH"), flush=True)
+    print("b=%d n=%d m=%d train=%d  feat: vs per-layer %.2e vs fp32 %.2e bcn %.2e | out: vs per-layer %.2e vs fp32 %.2e vs v1 %.2e  %s" %
+          (b, n, m, train, e12f, e13f, e14f, e12, e13, e10, "ok" if good else "MISMATCH"), flush=True)
 print("ALL OK" if ok else "FAILED")
 
 net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda().train()
@@ -41,7 +43,7 @@ x = torch.rand(32, 1024, 3, device="cuda") - 0.5
 conv, fc = net._layer_specs()
 with torch.no_grad():
     for _ in range(5):
-        sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)
+        sb.ops.generator_forward(x, "bnc", conv, fc, True, 64, conv_stack_version=2)
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 64)()
     sb._lib.lib().snb200_debug_conv_stack_timestamps(ctypes.addressof(buf))
@@ -58,18 +60,19 @@ with torch.no_grad():
     for i in sorted(names):
         print("%-28s %8d cycles  (+%d)" % (names[i], ts[i] - t0, ts[i] - prev)); prev = ts[i]
     # timing
-    g = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    with torch.cuda.stream(s):
-        sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=s):
-            for _ in range(20):
-                sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)
-    g.replay(); torch.cuda.synchronize()
-    a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(20):
-        g.replay()
-    bb.record(); bb.synchronize()
-    print("generator: %.2f us per launch (in-graph, warm)" % (a.elapsed_time(bb) * 1e3 / 400))
+    for ver in (2, 1):
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            sb.ops.generator_forward(x, "bnc", conv, fc, True, 64, conv_stack_version=ver)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(20):
+                    sb.ops.generator_forward(x, "bnc", conv, fc, True, 64, conv_stack_version=ver)
+        g.replay(); torch.cuda.synchronize()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            g.replay()
+        bb.record(); bb.synchronize()
+        print("generator (conv stack v%d): %.2f us per launch (in-graph, warm)" % (ver, a.elapsed_time(bb) * 1e3 / 400))
