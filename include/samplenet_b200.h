@@ -34,7 +34,7 @@ extern "C" {
 #define SNB200_BCN 1
 
 /* flags for the distance kernels */
-#define SNB200_DIST_FMA 0      /* d = fma(dz,dz,fma(dy,dy,dx*dx)): the arithmetic nvcc gives the reference CUDA kernels */
+#define SNB200_DIST_FMA 0      /* d = fma(dz,dz,fma(dx,dx,dy*dy)): the arithmetic nvcc gives the reference CUDA kernels (bit-identical results) */
 #define SNB200_DIST_UNFUSED 1  /* d = (dx*dx+dy*dy)+dz*dz, three roundings: the arithmetic of the reference CPU code */
 
 /* how the `sigma` device scalar of the projection entry points is interpreted (sigma_mode); `sigma_floor` is the clamp:

@@ -15,6 +15,8 @@
 namespace snb {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kStatStride = 16;     // doubles between two BatchNorm statistics accumulators of the conv-stack kernel: one per 128-byte line, so that the
+                                   // 148 CTAs' fp64 atomics on different channels do not serialise in the same L2 line
 
 // ------------------------------------------------------------------------------------------- host side
 void set_error(const char *fmt, ...);
@@ -64,7 +66,9 @@ template <bool kFma>
 __device__ __forceinline__ float sqdist(float dx, float dy, float dz)
 {
     if (kFma) {
-        return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        // the contraction nvcc applies to (dx*dx + dy*dy) + dz*dz in the reference kernels (chamfer_distance.cu:33-36, tf_nndistance_g.cu:25-28;
+        // SASS: FMUL dy*dy, FFMA dx*dx + ., FFMA dz*dz + .): results are bit-identical to the reference's own CUDA ops
+        return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
     } else {
         return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     }

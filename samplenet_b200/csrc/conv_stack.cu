@@ -25,6 +25,7 @@
 #include "encoder_internal.cuh"
 #include <cooperative_groups.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace snb {
 
@@ -37,7 +38,9 @@ constexpr int kCsMinPts = 64;
 constexpr int kCsNPT = kCsMaxPts / 4; // points per thread (register array)
 constexpr int kCsRing = 3;            // ring slots of one 32-wide K chunk (hi + lo)
 constexpr int kCsMaxSeg = 8;          // clouds a CTA's point range may touch
-constexpr uint32_t kCsColWhi = 256, kCsColWlo = 384;   // tensor-memory columns of the weight operand (D occupies 0..255)
+constexpr uint32_t kCsColWhi = 256, kCsColWlo = 384;
+constexpr int kCsLoPlane = kCsMaxPts * 128;          // a ring slot = hi plane (kCsMaxPts rows x 128 B) + lo plane, fixed size
+constexpr uint32_t kCsSlotBytes = 2u * kCsLoPlane;   // tensor-memory columns of the weight operand (D occupies 0..255)
 
 struct CsLayer {
     int c_in, c_out;
@@ -69,6 +72,7 @@ struct CsParams {
     int self_clean;
     char *clean_ptr;
     unsigned clean_bytes;
+    int dbg;                            // bring-up switches (env SNB200_CS_DEBUG; 0 in the product): 1 = skip the statistics atomics (timing experiments only)
 };
 
 // ---- tcgen05 helpers (same encodings as encoder_tc.cu, validated against fp64 in tests/test_gpu_parity.py::test_tc_gemm_3xtf32)
@@ -203,6 +207,12 @@ __device__ __forceinline__ void cs_head_stage_weights(const HeadLayer &L, int cb
 }
 
 
+// (sum, sumsq) accumulator idx of a layer: the dense [2C] block, or (spread != 0) the padded accumulators behind it
+__device__ __forceinline__ double cs_stat(const double *base, int c2, int idx, int spread)
+{
+    return __ldcg(spread ? base + c2 + (size_t)idx * kStatStride : base + idx);
+}
+
 // A-from-TMEM form: D[tmem] (+)= A[tmem, 128 lanes x 8 columns] . B[smem descriptor]
 __device__ __forceinline__ void cs_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -267,21 +277,50 @@ __device__ __forceinline__ void cs_store_w(uint32_t tmem_lane_base, int g, int K
     cs_st_wait();
 }
 
-// (B) of the layer loop: this thread's channel = column k of the B operand: normalise, split and store its npt points into ring slot `slot`
-__device__ __forceinline__ void cs_write_chunk(const uint32_t (&v)[kCsNPT], float sc, float sh, bool relu, int npt, int nvalid, unsigned char *hi_base,
-                                               unsigned char *lo_base, const uint32_t (&swz)[8])
+// (B) of the layer loop: this thread's channel = column k of the B operand: normalise, split and store its npt points into a ring slot.
+// adr[i] = shared-space address of (row col0 + i, this thread's swizzled 4-byte cell) of the slot's hi plane; row col0 + 8 jb + i lies
+// jb * 1024 bytes further (same swizzle phase: col0 and 8 jb are multiples of 8) and the lo plane kCsLoPlane bytes further: every store
+// is [register + immediate].  One warp-uniform branch per 8 points; columns beyond the CTA's last point carry don't-care values (each
+// accumulator column depends on its own operand row only, and those columns are excluded from every statistic).
+template <int JB>
+__device__ __forceinline__ void cs_write_block(const uint32_t (&v)[kCsNPT], float sc, float sh, float floor_v, const uint32_t (&adr)[8])
 {
 #pragma unroll
-    for (int j = 0; j < kCsNPT; j++) {
-        if (j < npt) {
-            float t = fmaf(__uint_as_float(v[j]), sc, sh);
-            if (relu) t = fmaxf(t, 0.f);
-            if (j >= nvalid) t = 0.f;
-            const float h = __uint_as_float(__float_as_uint(t) & 0xffffe000u);
-            const uint32_t off = (uint32_t)j * 128u + swz[j & 7];
-            *reinterpret_cast<float *>(hi_base + off) = h;
-            *reinterpret_cast<float *>(lo_base + off) = t - h;
+    for (int i = 0; i < 8; i++) {
+        const float t = fmaxf(fmaf(__uint_as_float(v[JB * 8 + i]), sc, sh), floor_v);   // floor_v = 0 (ReLU) or -inf
+        const float h = __uint_as_float(__float_as_uint(t) & 0xffffe000u);
+        asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(adr[i]), "n"(JB * 1024), "f"(h) : "memory");
+        asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(adr[i]), "n"(JB * 1024 + kCsLoPlane), "f"(t - h) : "memory");
+    }
+}
+__device__ __forceinline__ void cs_write_chunk(const uint32_t (&v)[kCsNPT], float sc, float sh, float floor_v, int npt, const uint32_t (&adr)[8])
+{
+    if (0 < npt) cs_write_block<0>(v, sc, sh, floor_v, adr);
+    if (8 < npt) cs_write_block<1>(v, sc, sh, floor_v, adr);
+    if (16 < npt) cs_write_block<2>(v, sc, sh, floor_v, adr);
+    if (24 < npt) cs_write_block<3>(v, sc, sh, floor_v, adr);
+    if (32 < npt) cs_write_block<4>(v, sc, sh, floor_v, adr);
+    if (40 < npt) cs_write_block<5>(v, sc, sh, floor_v, adr);
+    if (48 < npt) cs_write_block<6>(v, sc, sh, floor_v, adr);
+    if (56 < npt) cs_write_block<7>(v, sc, sh, floor_v, adr);
+}
+
+// raw outputs of this thread's channel at its points -> global (points x channels): lanes = 32 consecutive channels of one point = 128
+// contiguous bytes per warp store
+__device__ __forceinline__ void cs_save_rows(float *dst, int ld, const uint32_t (&v)[kCsNPT], int npt, int nvalid)
+{
+    if (nvalid == npt) {
+#pragma unroll
+        for (int jb = 0; jb < kCsNPT / 8; jb++) {
+            if (jb * 8 < npt) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) dst[(size_t)(jb * 8 + i) * ld] = __uint_as_float(v[jb * 8 + i]);
+            }
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kCsNPT; j++)
+            if (j < nvalid) dst[(size_t)j * ld] = __uint_as_float(v[j]);
     }
 }
 
@@ -294,7 +333,7 @@ __device__ __forceinline__ void cs_issue_chunk(unsigned char *smem_raw, uint32_t
     cs_fence_after();
     if (lane == 0) {
         const uint32_t sb = smem_u32(smem_raw) + slot * slot_bytes;
-        const uint64_t b_hi = cs_sdesc(sb), b_lo = cs_sdesc(sb + (uint32_t)ppc * 128u);
+        const uint64_t b_hi = cs_sdesc(sb), b_lo = cs_sdesc(sb + (uint32_t)kCsLoPlane);
         const uint32_t a_hi = tmem0 + kCsColWhi + (uint32_t)(c * 32), a_lo = tmem0 + kCsColWlo + (uint32_t)(c * 32);
 #pragma unroll
         for (int ks = 0; ks < 4; ks++) {   // K = 8 tf32 per step: +8 TMEM columns (A), +32 bytes = +2 in the 16-byte address field (B)
@@ -340,7 +379,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     const int npts = (int)min((long long)ppc, P.total - P0);
     const int col0 = g * npt;                           // first accumulator column of this thread
     const int nvalid = max(0, min(npt, npts - col0));   // its columns [0, nvalid) are real points
-    const uint32_t slot_bytes = (uint32_t)ppc * 256u;
+    const uint32_t slot_bytes = kCsSlotBytes;
 
     CS_TS(0);
     if (warp == 0) cs_tmem_alloc(&tmem_base_smem, 512);
@@ -435,25 +474,22 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         const bool cv = ch < L1.c_out;
         const float w0 = cv ? sW1[ch * 3 + 0] : 0.f, w1 = cv ? sW1[ch * 3 + 1] : 0.f, w2 = cv ? sW1[ch * 3 + 2] : 0.f, b1 = cv ? sB1[ch] : 0.f;
 #pragma unroll
-        for (int j = 0; j < kCsNPT; j++) {
-            if (j < npt) {
-                const float *xr = sX + (col0 + j) * 3;
-                v[j] = __float_as_uint(fmaf(w2, xr[2], fmaf(w1, xr[1], w0 * xr[0])) + b1);
+        for (int jb = 0; jb < kCsNPT / 8; jb++) {
+            if (jb * 8 < npt) {
+                const float *xr = sX + (col0 + jb * 8) * 3;
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[jb * 8 + i] = __float_as_uint(fmaf(w2, xr[i * 3 + 2], fmaf(w1, xr[i * 3 + 1], w0 * xr[i * 3 + 0])) + b1);
             }
         }
-        if (L1.zsave && cv) {   // a warp stores 32 consecutive channels of one point: 128 contiguous bytes
-            float *zs = L1.zsave + (size_t)(P0 + col0) * L1.c_out + ch;
-#pragma unroll
-            for (int j = 0; j < kCsNPT; j++)
-                if (j < nvalid) zs[(size_t)j * L1.c_out] = __uint_as_float(v[j]);
-        }
+        if (L1.zsave && cv) cs_save_rows(L1.zsave + (size_t)(P0 + col0) * L1.c_out + ch, L1.c_out, v, npt, nvalid);
     }
 
     uint32_t gchunk = 0;                // global K-chunk counter (same sequence in producers and issuer): slot = gchunk % kCsRing
-    // swizzle: point p's 128-byte row holds its 16-byte group c at position c ^ (p & 7); col0 is a multiple of 8, so p & 7 = j & 7
-    uint32_t swz[8];
+    // swizzle: point p's 128-byte row holds its 16-byte group c at position c ^ (p & 7); col0 is a multiple of 8, so p & 7 = j & 7.
+    // toff[i]: byte offset inside a ring slot's hi plane of (row col0 + i, this thread's k = lane)
+    uint32_t toff[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) swz[i] = (uint32_t)(((lane >> 2) ^ i) << 4) + (uint32_t)((lane & 3) << 2);
+    for (int i = 0; i < 8; i++) toff[i] = (uint32_t)(col0 + i) * 128u + (uint32_t)(((lane >> 2) ^ i) << 4) + (uint32_t)((lane & 3) << 2);
 
     for (int l = 1; l < P.num_layers; l++) {
         const CsLayer &Lp = P.L[l - 1];   // producer of this layer's input (its BN+ReLU is applied when the registers are stored)
@@ -468,7 +504,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             CS_TS(3 + (l - 1) * 8 + 0);
             // (A) BatchNorm (+ReLU) of the producer layer for this thread's channel: two registers
             float sc = 1.f, sh = 0.f;
-            if (Lp.has_bn && ch < K) {
+            if (Lp.has_bn && ch < K && g == 0) {   // one column group reads the statistics (hot L2 lines) and shares the result
+
                 float mean, var;
                 if (P.training) {
                     double m, vv;
@@ -480,13 +517,15 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         m = a0 * mx + a1 * my + a2 * mz + (double)sB1[ch];
                         vv = a0 * a0 * cxx + a1 * a1 * cyy + a2 * a2 * czz + 2.0 * (a0 * a1 * cxy + a0 * a2 * cxz + a1 * a2 * cyz);
                         if (vv < 0) vv = 0;
-                        if (blockIdx.x == 0 && g == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
+                        if (blockIdx.x == 0) {   // the (sum, sumsq) form every consumer of the statistics uses
                             Lp.stats[ch] = cnt * m;
                             Lp.stats[K + ch] = cnt * (vv + m * m);
                         }
                     } else {
-                        m = __ldcg(Lp.stats + ch) * inv_cnt;
-                        vv = __ldcg(Lp.stats + K + ch) * inv_cnt - m * m;
+                        const double s1 = cs_stat(Lp.stats, 2 * K, ch, 1), s2 = cs_stat(Lp.stats, 2 * K, K + ch, 1);
+                        if (blockIdx.x == 0) { Lp.stats[ch] = s1; Lp.stats[K + ch] = s2; }   // the canonical block (head, backward pass)
+                        m = s1 * inv_cnt;
+                        vv = s2 * inv_cnt - m * m;
                         if (vv < 0) vv = 0;
                     }
                     mean = (float)m; var = (float)vv;
@@ -496,6 +535,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 const float invstd = 1.0f / sqrtf(var + Lp.eps);
                 sc = Lp.gamma[ch] * invstd;
                 sh = Lp.beta[ch] - mean * sc;
+            }
+            if (Lp.has_bn) {
+                if (g == 0 && ch < K) { sRedS[0][ch] = sc; sRedQ[0][ch] = sh; }   // (the partial-sum arrays are free between the layers)
+                cs_named_sync(1, kCsProducers);
+                if (ch < K) { sc = sRedS[0][ch]; sh = sRedQ[0][ch]; }
+                cs_named_sync(1, kCsProducers);   // ... and must not be overwritten by this layer's partial sums before everybody has read them
             }
             CS_TS(3 + (l - 1) * 8 + 1);
             // (B) MMA issue (warp kCsIssuerWarp, chunks in order) around the operand preparation (every warp that owns a K chunk)
@@ -512,8 +557,11 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     cs_mbar_wait(&bar_ring[slot], (use - 1) & 1u);
                     cs_fence_after();
                 }
-                unsigned char *hi_base = smem_raw + slot * slot_bytes + (uint32_t)col0 * 128u;
-                cs_write_chunk(v, sc, sh, Lp.relu != 0, npt, nvalid, hi_base, hi_base + (uint32_t)ppc * 128u, swz);
+                uint32_t adr[8];
+                const uint32_t sbase = smem_u32(smem_raw) + slot * slot_bytes;
+#pragma unroll
+                for (int i = 0; i < 8; i++) adr[i] = sbase + toff[i];
+                cs_write_chunk(v, sc, sh, Lp.relu ? 0.f : -INFINITY, npt, adr);
                 cs_fence_before();     // this thread's tcgen05.ld of the previous accumulator are complete (wait::ld) and ordered
                 fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
                 cs_mbar_arrive(&bar_full[slot]);
@@ -535,59 +583,81 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 cs_mbar_arrive(&bar_w);
             }
             // (F) the accumulator: lane = channel, this thread's npt columns -> registers (+bias); statistics / extrema on the way
-            float sum = 0.f, sq = 0.f;
+            const int cl_first = (int)(P0 / n);
+            const int nseg = (int)((P0 + npts - 1) / n) - cl_first + 1;
+            float *sPmax = reinterpret_cast<float *>(smem_raw);                       // [4 groups][kCsMaxSeg][128]
+            float *sPmin = sPmax + 4 * kCsMaxSeg * 128;
             if (q * 32 < N) {
 #pragma unroll
                 for (int jb = 0; jb < kCsNPT / 8; jb++)
                     if (jb * 8 < npt) cs_ld8_issue(tmem_lane + (uint32_t)(col0 + jb * 8), v + jb * 8);
                 cs_ld_wait();
                 cs_fence_before();   // the next layer's first MMA overwrites these columns: ordered through the CTA barrier below
+                float sum = 0.f, sq = 0.f;
+                if (nvalid == npt) {   // (every CTA but the last: all columns are real points)
 #pragma unroll
-                for (int j = 0; j < kCsNPT; j++) {
-                    if (j < npt) {
+                    for (int jb = 0; jb < kCsNPT / 8; jb++) {
+                        if (jb * 8 < npt) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const float u = __uint_as_float(v[jb * 8 + i]) + bias;
+                                v[jb * 8 + i] = __float_as_uint(u);
+                                sum += u; sq = fmaf(u, u, sq);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kCsNPT; j++) {
                         const float u = __uint_as_float(v[j]) + bias;
                         v[j] = __float_as_uint(u);
-                        if (j < nvalid) { sum += u; sq = fmaf(u, u, sq); }
+                        const float uu = j < nvalid ? u : 0.f;
+                        sum += uu; sq = fmaf(uu, uu, sq);
                     }
                 }
                 if (want_stats) { sRedS[g][ch] = sum; sRedQ[g][ch] = sq; }
-                if (Lc.zsave && ch < N) {   // training with gradients: the raw outputs go to HBM / L2 as well (coalesced 128-byte rows)
-                    float *zs = Lc.zsave + (size_t)(P0 + col0) * N + ch;
+                // training with gradients: the raw outputs go to HBM / L2 as well (a warp stores 32 consecutive channels of a point)
+                if (Lc.zsave && ch < N) cs_save_rows(Lc.zsave + (size_t)(P0 + col0) * N + ch, N, v, npt, nvalid);
+                if (last) {   // per-cloud extrema of this thread's columns (the ring is dead: every MMA has completed)
+                    for (int sgi = 0; sgi < nseg; sgi++) { sPmax[(g * kCsMaxSeg + sgi) * 128 + ch] = -INFINITY; sPmin[(g * kCsMaxSeg + sgi) * 128 + ch] = INFINITY; }
+                    const long long gp0 = P0 + col0;
+                    const int cl = (int)(gp0 / n);
+                    const int first_nb = (int)((long long)(cl + 1) * n - gp0);   // column at which the next cloud starts
+                    if (nvalid == npt && first_nb >= npt) {   // the common case: all of this thread's columns belong to one cloud
+                        float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
-                    for (int j = 0; j < kCsNPT; j++)
-                        if (j < nvalid) zs[(size_t)j * N] = __uint_as_float(v[j]);
-                }
-            }
-            float *sPmax = reinterpret_cast<float *>(smem_raw);                       // [4 groups][kCsMaxSeg][128]
-            float *sPmin = sPmax + 4 * kCsMaxSeg * 128;
-            const int cl_first = (int)(P0 / n);
-            const int nseg = (int)((P0 + npts - 1) / n) - cl_first + 1;
-            if (last && q * 32 < N) {   // per-cloud extrema of this thread's columns (the ring is dead: every MMA has completed)
-                for (int s = 0; s < nseg; s++) { sPmax[(g * kCsMaxSeg + s) * 128 + ch] = -INFINITY; sPmin[(g * kCsMaxSeg + s) * 128 + ch] = INFINITY; }
-                const long long gp0 = P0 + col0;
-                const int cl = (int)(gp0 / n);
-                int seg = cl - cl_first;
-                int nb = (int)((long long)(cl + 1) * n - gp0);   // column at which the next cloud starts
-                float mx = -INFINITY, mn = INFINITY;
+                        for (int jb = 0; jb < kCsNPT / 8; jb++) {
+                            if (jb * 8 < npt) {
 #pragma unroll
-                for (int j = 0; j < kCsNPT; j++) {
-                    if (j < nvalid) {
-                        if (j == nb) {
-                            sPmax[(g * kCsMaxSeg + seg) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + seg) * 128 + ch] = mn;
-                            seg++; nb += n; mx = -INFINITY; mn = INFINITY;
+                                for (int i = 0; i < 8; i++) { mx = fmaxf(mx, __uint_as_float(v[jb * 8 + i])); mn = fminf(mn, __uint_as_float(v[jb * 8 + i])); }
+                            }
                         }
-                        mx = fmaxf(mx, __uint_as_float(v[j])); mn = fminf(mn, __uint_as_float(v[j]));
+                        sPmax[(g * kCsMaxSeg + cl - cl_first) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + cl - cl_first) * 128 + ch] = mn;
+                    } else {   // columns straddle cloud boundaries (or the batch ends inside them): one masked pass per cloud segment
+                        int jlo = 0;
+                        for (int c2 = cl; jlo < nvalid; c2++) {
+                            const int jhi = min(nvalid, (int)((long long)(c2 + 1) * n - gp0));
+                            float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+                            for (int j = 0; j < kCsNPT; j++) {
+                                const bool in = j >= jlo && j < jhi;
+                                mx = in ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+                                mn = in ? fminf(mn, __uint_as_float(v[j])) : mn;
+                            }
+                            sPmax[(g * kCsMaxSeg + c2 - cl_first) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + c2 - cl_first) * 128 + ch] = mn;
+                            jlo = jhi;
+                        }
                     }
                 }
-                if (nvalid > 0 && seg < nseg) { sPmax[(g * kCsMaxSeg + seg) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + seg) * 128 + ch] = mn; }
             }
             CS_TS(3 + (l - 1) * 8 + 4);
             if (want_stats || last) cs_named_sync(1, kCsProducers);
-            if (want_stats && g == 0 && ch < N) {
+            if (want_stats && g == 0 && ch < N && !(P.dbg & 1)) {
                 const float sm = (sRedS[0][ch] + sRedS[1][ch]) + (sRedS[2][ch] + sRedS[3][ch]);
                 const float sqq = (sRedQ[0][ch] + sRedQ[1][ch]) + (sRedQ[2][ch] + sRedQ[3][ch]);
-                atomicAdd(Lc.stats + ch, (double)sm);
-                atomicAdd(Lc.stats + N + ch, (double)sqq);
+                double *acc = Lc.stats + 2 * N;   // padded accumulators: one 128-byte line each
+                atomicAdd(acc + (size_t)ch * kStatStride, (double)sm);
+                atomicAdd(acc + (size_t)(N + ch) * kStatStride, (double)sqq);
             }
             if (last) {   // (cloud, slot) partial extrema; slot = this CTA's rank among the CTAs that touch the cloud
                 const int S = P.slots_per_cloud;
@@ -616,6 +686,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 cs_named_sync(1, kCsProducers);
                 if (tid == 0) {
                     cs_grid_arrive(P.barrier);
+                    CS_TS(3 + (l - 1) * 8 + 7);
                     cs_grid_wait(P.barrier, (barrier_epoch + 1) * G);
                 }
                 cs_named_sync(1, kCsProducers);
@@ -629,10 +700,9 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         if (want_stats) barrier_epoch++;
     }
 
-    // every commit has been observed through bar_acc; release tensor memory
+    // every commit has been observed through bar_acc; tensor memory is released at the end of the kernel (off the head's critical path)
     cs_fence_before();
     __syncthreads();
-    if (warp == 0) cs_tmem_dealloc(tmem0, 512);
 
     // ================================================================================================================
     // Fused tail: max-pool finalise + FC head (samplenet.py:97-104) on the CTAs of the grid.  Each FC layer's output channels
@@ -643,7 +713,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // Programmatic dependent launch: a kernel queued behind this one with the PDL attribute (the fused tail) may be scheduled onto
     // SMs as this grid's CTAs exit; it synchronises on this grid's completion itself (griddepcontrol.wait) before touching our output.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (!P.fuse_head) return;
+    if (!P.fuse_head) {   // stand-alone conv stack: the consumers (cluster head kernel, backward pass) read the canonical statistics block
+        const CsLayer &LL = P.L[P.num_layers - 1];
+        if (blockIdx.x == 0 && need_stats && LL.has_bn && tid < 2 * LL.c_out) LL.stats[tid] = cs_stat(LL.stats, 2 * LL.c_out, tid, 1);
+        if (warp == 0) cs_tmem_dealloc(tmem0, 512);
+        return;
+    }
     const HeadParams &H = P.H;
     // shared memory of the head (the conv stack's buffers are dead): input row group | partial sums | first weight rows of every layer
     float *s_in = reinterpret_cast<float *>(smem_raw);                 // [32 rows][c_in + 1] one row group of the input
@@ -695,8 +770,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             const float *tm = H.tile_max + (size_t)bi * H.tiles_per_cloud * H.c_feat + c;
             const float *tn = H.tile_min + (size_t)bi * H.tiles_per_cloud * H.c_feat + c;
             // every load of this element is issued before the first use
-            const double st0 = (H.last_has_bn && H.training) ? __ldcg(H.last_stats + c) : 0.0;
-            const double st1 = (H.last_has_bn && H.training) ? __ldcg(H.last_stats + H.c_feat + c) : 0.0;
+            const double st0 = (H.last_has_bn && H.training) ? cs_stat(H.last_stats, 2 * H.c_feat, c, H.stat_rep) : 0.0;
+            const double st1 = (H.last_has_bn && H.training) ? cs_stat(H.last_stats, 2 * H.c_feat, H.c_feat + c, H.stat_rep) : 0.0;
+            if (H.stat_rep && bi == 0 && H.last_has_bn && H.training) {   // canonical block of the last layer (read by the backward pass)
+                double *canon = const_cast<double *>(H.last_stats);
+                canon[c] = st0; canon[H.c_feat + c] = st1;
+            }
             const float lg = H.last_has_bn ? __ldg(H.last_gamma + c) : 1.f, lb = H.last_has_bn ? __ldg(H.last_beta + c) : 0.f;
 #pragma unroll 8
             for (int t = 0; t < H.tiles_per_cloud; t++) {
@@ -920,8 +999,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         for (int l = 0; l < H.ru_num; l++) {
             for (int c = gt - base; c < H.ru_c[l]; c += gn) {
                 if (c < 0) continue;
-                const double m = __ldcg(H.ru_stats[l] + c) * inv_cnt_h;
-                double v = __ldcg(H.ru_stats[l] + H.ru_c[l] + c) * inv_cnt_h - m * m;
+                const double m = cs_stat(H.ru_stats[l], 2 * H.ru_c[l], c, H.ru_rep[l]) * inv_cnt_h;
+                double v = cs_stat(H.ru_stats[l], 2 * H.ru_c[l], H.ru_c[l] + c, H.ru_rep[l]) * inv_cnt_h - m * m;
                 if (v < 0) v = 0;
                 const double unb = H.count > 1 ? v * (H.count / (H.count - 1)) : v;
                 const float mom = H.ru_momentum[l];
@@ -931,6 +1010,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             base = (base + H.ru_c[l]) % gn;
         }
     }
+    if (warp == 0) cs_tmem_dealloc(tmem0, 512);
     if (P.self_clean) {   // the last CTA to leave puts the moments, the barrier word and the exit word back to zero for the next launch
         __syncthreads();
         if (tid == 0) {
@@ -1015,9 +1095,14 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
         D.eps = conv[l].bn_eps; D.has_bn = conv[l].bn_weight != nullptr; D.relu = conv[l].relu; D.stats = stats[l];
         D.zsave = zsave ? zsave[l] : nullptr;
     }
+    { const char *e = getenv("SNB200_CS_DEBUG"); P.dbg = e ? atoi(e) : 0; }
     if (tiles_per_cloud_out) *tiles_per_cloud_out = P.slots_per_cloud;
-    if (head) P.H.tiles_per_cloud = P.slots_per_cloud;
-    size_t smem = (size_t)kCsRing * P.ppc * 256 + 1024;
+    if (head) {
+        P.H.tiles_per_cloud = P.slots_per_cloud;
+        P.H.stat_rep = 1;
+        for (int i = 0; i < P.H.ru_num; i++) P.H.ru_rep[i] = (P.H.ru_stats[i] == stats[0]) ? 0 : 1;   // layer 1's statistics are analytic (canonical only)
+    }
+    size_t smem = (size_t)kCsRing * kCsSlotBytes + 1024;
     if (head) {   // the fused tail reuses the same dynamic shared memory: input tile + partial sums + 8 weight rows
         int hcmax = head->c_feat;
         for (int l = 0; l < head->num_fc; l++) hcmax = max(hcmax, head->fc[l].c_in);

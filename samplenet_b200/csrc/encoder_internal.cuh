@@ -51,6 +51,8 @@ struct HeadParams {
     int c_feat, tiles_per_cloud;
     const float *tile_max, *tile_min;
     const double *last_stats;
+    int stat_rep;                // 0: (sum, sumsq) of every conv layer are the plain [2][C] block; 1: the accumulators the conv-stack kernel adds into
+                                 // are spread one per 128-byte line behind that block: accumulator idx at stats[2C + idx * kStatStride]
     const float *last_gamma, *last_beta, *last_run_mean, *last_run_var;
     float last_eps;
     int last_has_bn, last_relu;
@@ -59,6 +61,7 @@ struct HeadParams {
     // running-statistics updates of the conv layers
     int ru_num;
     const double *ru_stats[SNB200_MAX_CONV_LAYERS];
+    int ru_rep[SNB200_MAX_CONV_LAYERS];   // replicas behind each of them (see stat_rep)
     float *ru_mean[SNB200_MAX_CONV_LAYERS];
     float *ru_var[SNB200_MAX_CONV_LAYERS];
     float ru_momentum[SNB200_MAX_CONV_LAYERS];

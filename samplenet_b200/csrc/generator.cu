@@ -376,7 +376,7 @@ static GenWorkspace carve_gen_ws(void *base, int b, int n, int nconv, const snb2
     W.counter = reinterpret_cast<unsigned *>(p + off + sb); sb += 256 - 16 * sizeof(double);
     for (int l = 0; l < nconv; l++) {
         W.stats[l] = reinterpret_cast<double *>(p + off + sb);
-        sb += align_up((size_t)2 * conv[l].c_out * sizeof(double), 256);
+        sb += align_up((size_t)(1 + kStatStride) * 2 * conv[l].c_out * sizeof(double), 256);   // canonical [2C] block + one line per accumulator
     }
     for (int l = 0; l <= SNB200_MAX_FC_LAYERS; l++) W.ll[l] = nullptr;
     for (int l = 0; l < nfc; l++) {   // exchange buffers of the fused head (zeroed with the statistics): the input of FC layer l
@@ -439,6 +439,7 @@ static void fill_head_params(HeadParams &H, int b, int n, int tpc, int nconv, co
     H.act[0] = W.head_act[0]; H.act[1] = W.head_act[1];
     H.out = out; H.out_inner = out_transpose_inner;
     H.dbg = 0;
+    H.stat_rep = 0;
     for (int l = 0; l <= SNB200_MAX_FC_LAYERS; l++) H.ll[l] = W.ll[l];
     if (training) {
         for (int l = 0; l < nconv; l++)

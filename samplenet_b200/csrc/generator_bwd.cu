@@ -20,6 +20,7 @@
 // ~120 library launches, the recompute of the forward in stock ops and every activation / mask / BatchNorm intermediate in HBM.
 #include "encoder_internal.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace snb {
 
@@ -36,6 +37,7 @@ constexpr int kFcbMaxRows = 64;
 struct FcBwdParams {
     int b, c_in, c_out;
     const float *a_in;          // (b, c_in) the layer's input (post-activation of the layer below / pooled feature)
+    const float *a_out;         // (b, c_out) the layer's OUTPUT as the forward stored it (post-ReLU), or null: the ReLU mask the forward used
     const float *weight, *bias, *gamma, *beta;
     float eps;
     int has_bn, relu;
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(kFcbThreads) fc_bwd_kernel(const __grid_consta
         float zh[2] = {d0 * invstd, d1 * invstd}, dy[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const float y = fmaf(gam, zh[h], bet);
+            // the ReLU mask is the one the FORWARD applied (its stored output), not a recomputation: a pre-activation within rounding of
+            // zero must not get a gradient the forward pass did not see (one flipped element of a 32..64-row batch moves every row)
+            const float y = (P.a_out && lane + 32 * h < b) ? P.a_out[(size_t)(lane + 32 * h) * O + c] : fmaf(gam, zh[h], bet);
             dy[h] = (lane + 32 * h < b && (!P.relu || y > 0.f)) ? dout[h] : 0.f;
         }
         const float s1 = warp_sum(dy[0] + dy[1]);
@@ -167,11 +171,15 @@ __global__ void __launch_bounds__(1024) pool_bwd_kernel(const __grid_constant__ 
         mean = (float)m; invstd = 1.0f / sqrtf((float)v + P.eps);
         sc = P.gamma[c] * invstd; sh = P.beta[c] - mean * sc;
     }
+    // The forward pools the RAW layer output (max where the BatchNorm scale is >= 0, min otherwise: the max-pool commutes with the monotone
+    // BN + ReLU map), by exact comparisons: the same rule here -- first index among equal values -- so the gradient goes to the very point
+    // whose value the forward used.  `best` is kept as sign * z.
+    const float sgn = sc >= 0.f ? 1.f : -1.f;
     float best = -INFINITY; int bi = 0x7fffffff;
     if (c < C) {
         const float *zc = P.z + (size_t)cloud * P.n * C + c;
         for (int p = grp; p < P.n; p += 8) {
-            const float y = fmaf(sc, zc[(size_t)p * C], sh);
+            const float y = sgn * zc[(size_t)p * C];
             if (y > best) { best = y; bi = p; }
         }
     }
@@ -183,9 +191,10 @@ __global__ void __launch_bounds__(1024) pool_bwd_kernel(const __grid_constant__ 
             const float o = sRed[g2][c]; const int oi = sIdx[g2][c];
             if (o > best || (o == best && oi < bi)) { best = o; bi = oi; }
         }
-        const float g = (!P.relu || best > 0.f) ? sDf[c] : 0.f;
         const size_t flat = (size_t)cloud * P.n + bi;
-        const float zh = (P.z[flat * C + c] - mean) * invstd;
+        const float zstar = P.z[flat * C + c];
+        const float g = (!P.relu || fmaf(sc, zstar, sh) > 0.f) ? sDf[c] : 0.f;
+        const float zh = (zstar - mean) * invstd;
         P.pstar[(size_t)cloud * C + c] = (int)flat;
         P.gval[(size_t)cloud * C + c] = g;
         atomicAdd(P.s12 + c, (double)g);
@@ -568,6 +577,7 @@ int launch_generator_backward(int b, int n, int layout, const float *x, int ncon
         FcBwdParams F;
         memset(&F, 0, sizeof(F));
         F.b = b; F.c_in = fc[l].c_in; F.c_out = fc[l].c_out; F.a_in = V.ll[l];
+        F.a_out = (l + 1 < nfc && fc[l].relu) ? V.ll[l + 1] : nullptr;
         F.weight = fc[l].weight; F.bias = fc[l].bias; F.gamma = fc[l].bn_weight; F.beta = fc[l].bn_bias; F.eps = fc[l].bn_eps;
         F.has_bn = fc[l].bn_weight != nullptr; F.relu = fc[l].relu;
         if (l == nfc - 1) { F.grad_out = grad_out; F.out_inner = out_transpose_inner; }
@@ -609,6 +619,7 @@ int launch_generator_backward(int b, int n, int layout, const float *x, int ncon
         else if (ci == 64 && co == 128) rc = launch_conv_bwd<64, 128>(Q, sparse, grid, stream);
         else rc = launch_conv_bwd<64, 64>(Q, sparse, grid, stream);
         if (rc) return rc;
+        { const char *e = getenv("SNB200_BWD_STOP"); if (e && atoi(e) == l) return SNB200_OK; }   // bring-up: leave dy / s12 of layer l-1 in the workspace
     }
     // ---- conv1
     const int g1 = c1_grid(P);

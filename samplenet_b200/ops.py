@@ -648,8 +648,13 @@ def generator_backward(x, layout, conv_specs, fc_specs, saved, grad_out, out_tra
         zp = (ctypes.c_void_p * len(zs))(*[z.data_ptr() for z in zs])
         check(lib().snb200_generator_backward(b, n, lay, _p(x), len(conv_specs), conv, len(fc_specs), fc, zp, _p(fwd_ws), _p(grad_out), int(out_transpose_inner),
                                               gconv, gfc, _p(ws), wsb, _stream()), "generator_backward")
+    global _LAST_BWD_WS
+    _LAST_BWD_WS = ws          # (bring-up: tools/diag_bwd_layers.py inspects the intermediate gradients)
     del keep1, keep2
     return grads
+
+
+_LAST_BWD_WS = None
 
 
 def generator_forward_unfused(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0):

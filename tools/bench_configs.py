@@ -211,6 +211,21 @@ def cfg_train(dev, rank, world):
         t = torch.tensor([msg], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         msg = float(t.item())
+    ar_us = None
+    if world > 1:   # the collective alone: one all-reduce of the flat gradient bucket, back to back (device time, max over ranks)
+        flat = ddp.flat_grad
+        for _ in range(10):
+            torch.distributed.all_reduce(flat)
+        torch.distributed.barrier(); torch.cuda.synchronize()
+        a.record()
+        for _ in range(100):
+            torch.distributed.all_reduce(flat)
+        b.record(); b.synchronize()
+        t = torch.tensor([a.elapsed_time(b) * 10.0], device=dev, dtype=torch.float64)   # us per all-reduce
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ar_us = float(t.item())
+    if rank == 0:
+        emit({"config": "gradient all-reduce alone: flat bucket of %d bytes over NCCL (NVLink/NVSwitch), back to back" % ddp.bucket_bytes(), "n_gpus": world, "us_per_allreduce": ar_us})
     if rank == 0:
         emit({"config": "training step in ONE CUDA graph (samplenet_b200.GraphedTrainStep): fwd + losses + backward + flat-bucket all-reduce + Adam, 32 clouds/GPU",
               "n_gpus": world, "ms_per_step": msg / steps, "clouds_per_s": world * B * steps / (msg * 1e-3), "loss": float(gstep.loss),
