@@ -66,22 +66,36 @@ __global__ void __launch_bounds__(kFcbThreads) fc_bwd_kernel(const __grid_consta
     if (!cv) return;
     // rows r = lane, lane + 32 (b <= 64)
     float dout[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
+    float *sWu = sWr + 8 * I + warp * (P.dz_up ? P.c_up : 0);   // this warp's column of the upper layer's weight: w_up[u][c], u < c_up
+    if (P.dz_up) {
+        for (int u = lane; u < P.c_up; u += 32) sWu[u] = __ldg(P.w_up + (size_t)u * O + c);
+        __syncwarp();
+    }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int r = lane + 32 * h;
         if (r < b) {
             if (P.dz_up) {
-                float acc = 0.f;
-                for (int u = 0; u < P.c_up; u++) acc = fmaf(sU[r * (P.c_up + 1) + u], __ldg(P.w_up + (size_t)u * O + c), acc);
-                dout[h] = acc;
+                const float *su = sU + r * (P.c_up + 1);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int u = 0;
+                for (; u + 4 <= P.c_up; u += 4) {
+                    a0 = fmaf(su[u], sWu[u], a0); a1 = fmaf(su[u + 1], sWu[u + 1], a1); a2 = fmaf(su[u + 2], sWu[u + 2], a2); a3 = fmaf(su[u + 3], sWu[u + 3], a3);
+                }
+                for (; u < P.c_up; u++) a0 = fmaf(su[u], sWu[u], a0);
+                dout[h] = (a0 + a1) + (a2 + a3);
             } else {
                 const int oc = (P.out_inner > 0) ? (c % P.out_inner) * (O / P.out_inner) + c / P.out_inner : c;
                 dout[h] = P.grad_out[(size_t)r * O + oc];
             }
-            float acc = 0.f;
-            const float *wr = sWr + warp * I;
-            for (int k = 0; k < I; k++) acc = fmaf(sA[r * (I + 1) + k], wr[k], acc);
-            z[h] = acc + (P.bias ? P.bias[c] : 0.f);
+            const float *wr = sWr + warp * I, *sa = sA + r * (I + 1);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int k = 0;
+            for (; k + 4 <= I; k += 4) {
+                a0 = fmaf(sa[k], wr[k], a0); a1 = fmaf(sa[k + 1], wr[k + 1], a1); a2 = fmaf(sa[k + 2], wr[k + 2], a2); a3 = fmaf(sa[k + 3], wr[k + 3], a3);
+            }
+            for (; k < I; k++) a0 = fmaf(sa[k], wr[k], a0);
+            z[h] = ((a0 + a1) + (a2 + a3)) + (P.bias ? P.bias[c] : 0.f);
         }
     }
     float dzv[2];
@@ -329,8 +343,10 @@ __global__ void __launch_bounds__(kCbThreads, 2) conv_bwd_kernel(const __grid_co
                 for (int i = 0; i < PPT; i++) d[i] = *reinterpret_cast<const float4 *>(sDz + (pb * PPT + i) * LDZ + co);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(sW + (co + q) * CIN + cb * 8);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(sW + (co + q) * CIN + cb * 8 + 4);
+                    // this thread's 8 input channels are [4 cb, 4 cb + 4) and [CIN/2 + 4 cb, CIN/2 + 4 cb + 4): a quarter warp's 16-byte reads
+                    // are then 128 contiguous bytes (an 8-wide block per thread would put lanes cb and cb + 4 on the same banks)
+                    const float4 w0 = *reinterpret_cast<const float4 *>(sW + (co + q) * CIN + cb * 4);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(sW + (co + q) * CIN + CIN / 2 + cb * 4);
 #pragma unroll
                     for (int i = 0; i < PPT; i++) {
                         const float dv = q == 0 ? d[i].x : (q == 1 ? d[i].y : (q == 2 ? d[i].z : d[i].w));
@@ -344,21 +360,21 @@ __global__ void __launch_bounds__(kCbThreads, 2) conv_bwd_kernel(const __grid_co
             for (int i = 0; i < PPT; i++) {
                 const long long gp = p0 + pb * PPT + i;
                 if (gp < Q.P) {
-                    const float4 za = __ldg(reinterpret_cast<const float4 *>(Q.z_in + gp * CIN + cb * 8));
-                    const float4 zb = __ldg(reinterpret_cast<const float4 *>(Q.z_in + gp * CIN + cb * 8 + 4));
+                    const float4 za = __ldg(reinterpret_cast<const float4 *>(Q.z_in + gp * CIN + cb * 4));
+                    const float4 zb = __ldg(reinterpret_cast<const float4 *>(Q.z_in + gp * CIN + CIN / 2 + cb * 4));
                     const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
                     float dyv[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const int c = cb * 8 + j;
+                        const int c = (j < 4 ? 0 : CIN / 2) + cb * 4 + (j & 3);
                         const float y = fmaf(vSc[c], zv[j], vSh[c]);
                         const float zh = (zv[j] - vMeanI[c]) * vInvI[c];
                         dyv[j] = y > 0.f ? o[i][j] : 0.f;
                         s1acc[j] += dyv[j];
                         s2acc[j] = fmaf(dyv[j], zh, s2acc[j]);
                     }
-                    *reinterpret_cast<float4 *>(Q.dy_in + gp * CIN + cb * 8) = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
-                    *reinterpret_cast<float4 *>(Q.dy_in + gp * CIN + cb * 8 + 4) = make_float4(dyv[4], dyv[5], dyv[6], dyv[7]);
+                    *reinterpret_cast<float4 *>(Q.dy_in + gp * CIN + cb * 4) = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+                    *reinterpret_cast<float4 *>(Q.dy_in + gp * CIN + CIN / 2 + cb * 4) = make_float4(dyv[4], dyv[5], dyv[6], dyv[7]);
                 }
             }
         }
@@ -372,8 +388,8 @@ __global__ void __launch_bounds__(kCbThreads, 2) conv_bwd_kernel(const __grid_co
                 dzr[i] = t4.x; dzr[i + 1] = t4.y; dzr[i + 2] = t4.z; dzr[i + 3] = t4.w;
             }
 #pragma unroll
-            for (int j = 0; j < WCI; j += 4) {
-                const float4 t4 = *reinterpret_cast<const float4 *>(sA + p * LDA + cib * WCI + j);
+            for (int j = 0; j < WCI; j += 4) {   // columns [4 cib, +4) (and [CIN/2 + 4 cib, +4) when WCI = 8): conflict-free 16-byte reads
+                const float4 t4 = *reinterpret_cast<const float4 *>(sA + p * LDA + (j ? CIN / 2 : 0) + cib * 4);
                 ar[j] = t4.x; ar[j + 1] = t4.y; ar[j + 2] = t4.z; ar[j + 3] = t4.w;
             }
 #pragma unroll
@@ -390,7 +406,7 @@ __global__ void __launch_bounds__(kCbThreads, 2) conv_bwd_kernel(const __grid_co
     for (int i = 0; i < WCO; i++) {
 #pragma unroll
         for (int j = 0; j < WCI; j += 4)
-            *reinterpret_cast<float4 *>(part + (size_t)(cob * WCO + i) * CIN + cib * WCI + j) = make_float4(wacc[i][j], wacc[i][j + 1], wacc[i][j + 2], wacc[i][j + 3]);
+            *reinterpret_cast<float4 *>(part + (size_t)(cob * WCO + i) * CIN + (j ? CIN / 2 : 0) + cib * 4) = make_float4(wacc[i][j], wacc[i][j + 1], wacc[i][j + 2], wacc[i][j + 3]);
         if (cib == 0) part[COUT * CIN + cob * WCO + i] = bacc[i];
     }
     __syncthreads();
@@ -398,7 +414,10 @@ __global__ void __launch_bounds__(kCbThreads, 2) conv_bwd_kernel(const __grid_co
     constexpr int NPB = kCbTP / PPT;
     static_assert(NPB * 2 * CIN <= kCbTP * LDZ + kCbTP * LDA, "reduction scratch");
 #pragma unroll
-    for (int j = 0; j < 8; j++) { sR[(pb * 2 + 0) * CIN + cb * 8 + j] = s1acc[j]; sR[(pb * 2 + 1) * CIN + cb * 8 + j] = s2acc[j]; }
+    for (int j = 0; j < 8; j++) {
+        const int c = (j < 4 ? 0 : CIN / 2) + cb * 4 + (j & 3);
+        sR[(pb * 2 + 0) * CIN + c] = s1acc[j]; sR[(pb * 2 + 1) * CIN + c] = s2acc[j];
+    }
     __syncthreads();
     for (int e = tid; e < 2 * CIN; e += kCbThreads) {
         const int which = e / CIN, c = e - which * CIN;
@@ -470,16 +489,24 @@ struct ReduceJob { const float *part; int nparts; int nw, nb; float *g_weight, *
 struct ReduceParams { int njobs; ReduceJob job[SNB200_MAX_CONV_LAYERS]; };
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const __grid_constant__ ReduceParams R)
 {
-    for (int j = 0; j < R.njobs; j++) {
-        const ReduceJob &J = R.job[j];
-        const int total = J.nw + J.nb;
-        for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
-            float s = 0.f;
-            const float *p = J.part + e;
-            for (int k = 0; k < J.nparts; k++) s += p[(size_t)k * total];
-            if (e < J.nw) { if (J.g_weight) J.g_weight[e] = s; }
-            else if (J.g_bias) J.g_bias[e - J.nw] = s;
+    // blockIdx.y = job (conv layer); one thread per gradient element; the CTAs' partials are pulled 8 at a time (independent loads in flight)
+    // and added in CTA order
+    const ReduceJob &J = R.job[blockIdx.y];
+    const int total = J.nw + J.nb;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const float *p = J.part + e;
+        float s = 0.f;
+        int k = 0;
+        for (; k + 8 <= J.nparts; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcs(p + (size_t)(k + u) * total);
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += v[u];
         }
+        for (; k < J.nparts; k++) s += __ldcs(p + (size_t)k * total);
+        if (e < J.nw) { if (J.g_weight) J.g_weight[e] = s; }
+        else if (J.g_bias) J.g_bias[e - J.nw] = s;
     }
 }
 
@@ -504,7 +531,7 @@ bool generator_backward_supported(int b, int n, int nconv, const snb200_layer *c
         if (!((ci == 64 && co == 64) || (ci == 64 && co == 128) || (ci == 128 && co == 128))) return false;
     }
     for (int l = 0; l < nfc; l++) {
-        if (fc[l].c_in > 1024 || (size_t)b * (fc[l].c_in + 1) * 4 + (l + 1 < nfc ? (size_t)b * (fc[l + 1].c_out + 1) * 4 : 0) + 8 * (size_t)fc[l].c_in * 4 > 200 * 1024) return false;
+        if (fc[l].c_in > 1024 || (size_t)b * (fc[l].c_in + 1) * 4 + (l + 1 < nfc ? (size_t)(b + 8) * (fc[l + 1].c_out + 1) * 4 : 0) + 8 * (size_t)fc[l].c_in * 4 > 200 * 1024) return false;
         if ((fc[l].bn_weight != nullptr) != (fc[l].relu != 0)) return false;
     }
     return conv[nconv - 1].c_out <= 128 && fc[0].c_out <= 1024;
@@ -584,7 +611,7 @@ int launch_generator_backward(int b, int n, int layout, const float *x, int ncon
         else { F.dz_up = W.dzfc[l + 1]; F.w_up = fc[l + 1].weight; F.c_up = fc[l + 1].c_out; }
         F.dz = W.dzfc[l];
         F.g_weight = gfc[l].weight; F.g_bias = gfc[l].bias; F.g_gamma = gfc[l].bn_weight; F.g_beta = gfc[l].bn_bias;
-        const size_t smem = ((size_t)b * (F.c_in + 1) + (F.dz_up ? (size_t)b * (F.c_up + 1) : 0) + (size_t)8 * F.c_in) * sizeof(float);
+        const size_t smem = ((size_t)b * (F.c_in + 1) + (F.dz_up ? (size_t)b * (F.c_up + 1) + (size_t)8 * F.c_up : 0) + (size_t)8 * F.c_in) * sizeof(float);
         fc_bwd_kernel<<<(F.c_out + 7) / 8, kFcbThreads, smem, stream>>>(F);
         int rc = check_launch("generator backward: fc layer");
         if (rc) return rc;
@@ -642,7 +669,7 @@ int launch_generator_backward(int b, int n, int layout, const float *x, int ncon
         R.job[l].nw = conv[l].c_out * conv[l].c_in; R.job[l].nb = conv[l].c_out;
         R.job[l].g_weight = gconv[l].weight; R.job[l].g_bias = gconv[l].bias;
     }
-    reduce_partials_kernel<<<64, 256, 0, stream>>>(R);
+    reduce_partials_kernel<<<dim3(64, nconv), 256, 0, stream>>>(R);
     return check_launch("generator backward: reduce");
 }
 

@@ -6,9 +6,9 @@
 // Both Chamfer directions of ALL prefixes come out of one pass over the pair matrix:
 //   * sample -> input  : the nearest input point of sample j does not depend on the prefix; dist1 of prefix s is the slice [:s];
 //   * input  -> sample : the nearest of the first s samples is a running prefix minimum over the sample index.  A reference point is
-//     owned by S lanes, lane l scans the contiguous sample chunk l and records its running (distance, index) minimum at every prefix
-//     boundary that falls into (or before the end of) its chunk; the lanes' records are merged lexicographically (lower chunk = lower
-//     indices wins ties), which reproduces the strict-'<' lowest-index rule of the reference kernel for every prefix.
+//     owned by S lanes, lane l scans the samples l, l + S, ... and records its running (distance, index) minimum at every prefix
+//     boundary; the lanes' records are merged lexicographically, which reproduces the strict-'<' lowest-index rule of the reference
+//     kernel for every prefix.
 // Loss terms are reduced in a fixed order: per-CTA partials, the last CTA to finish (ticket) combines them (bit-reproducible).
 #include "pairwise_device.cuh"
 
@@ -29,6 +29,7 @@ struct ProgParams {
     float *partial;                  // (b, tiles2, np): per-CTA sums of dist2
     unsigned *ticket;
     float *terms;                    // (np, 3) then [3*np] = total loss
+    int cl_batch;                    // clouds whose dist1 rows the final reduction stages at a time (1..8)
 };
 
 template <bool kFma>
@@ -58,16 +59,18 @@ __global__ void __launch_bounds__(kPgThreads) progressive_loss_kernel(const __gr
         const float qx = __ldg(rp), qy = __ldg(rp + 1), qz = __ldg(rp + 2);
         uint32_t phase = 0;
         stage_floats(s_dyn, P.samp + (size_t)bi * P.m * 3, P.m * 3, &bar, phase);
-        const int chunk = (P.m + S - 1) / S;
-        const int a = min(P.m, l * chunk), e = min(P.m, a + chunk);   // this lane scans samples [a, e)
+        // lane l scans the samples j = l, l + S, l + 2S, ... (neighbouring lanes read neighbouring points: conflict-free shared-memory reads);
+        // at a prefix boundary s its running minimum covers {j < s, j = l mod S}, and the lexicographic merge over the S lanes below gives
+        // the minimum over all j < s with the lowest index among equal distances
         float best = INFINITY; int besti = 0x7fffffff;
         float rec[kPgMaxPrefix]; int reci[kPgMaxPrefix];
-        int j = a;
+        int j = l;
 #pragma unroll
         for (int p = 0; p < kPgMaxPrefix; p++) {
             if (p < P.np) {
-                const int end = min(max(P.sizes[p], a), e);
-                for (; j < end; j++) {
+                const int end = P.sizes[p];
+#pragma unroll 4
+                for (; j < end; j += S) {
                     const float d = sqdist<kFma>(s_dyn[j * 3 + 0] - qx, s_dyn[j * 3 + 1] - qy, s_dyn[j * 3 + 2] - qz);   // (candidate - query)
                     if (d < best) { best = d; besti = j; }
                 }
@@ -121,13 +124,29 @@ __global__ void __launch_bounds__(kPgThreads) progressive_loss_kernel(const __gr
     __shared__ float s_seg[kPgThreads / 32][kPgMaxPrefix][2];
     __syncthreads();
     const float *d1 = P.d0.dist;
-    for (int c0 = 0; c0 < P.b; c0 += kPgThreads / 32) {     // a warp per cloud: per-segment sum / max of dist1, then prefix over the segments
+    // dist1 of kPgThreads / 32 clouds at a time is pulled into shared memory with independent, coalesced loads (one L2 round trip), then a
+    // warp per cloud forms the per-segment sums / maxima and the prefix over the segments -- everything in a fixed order
+    float *s_d1 = s_dyn + 64;                                   // [8 clouds][m] behind the accumulators
+    const int kCl = P.cl_batch;
+    for (int c0 = 0; c0 < P.b; c0 += kCl) {
+        const int ncl = min(kCl, P.b - c0);
+        const int tot = ncl * P.m;
+        __syncthreads();
+        for (int e0 = threadIdx.x; e0 < tot; e0 += kPgThreads * 8) {
+            float v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v8[u] = (e0 + u * kPgThreads < tot) ? __ldcg(d1 + (size_t)c0 * P.m + e0 + u * kPgThreads) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (e0 + u * kPgThreads < tot) s_d1[e0 + u * kPgThreads] = v8[u];
+        }
+        __syncthreads();
         const int bi = c0 + warp;
-        if (bi < P.b) {
+        if (warp < ncl) {
             int lo = 0;
             for (int p = 0; p < P.np; p++) {
                 float s = 0.f, mx = -INFINITY;
-                for (int jj = lo + lane; jj < P.sizes[p]; jj += 32) { const float v = __ldcg(d1 + (size_t)bi * P.m + jj); s += v; mx = fmaxf(mx, v); }
+                for (int jj = lo + lane; jj < P.sizes[p]; jj += 32) { const float v = s_d1[warp * P.m + jj]; s += v; mx = fmaxf(mx, v); }
                 s = warp_sum(s); mx = warp_max(mx);
                 if (lane == 0) { s_seg[warp][p][0] = s; s_seg[warp][p][1] = mx; }
                 lo = P.sizes[p];
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(kPgThreads) progressive_loss_kernel(const __gr
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 0; w < kPgThreads / 32 && c0 + w < P.b; w++) {
+            for (int w = 0; w < kCl && c0 + w < P.b; w++) {
                 float run_s = 0.f, run_m = -INFINITY;
                 for (int p = 0; p < P.np; p++) {
                     run_s += s_seg[w][p][0]; run_m = fmaxf(run_m, s_seg[w][p][1]);
@@ -146,14 +165,23 @@ __global__ void __launch_bounds__(kPgThreads) progressive_loss_kernel(const __gr
         }
         __syncthreads();
     }
-    if ((int)threadIdx.x < P.np) {
-        const int p = threadIdx.x;
-        float t = 0.f;
-        for (int bi = 0; bi < P.b; bi++)
-            for (int tl = 0; tl < P.tiles2; tl++) t += __ldcg(P.partial + ((size_t)bi * P.tiles2 + tl) * P.np + p);
-        s_t[p * 3 + 2] = t;
+    {   // per-prefix sums of the input -> sample partials: all threads pull the (cloud, tile) partials with independent loads, then a
+        // fixed-order tree (bit-reproducible)
+        __shared__ float s_tree[kPgThreads];
+        const int nparts = P.b * P.tiles2;
+        for (int p = 0; p < P.np; p++) {
+            float t = 0.f;
+            for (int e2 = threadIdx.x; e2 < nparts; e2 += kPgThreads) t += __ldcg(P.partial + (size_t)e2 * P.np + p);
+            s_tree[threadIdx.x] = t;
+            __syncthreads();
+            for (int o = kPgThreads / 2; o > 0; o >>= 1) {
+                if ((int)threadIdx.x < o) s_tree[threadIdx.x] += s_tree[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) s_t[p * 3 + 2] = s_tree[0];
+            __syncthreads();
+        }
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
         float total = 0.f;
         for (int p = 0; p < P.np; p++) {
@@ -188,11 +216,12 @@ int launch_progressive_loss(int b, int n, int m, const float *ref, const float *
     P.S2 = S;
     P.tiles2 = (n + kPgThreads / S - 1) / (kPgThreads / S);
     P.dist2 = dist2; P.idx2 = idx2; P.partial = reinterpret_cast<float *>(workspace); P.ticket = ticket; P.terms = terms;
-    const size_t smem = (size_t)max(max(min(n, kChamferTile), m) * 3, 64) * sizeof(float);
+    P.cl_batch = max(1, min(kPgThreads / 32, (12 * 1024 - 64) / m));   // at most 48 KB of staging (keeps several CTAs per SM)
+    const size_t smem = (size_t)max(max(max(min(n, kChamferTile), m) * 3, 64 + P.cl_batch * m), 64) * sizeof(float);
     static PerDeviceOnce once;
     if (once.first()) {
-        cudaFuncSetAttribute(progressive_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(progressive_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(progressive_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(progressive_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     }
     const int grid = b * (P.d0.tiles + P.tiles2);
     if (flags & SNB200_DIST_UNFUSED) progressive_loss_kernel<false><<<grid, kPgThreads, smem, stream>>>(P);

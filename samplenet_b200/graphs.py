@@ -190,7 +190,10 @@ class GraphedTrainStep:
             raise ValueError("GraphedTrainStep expects a SampleNet with input_shape = output_shape = 'bnc'")
         self.ddp = FlatBucketDataParallel(net)
         params = [p for p in net.parameters() if p.requires_grad]
-        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=True)
+        # one fused multi-tensor Adam launch (torch's fused optimizer is capturable); gradients are written by the backward kernels straight
+        # into the flat bucket's views (no per-parameter accumulate / zero-fill launches)
+        self.optimizer = torch.optim.Adam(params, lr=lr, fused=True, capturable=True)
+        net.direct_parameter_grads = True     # (one sampler forward per captured step)
         self.x = torch.zeros(batch_size, num_points, 3, device=dev)
         m = net.num_out_points
 

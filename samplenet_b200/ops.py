@@ -538,7 +538,7 @@ class primed_workspaces:
 
 
 # Which persistent conv-stack kernel the default generator path uses: 2 = transposed GEMMs (round 2), 1 = the round-1 kernel.
-CONV_STACK_VERSION = 2 if os.environ.get("SNB200_CONV_STACK", "") == "v2" else 1   # TODO(flip after hardware validation)
+CONV_STACK_VERSION = 1 if os.environ.get("SNB200_CONV_STACK", "") == "v1" else 2
 
 
 def generator_forward(x, layout, conv_specs, fc_specs, training, out_transpose_inner=0, exact_fp32=False, _profile_flags=0, per_layer_kernels=False, separate_head=False,
@@ -614,9 +614,10 @@ def generator_train_forward(x, layout, conv_specs, fc_specs, out_transpose_inner
     return out, feat, (zs, ws)
 
 
-def generator_backward(x, layout, conv_specs, fc_specs, saved, grad_out, out_transpose_inner=0):
+def generator_backward(x, layout, conv_specs, fc_specs, saved, grad_out, out_transpose_inner=0, dest=None):
     """Gradients of every generator parameter (hand-written CUDA; csrc/generator_bwd.cu).  Returns a list, in layer order (conv then fc), of
-    dicts {weight, bias, bn_weight, bn_bias} (bn_* None for layers without BatchNorm)."""
+    dicts {weight, bias, bn_weight, bn_bias} (bn_* None for layers without BatchNorm).  dest: optional list of such dicts of preallocated
+    contiguous tensors the kernels write into (e.g. the parameters' .grad views of a flat bucket) instead of fresh tensors."""
     lay = _layout(layout)
     x = _req(x, "x"); grad_out = _req(grad_out, "grad_out")
     b = x.shape[0]
@@ -631,10 +632,13 @@ def generator_backward(x, layout, conv_specs, fc_specs, saved, grad_out, out_tra
         arr = (LayerGrad * len(specs))()
         for i, s in enumerate(specs):
             w = s["weight"]
-            g = {"weight": torch.empty_like(w), "bias": torch.empty(w.shape[0], device=dev) if s.get("bias") is not None else None,
-                 "bn_weight": None, "bn_bias": None}
-            if s.get("bn") is not None:
-                g["bn_weight"] = torch.empty(w.shape[0], device=dev); g["bn_bias"] = torch.empty(w.shape[0], device=dev)
+            if dest is not None:
+                g = dest[len(grads)]
+            else:
+                g = {"weight": torch.empty_like(w), "bias": torch.empty(w.shape[0], device=dev) if s.get("bias") is not None else None,
+                     "bn_weight": None, "bn_bias": None}
+                if s.get("bn") is not None:
+                    g["bn_weight"] = torch.empty(w.shape[0], device=dev); g["bn_bias"] = torch.empty(w.shape[0], device=dev)
             arr[i].weight, arr[i].bias = _p(g["weight"]), _p(g["bias"])
             arr[i].bn_weight, arr[i].bn_bias = _p(g["bn_weight"]), _p(g["bn_bias"])
             grads.append(g)

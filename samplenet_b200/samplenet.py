@@ -56,6 +56,20 @@ class _GeneratorFunction(torch.autograd.Function):
         names = [n for n, _ in net._generator_named_parameters()]
         if ctx.cuda_saved is not None:
             conv_specs, fc_specs = net._layer_specs()
+            if net.direct_parameter_grads and all(p.grad is not None and p.grad.is_contiguous() for p in params):
+                # the kernels write straight into the parameters' .grad storage (e.g. views of FlatBucketDataParallel's bucket): no fresh
+                # gradient tensors, no AccumulateGrad adds (35 launches per step).  OVERWRITES: valid when this is the only backward
+                # contribution to the generator's parameters between two zero_grad() calls (one sampler forward per step).
+                dest, k = [], 0
+                for lin, bn in net._convs() + net._fcs():
+                    d = {"weight": params[k].grad, "bias": params[k + 1].grad, "bn_weight": None, "bn_bias": None}
+                    k += 2
+                    if bn is not None:
+                        d["bn_weight"], d["bn_bias"] = params[k].grad, params[k + 1].grad
+                        k += 2
+                    dest.append(d)
+                ops.generator_backward(x, ctx.layout, conv_specs, fc_specs, ctx.cuda_saved, g.contiguous(), ctx.out_inner, dest=dest)
+                return (None,) * (5 + len(params))
             grads = ops.generator_backward(x, ctx.layout, conv_specs, fc_specs, ctx.cuda_saved, g.contiguous(), ctx.out_inner)
             gp = []
             for gl in grads:   # same order as _generator_named_parameters: w, b[, g, beta] per layer
@@ -138,7 +152,9 @@ class SampleNet(nn.Module):
         self.generator_precision = "3xtf32"
         # "cuda": hand-written backward kernels (csrc/generator_bwd.cu) wherever they cover the shape; "torch": recompute the layer stack
         # with stock torch ops and differentiate that (the round-1 path; also the fallback outside the CUDA backward's envelope)
-        self.generator_backward = os.environ.get("SNB200_GENERATOR_BACKWARD", "torch")   # TODO(flip to "cuda" after hardware validation)
+        self.generator_backward = os.environ.get("SNB200_GENERATOR_BACKWARD", "cuda")
+        # opt-in (set by GraphedTrainStep): the CUDA backward writes into existing .grad tensors instead of returning fresh ones
+        self.direct_parameter_grads = False
         # project + Chamfer + loss reductions of (simp, x) in one launch when forward() runs in training mode ("bnc" in and out)
         self.fused_tail = True
         self._tail = None
