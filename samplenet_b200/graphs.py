@@ -100,6 +100,23 @@ class PipelinedHostStep:
         self.launch()
         return self.finish()
 
+    def run_async(self, x):
+        """Device-ordered variant for inputs that already live in HBM (or pinned host memory) when NO per-step host read-back is wanted:
+        the batch is copied into the idle slot's capture buffer on the copy stream -- overlapping the other slot's graph, which is still
+        running -- and that slot's graph is queued behind the copy.  Returns the slot (its static `simp`, `proj`, `loss` tensors are valid
+        once the current stream reaches this point).  Do not mix with submit()/launch()/finish() on the same object."""
+        k = self.head
+        st = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_event(self.done[k])              # the graph that last read this buffer has finished
+        with torch.cuda.stream(self.copy_stream):
+            self.slots[k].x.copy_(x, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        st.wait_event(self.ready[k])
+        self.slots[k].replay()
+        self.done[k].record(st)
+        self.head ^= 1
+        return self.slots[k]
+
 
 class GraphedStep:
     def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None, warmup=2, loss_to_host=False):

@@ -10,7 +10,7 @@ import torch
 import samplenet_b200 as sb
 from samplenet_b200 import tf_ops
 
-fam = set(sys.argv[1:]) or {"chamfer", "softproj", "tail", "generator", "emd", "matching", "group", "train"}
+fam = set(sys.argv[1:]) or {"chamfer", "softproj", "tail", "generator", "emd", "matching", "group", "train", "progressive"}
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 x = (torch.rand(4, 256, 3, device=dev) - 0.5)
@@ -60,6 +60,15 @@ if "emd" in fam:
     match = tf_ops.approx_match(a, b)
     tf_ops.match_cost(a, b, match).sum().backward()
     print("emd ok")
+if "progressive" in fam:
+    from samplenet_b200 import trainers
+    so = torch.rand(4, 64, 3, device=dev, requires_grad=True)
+    xr = x.clone().requires_grad_(True)
+    trainers.progressive_simplification_loss(xr, so, [2, 4, 8, 16, 32, 64]).backward()
+    print("progressive ok")
+if "emd" in fam:
+    tf_ops.approx_match(torch.rand(2, 48, 3, device=dev), torch.rand(2, 32, 3, device=dev), exact=True)
+    print("emd exact ok")
 if "matching" in fam:
     _, idx1, _, _ = sb.ops.nn_distance_forward(q, x)
     sb.sputils.nn_matching_cuda(x, idx1, 32)
