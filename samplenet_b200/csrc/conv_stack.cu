@@ -213,6 +213,12 @@ __device__ __forceinline__ double cs_stat(const double *base, int c2, int idx, i
     return __ldcg(spread ? base + c2 + (size_t)idx * kStatStride : base + idx);
 }
 
+// arrival word of channel ch of a layer with C channels: the second 8 bytes of the channel's sum-accumulator line (zeroed with the accumulators)
+__device__ __forceinline__ unsigned *cs_stat_arrivals(double *base, int C, int ch)
+{
+    return reinterpret_cast<unsigned *>(base + 2 * C + (size_t)ch * kStatStride + 1);
+}
+
 // A-from-TMEM form: D[tmem] (+)= A[tmem, 128 lanes x 8 columns] . B[smem descriptor]
 __device__ __forceinline__ void cs_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -361,12 +367,13 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory: ring of kCsRing slots x [hi: ppc x 128 B | lo: ppc x 128 B]; reused by the pool partials and by the head
-    __shared__ float sX[kCsMaxPts * 3];
+    __shared__ __align__(16) float sX[kCsMaxPts * 3];
     __shared__ float sW1[128 * 3], sB1[128];
     __shared__ float sRedS[4][128], sRedQ[4][128];
     __shared__ uint64_t bar_full[kCsRing], bar_ring[kCsRing], bar_acc, bar_w;
     __shared__ uint32_t tmem_base_smem;
     __shared__ double sMom[9];
+    __shared__ float sMomW[kCsProducers / 32][9];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool producer = true;                          // every warp prepares operands; warp kCsIssuerWarp also issues the MMAs
@@ -446,14 +453,17 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 for (int j = 0; j < 9; j++) {
                     float v = a9[j];
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-                    if (lane == 0) atomicAdd(&sMom[j], (double)v);
+                    if (lane == 0) sMomW[warp][j] = v;
                 }
             }
         }
         __syncthreads();
-        if (tid < 9) atomicAdd(P.mom + tid, sMom[tid]);
-        __syncthreads();
-        if (tid == 0) cs_grid_arrive(P.barrier);
+        if (tid < 9) {   // one thread per moment: this CTA's sum, the grid's accumulator, then the arrival word (release: after the add, and --
+            double t = 0.0;   // through the CTA barrier above -- after every thread's share of the self-clean stores)
+            for (int w = 0; w * 32 < npts && w < kCsProducers / 32; w++) t += (double)sMomW[w][tid];
+            atomicAdd(P.mom + tid, t);
+            cs_grid_arrive(reinterpret_cast<unsigned *>(P.mom + 9));
+        }
     }
     if (producer) {   // weights of the first tensor layer into tensor memory
         cs_store_w(tmem_lane, g, P.L[1].c_in >> 2, wreg);
@@ -461,9 +471,10 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         cs_mbar_arrive(&bar_w);
     }
     if (need_stats && L1.has_bn) {
-        if (tid == 0) cs_grid_wait(P.barrier, ++barrier_epoch * G);
-        __syncthreads();
-        if (tid < 9) sMom[tid] = __ldcg(P.mom + tid);
+        if (tid < 9) {
+            cs_grid_wait(reinterpret_cast<unsigned *>(P.mom + 9), 9u * G);
+            sMom[tid] = __ldcg(P.mom + tid);
+        }
         __syncthreads();
     }
     CS_TS(2);
@@ -476,7 +487,11 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
 #pragma unroll
         for (int jb = 0; jb < kCsNPT / 8; jb++) {
             if (jb * 8 < npt) {
-                const float *xr = sX + (col0 + jb * 8) * 3;
+                // 8 points = 24 consecutive floats = six 16-byte broadcast reads (col0 and 8 jb are multiples of 8: 96-byte aligned)
+                const float4 *xq = reinterpret_cast<const float4 *>(sX + (col0 + jb * 8) * 3);
+                float xr[24];
+#pragma unroll
+                for (int u = 0; u < 6; u++) { const float4 t4 = xq[u]; xr[u * 4 + 0] = t4.x; xr[u * 4 + 1] = t4.y; xr[u * 4 + 2] = t4.z; xr[u * 4 + 3] = t4.w; }
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[jb * 8 + i] = __float_as_uint(fmaf(w2, xr[i * 3 + 2], fmaf(w1, xr[i * 3 + 1], w0 * xr[i * 3 + 0])) + b1);
             }
@@ -522,6 +537,10 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             Lp.stats[K + ch] = cnt * (vv + m * m);
                         }
                     } else {
+                        // this channel's arrival word sits in the line of its sum accumulator: every CTA's channel thread added its two partial
+                        // sums and then released the word, so "word == grid size" (acquire) means both totals are final -- the layers need no
+                        // grid-wide barrier, only 128 independent per-channel ones, and the CTA-wide barrier round trips around it go away
+                        cs_grid_wait(cs_stat_arrivals(Lp.stats, K, ch), G);
                         const double s1 = cs_stat(Lp.stats, 2 * K, ch, 1), s2 = cs_stat(Lp.stats, 2 * K, K + ch, 1);
                         if (blockIdx.x == 0) { Lp.stats[ch] = s1; Lp.stats[K + ch] = s2; }   // the canonical block (head, backward pass)
                         m = s1 * inv_cnt;
@@ -652,12 +671,13 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             }
             CS_TS(3 + (l - 1) * 8 + 4);
             if (want_stats || last) cs_named_sync(1, kCsProducers);
-            if (want_stats && g == 0 && ch < N && !(P.dbg & 1)) {
+            if (want_stats && g == 0 && ch < N) {
                 const float sm = (sRedS[0][ch] + sRedS[1][ch]) + (sRedS[2][ch] + sRedS[3][ch]);
                 const float sqq = (sRedQ[0][ch] + sRedQ[1][ch]) + (sRedQ[2][ch] + sRedQ[3][ch]);
                 double *acc = Lc.stats + 2 * N;   // padded accumulators: one 128-byte line each
                 atomicAdd(acc + (size_t)ch * kStatStride, (double)sm);
                 atomicAdd(acc + (size_t)(N + ch) * kStatStride, (double)sqq);
+                if (!last) cs_grid_arrive(cs_stat_arrivals(Lc.stats, N, ch));   // release: ordered after this thread's two atomics
             }
             if (last) {   // (cloud, slot) partial extrema; slot = this CTA's rank among the CTAs that touch the cloud
                 const int S = P.slots_per_cloud;
@@ -682,7 +702,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 }
             }
             CS_TS(3 + (l - 1) * 8 + 5);
-            if (want_stats) {   // grid barrier: every CTA's statistics (and, last layer, extrema) are in
+            if (want_stats && last) {   // grid barrier: every CTA's statistics and extrema are in (the head reads both)
                 cs_named_sync(1, kCsProducers);
                 if (tid == 0) {
                     cs_grid_arrive(P.barrier);
@@ -690,14 +710,14 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     cs_grid_wait(P.barrier, (barrier_epoch + 1) * G);
                 }
                 cs_named_sync(1, kCsProducers);
-            } else if (!last) {
-                // no statistics barrier (eval mode / no BatchNorm): still, every warp must have read its accumulator columns before the
-                // next layer's MMAs (which need only K chunk 0) start overwriting them
+            } else if (!last && !want_stats) {
+                // eval mode / no BatchNorm: still, every warp must have read its accumulator columns before the next layer's MMAs (which need
+                // only K chunk 0) start overwriting them.  (With statistics, the CTA barrier in front of the atomics above already orders that.)
                 cs_named_sync(1, kCsProducers);
             }
             CS_TS(3 + (l - 1) * 8 + 6);
         }
-        if (want_stats) barrier_epoch++;
+        if (want_stats && last) barrier_epoch++;
     }
 
     // every commit has been observed through bar_acc; tensor memory is released at the end of the kernel (off the head's critical path)
@@ -736,23 +756,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         for (int l = 0; l < H.num_fc; l++) mbar_init(&hbar[l], 1);
         fence_mbar_init();
     }
-    __syncthreads();
-    if (tid == 0) {
-        fence_proxy_async();   // the smem region was written through the generic proxy by the conv stack
-        int woff = 0;
-        for (int l = 0; l < H.num_fc; l++) {
-            const HeadLayer &L = H.fc[l];
-            const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
-            const int lo = blockIdx.x * cpc, hi = min(L.c_out, lo + cpc);
-            const bool tma_ok = (L.c_in & 3) == 0 && (hcmax & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
-            if (lo < hi && tma_ok) {
-                const uint32_t bytes = (uint32_t)min(8, hi - lo) * L.c_in * 4u;
-                mbar_expect_tx(&hbar[l], bytes);
-                tma_load_1d(s_wall + woff, L.weight + (size_t)lo * L.c_in, bytes, &hbar[l]);
-            }
-            woff += 8 * L.c_in;
-        }
-    }
+    // (the TMA requests themselves are issued after the pooling phase below: thread 0 owns a pooled element too, and every consumer of the
+    //  pooled feature waits for the slowest element)
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
     // no grid barrier has been crossed yet.
     if (!(need_stats && P.L[P.num_layers - 1].has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);
@@ -777,10 +782,16 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 canon[c] = st0; canon[H.c_feat + c] = st1;
             }
             const float lg = H.last_has_bn ? __ldg(H.last_gamma + c) : 1.f, lb = H.last_has_bn ? __ldg(H.last_beta + c) : 0.f;
-#pragma unroll 8
-            for (int t = 0; t < H.tiles_per_cloud; t++) {
-                mx = fmaxf(mx, __ldcg(tm + (size_t)t * H.c_feat));
-                mn = fminf(mn, __ldcg(tn + (size_t)t * H.c_feat));
+            for (int t0 = 0; t0 < H.tiles_per_cloud; t0 += 8) {   // 8 slots at a time, all 16 loads in flight before the first max / min
+                float a8[8], b8[8];                                  // (a run-time trip count would serialise one L2 round trip per slot)
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const bool in = t0 + u < H.tiles_per_cloud;
+                    a8[u] = in ? __ldcg(tm + (size_t)(t0 + u) * H.c_feat) : -INFINITY;
+                    b8[u] = in ? __ldcg(tn + (size_t)(t0 + u) * H.c_feat) : INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { mx = fmaxf(mx, a8[u]); mn = fminf(mn, b8[u]); }
             }
             float v = mx;
             if (H.last_has_bn) {
@@ -803,6 +814,23 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         }
     }
     CS_TS(37);
+    __syncthreads();   // mbarrier inits visible; every thread of this CTA is done with the conv stack's shared memory
+    if (tid == 0) {
+        fence_proxy_async();   // the smem region was written through the generic proxy by the conv stack
+        int woff = 0;
+        for (int l = 0; l < H.num_fc; l++) {
+            const HeadLayer &L = H.fc[l];
+            const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
+            const int lo = blockIdx.x * cpc, hi = min(L.c_out, lo + cpc);
+            const bool tma_ok = (L.c_in & 3) == 0 && (hcmax & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+            if (lo < hi && tma_ok) {
+                const uint32_t bytes = (uint32_t)min(8, hi - lo) * L.c_in * 4u;
+                mbar_expect_tx(&hbar[l], bytes);
+                tma_load_1d(s_wall + woff, L.weight + (size_t)lo * L.c_in, bytes, &hbar[l]);
+            }
+            woff += 8 * L.c_in;
+        }
+    }
     CS_TS(38);
 
     int woff = 0;
