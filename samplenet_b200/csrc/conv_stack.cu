@@ -207,16 +207,92 @@ __device__ __forceinline__ void cs_head_stage_weights(const HeadLayer &L, int cb
 }
 
 
+__device__ __forceinline__ float cs_ld_now(const float *p)   // a load that is issued where it is written
+{
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one thread's share of an FC layer: 4 output channels x KR inputs of its batch row; x = the row's inputs (stride 1), w = 4 weight rows (stride c_in)
+template <int KR>
+__device__ __forceinline__ void cs_head_dot(const float *x, const float *w, int c_in, float (&a4)[4])
+{
+    float xr[KR];
+#pragma unroll
+    for (int i = 0; i < KR; i++) xr[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < KR; i += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + j * c_in + i);
+            a4[j] = fmaf(xr[i + 3], wv.w, fmaf(xr[i + 2], wv.z, fmaf(xr[i + 1], wv.y, fmaf(xr[i], wv.x, a4[j]))));
+        }
+    }
+}
+
 // (sum, sumsq) accumulator idx of a layer: the dense [2C] block, or (spread != 0) the padded accumulators behind it
 __device__ __forceinline__ double cs_stat(const double *base, int c2, int idx, int spread)
 {
     return __ldcg(spread ? base + c2 + (size_t)idx * kStatStride : base + idx);
 }
 
-// arrival word of channel ch of a layer with C channels: the second 8 bytes of the channel's sum-accumulator line (zeroed with the accumulators)
-__device__ __forceinline__ unsigned *cs_stat_arrivals(double *base, int C, int ch)
+// ---- BatchNorm statistics between the conv layers: fixed-point words that carry their own arrival count --------------------------
+// Every CTA contributes one partial (sum, sum of squares) per channel and layer; the next layer cannot start before the totals are
+// known.  A floating-point accumulator needs a separate "everybody has added" signal, ordered after the adds (release -> acquire:
+// three dependent L2 round trips plus the fences).  Here each partial is converted to fixed point and added, together with a 1 in
+// the top byte, by ONE 64-bit integer reduction: the word is its own arrival counter, a consumer that reads "count == grid size"
+// holds the final total -- no fence, no flag, no barrier, one L2 round trip after the last add -- and integer addition is exact and
+// order-independent, so the statistics are bit-reproducible by construction.
+//   sum      : units of 2^-24, offset 2^47 per partial (non-negative fields cannot borrow from the count)   |partial| < 2^23
+//   sumsq hi : units of 2^-9 (floor)                                                                          partial  < 2^38
+//   sumsq lo : the remainder in units of 2^-48
+// Absolute resolution of a total: 148 * 2^-25 = 4.4e-6 on a sum of b*n values and 5e-13 on a sum of squares -- far below what the
+// eps of the BatchNorm lets through.  A partial outside the range (per-point pre-activations beyond ~3e4, or NaN / Inf input)
+// contributes zero and poisons the CTA's pooled extrema (+-Inf), so the launch returns NaN rows instead of wrong numbers.
+// Word placement: sum and sumsq-lo in the line of accumulator ch, sumsq-hi in the line of accumulator C + ch (two adds per line).
+constexpr unsigned long long kFxCountOne = 1ull << 56, kFxFieldMask = kFxCountOne - 1;
+constexpr long long kFxSumOffset = 1ll << 47;
+__device__ __forceinline__ unsigned long long *cs_fx_line(double *stats, int C, int idx)
 {
-    return reinterpret_cast<unsigned *>(base + 2 * C + (size_t)ch * kStatStride + 1);
+    return reinterpret_cast<unsigned long long *>(stats + 2 * C + (size_t)idx * kStatStride);
+}
+__device__ __forceinline__ void cs_fx_add(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long cs_fx_load(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// returns false when the partial is outside the fixed-point range (nothing but the arrival counts is added then)
+__device__ __forceinline__ bool cs_fx_contribute(double *stats, int C, int ch, float sum, float sumsq)
+{
+    const bool ok = fabsf(sum) < 8388608.f && sumsq < 274877906944.f;   // (false for NaN)
+    if (!ok) { sum = 0.f; sumsq = 0.f; }
+    const long long ps = __double2ll_rn((double)sum * 16777216.0) + kFxSumOffset;
+    const double qd = (double)sumsq, qh = floor(qd * 512.0);
+    const long long hi = (long long)qh, lo = __double2ll_rn((qd - qh * (1.0 / 512.0)) * 281474976710656.0);
+    unsigned long long *la = cs_fx_line(stats, C, ch), *lb = cs_fx_line(stats, C, C + ch);
+    cs_fx_add(la, kFxCountOne + (unsigned long long)ps);
+    cs_fx_add(lb, kFxCountOne + (unsigned long long)hi);
+    cs_fx_add(la + 1, kFxCountOne + (unsigned long long)lo);
+    return ok;
+}
+// spins until all G partials of channel ch are in, then decodes the totals
+__device__ __forceinline__ void cs_fx_collect(double *stats, int C, int ch, unsigned G, double &sum, double &sumsq)
+{
+    const unsigned long long *la = cs_fx_line(stats, C, ch), *lb = cs_fx_line(stats, C, C + ch);
+    unsigned long long a, b, c;
+    unsigned spin = 0;
+    do {
+        a = cs_fx_load(la); c = cs_fx_load(la + 1); b = cs_fx_load(lb);
+        if (++spin > (1u << 24)) __trap();
+    } while ((unsigned)(a >> 56) != G || (unsigned)(b >> 56) != G || (unsigned)(c >> 56) != G);
+    sum = (double)((long long)(a & kFxFieldMask) - (long long)G * kFxSumOffset) * (1.0 / 16777216.0);
+    sumsq = (double)(long long)(b & kFxFieldMask) * (1.0 / 512.0) + (double)(long long)(c & kFxFieldMask) * (1.0 / 281474976710656.0);
 }
 
 // A-from-TMEM form: D[tmem] (+)= A[tmem, 128 lanes x 8 columns] . B[smem descriptor]
@@ -374,6 +450,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     __shared__ uint32_t tmem_base_smem;
     __shared__ double sMom[9];
     __shared__ float sMomW[kCsProducers / 32][9];
+    __shared__ int sBad;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool producer = true;                          // every warp prepares operands; warp kCsIssuerWarp also issues the MMAs
@@ -397,6 +474,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         fence_mbar_init();
     }
     if (tid < 9) sMom[tid] = 0.0;
+    if (tid == 0) sBad = 0;
     // the points of this CTA and layer 1's weights
     const CsLayer &L1 = P.L[0];
     if (producer) {
@@ -520,6 +598,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             // (A) BatchNorm (+ReLU) of the producer layer for this thread's channel: two registers
             float sc = 1.f, sh = 0.f;
             if (Lp.has_bn && ch < K && g == 0) {   // one column group reads the statistics (hot L2 lines) and shares the result
+                const float pgamma = cs_ld_now(Lp.gamma + ch), pbeta = cs_ld_now(Lp.beta + ch);   // in flight while the statistics are collected
 
                 float mean, var;
                 if (P.training) {
@@ -537,11 +616,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             Lp.stats[K + ch] = cnt * (vv + m * m);
                         }
                     } else {
-                        // this channel's arrival word sits in the line of its sum accumulator: every CTA's channel thread added its two partial
-                        // sums and then released the word, so "word == grid size" (acquire) means both totals are final -- the layers need no
-                        // grid-wide barrier, only 128 independent per-channel ones, and the CTA-wide barrier round trips around it go away
-                        cs_grid_wait(cs_stat_arrivals(Lp.stats, K, ch), G);
-                        const double s1 = cs_stat(Lp.stats, 2 * K, ch, 1), s2 = cs_stat(Lp.stats, 2 * K, K + ch, 1);
+                        double s1, s2;   // the grid's totals for this channel (see cs_fx_*: the words carry their own arrival count)
+                        cs_fx_collect(Lp.stats, K, ch, (unsigned)G, s1, s2);
                         if (blockIdx.x == 0) { Lp.stats[ch] = s1; Lp.stats[K + ch] = s2; }   // the canonical block (head, backward pass)
                         m = s1 * inv_cnt;
                         vv = s2 * inv_cnt - m * m;
@@ -552,8 +628,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     mean = Lp.run_mean[ch]; var = Lp.run_var[ch];
                 }
                 const float invstd = 1.0f / sqrtf(var + Lp.eps);
-                sc = Lp.gamma[ch] * invstd;
-                sh = Lp.beta[ch] - mean * sc;
+                sc = pgamma * invstd;
+                sh = pbeta - mean * sc;
             }
             if (Lp.has_bn) {
                 if (g == 0 && ch < K) { sRedS[0][ch] = sc; sRedQ[0][ch] = sh; }   // (the partial-sum arrays are free between the layers)
@@ -674,10 +750,13 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             if (want_stats && g == 0 && ch < N) {
                 const float sm = (sRedS[0][ch] + sRedS[1][ch]) + (sRedS[2][ch] + sRedS[3][ch]);
                 const float sqq = (sRedQ[0][ch] + sRedQ[1][ch]) + (sRedQ[2][ch] + sRedQ[3][ch]);
-                double *acc = Lc.stats + 2 * N;   // padded accumulators: one 128-byte line each
-                atomicAdd(acc + (size_t)ch * kStatStride, (double)sm);
-                atomicAdd(acc + (size_t)(N + ch) * kStatStride, (double)sqq);
-                if (!last) cs_grid_arrive(cs_stat_arrivals(Lc.stats, N, ch));   // release: ordered after this thread's two atomics
+                if (last) {   // the head reads these behind the grid barrier below: plain fp64 accumulators, one 128-byte line each
+                    double *acc = Lc.stats + 2 * N;
+                    atomicAdd(acc + (size_t)ch * kStatStride, (double)sm);
+                    atomicAdd(acc + (size_t)(N + ch) * kStatStride, (double)sqq);
+                } else if (!cs_fx_contribute(Lc.stats, N, ch, (P.dbg & 1) ? 0.f : sm, (P.dbg & 1) ? 0.f : sqq)) {
+                    sBad = 1;
+                }
             }
             if (last) {   // (cloud, slot) partial extrema; slot = this CTA's rank among the CTAs that touch the cloud
                 const int S = P.slots_per_cloud;
@@ -691,6 +770,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         mx = fmaxf(mx, sPmax[(gg * kCsMaxSeg + s) * 128 + c]);
                         mn = fminf(mn, sPmin[(gg * kCsMaxSeg + s) * 128 + c]);
                     }
+                    if (sBad) { mx = INFINITY; mn = -INFINITY; }   // a statistics partial left the fixed-point range: the pooled feature becomes +-Inf
+                                                                     // (fmaxf would drop a NaN) and the head's BatchNorm turns that into NaN rows
                     P.tile_max[((size_t)cl * S + slot) * N + c] = mx;
                     P.tile_min[((size_t)cl * S + slot) * N + c] = mn;
                     // the CTA that holds a cloud's last point also fills the slots no CTA owns
@@ -723,6 +804,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // every commit has been observed through bar_acc; tensor memory is released at the end of the kernel (off the head's critical path)
     cs_fence_before();
     __syncthreads();
+    CS_TS(35);
 
     // ================================================================================================================
     // Fused tail: max-pool finalise + FC head (samplenet.py:97-104) on the CTAs of the grid.  Each FC layer's output channels
@@ -755,9 +837,23 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     if (tid == 0) {
         for (int l = 0; l < H.num_fc; l++) mbar_init(&hbar[l], 1);
         fence_mbar_init();
+        fence_proxy_async();   // the smem region was written through the generic proxy by the conv stack (every thread is past the CTA barrier above)
+        int woff = 0;
+        for (int l = 0; l < H.num_fc; l++) {
+            const HeadLayer &L = H.fc[l];
+            const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
+            const int lo = blockIdx.x * cpc, hi = min(L.c_out, lo + cpc);
+            const bool tma_ok = (L.c_in & 3) == 0 && (hcmax & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
+            if (lo < hi && tma_ok) {
+                const uint32_t bytes = (uint32_t)min(8, hi - lo) * L.c_in * 4u;
+                mbar_expect_tx(&hbar[l], bytes);
+                tma_load_1d(s_wall + woff, L.weight + (size_t)lo * L.c_in, bytes, &hbar[l]);
+            }
+            woff += 8 * L.c_in;
+        }
     }
-    // (the TMA requests themselves are issued after the pooling phase below: thread 0 owns a pooled element too, and every consumer of the
-    //  pooled feature waits for the slowest element)
+    // (the pooled feature below is computed by the CTAs at the TOP of the grid, the FC layers by the CTAs at the bottom: the thread that issues
+    //  these requests has no pooled element to wait for at the headline size)
     // In training mode the last layer's statistics barrier already ordered every CTA's extrema before this point; in eval mode
     // no grid barrier has been crossed yet.
     if (!(need_stats && P.L[P.num_layers - 1].has_bn)) cs_grid_barrier(P.barrier, ++barrier_epoch * G);
@@ -767,7 +863,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     // ---- phase P: pooled feature, spread over the grid
     {
         const int total = H.b * H.c_feat;
-        const int gt = blockIdx.x * kCsThreadsAll + tid, gn = G * kCsThreadsAll;
+        const int gt = (G - 1 - (int)blockIdx.x) * kCsThreadsAll + tid, gn = G * kCsThreadsAll;
         float *ll0 = H.ll[0];
         for (int e = gt; e < total; e += gn) {
             const int bi = e / H.c_feat, c = e % H.c_feat;
@@ -815,22 +911,6 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     }
     CS_TS(37);
     __syncthreads();   // mbarrier inits visible; every thread of this CTA is done with the conv stack's shared memory
-    if (tid == 0) {
-        fence_proxy_async();   // the smem region was written through the generic proxy by the conv stack
-        int woff = 0;
-        for (int l = 0; l < H.num_fc; l++) {
-            const HeadLayer &L = H.fc[l];
-            const int cpc = max(8, (((L.c_out + G - 1) / G + 7) / 8) * 8);
-            const int lo = blockIdx.x * cpc, hi = min(L.c_out, lo + cpc);
-            const bool tma_ok = (L.c_in & 3) == 0 && (hcmax & 3) == 0 && (reinterpret_cast<uintptr_t>(L.weight) & 15) == 0;
-            if (lo < hi && tma_ok) {
-                const uint32_t bytes = (uint32_t)min(8, hi - lo) * L.c_in * 4u;
-                mbar_expect_tx(&hbar[l], bytes);
-                tma_load_1d(s_wall + woff, L.weight + (size_t)lo * L.c_in, bytes, &hbar[l]);
-            }
-            woff += 8 * L.c_in;
-        }
-    }
     CS_TS(38);
 
     int woff = 0;
@@ -854,11 +934,13 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             // per-channel parameters of the channel this warp will finish (warps 0..7): loads start now
             const int cw = cb + (warp & 7);
             const bool cvw = warp < 8 && (warp & 7) < nch;
-            const float pbias = (cvw && L.bias) ? __ldg(L.bias + cw) : 0.f;
-            const float pgam = (cvw && L.has_bn) ? __ldg(L.gamma + cw) : 1.f;
-            const float pbet = (cvw && L.has_bn) ? __ldg(L.beta + cw) : 0.f;
-            const float prm = (cvw && L.has_bn && L.run_mean) ? L.run_mean[cw] : 0.f;
-            const float prv = (cvw && L.has_bn && L.run_var) ? L.run_var[cw] : 1.f;
+            // (volatile loads: the compiler would otherwise sink them to their first use, behind the layer's math, and put an L2 round trip
+            //  on the chain between two layers)
+            const float pbias = (cvw && L.bias) ? cs_ld_now(L.bias + cw) : 0.f;
+            const float pgam = (cvw && L.has_bn) ? cs_ld_now(L.gamma + cw) : 1.f;
+            const float pbet = (cvw && L.has_bn) ? cs_ld_now(L.beta + cw) : 0.f;
+            const float prm = (cvw && L.has_bn && L.run_mean) ? cs_ld_now(L.run_mean + cw) : 0.f;
+            const float prv = (cvw && L.has_bn && L.run_var) ? cs_ld_now(L.run_var + cw) : 1.f;
             if (cb != c_lo || !w_tma) {   // (the first group of every layer was fetched by TMA at the start of the head)
                 __syncthreads();
                 cs_head_stage_weights(L, cb, nch, s_wh, tid, producer);
@@ -932,7 +1014,11 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         const float *wq = s_wh + cq * c_in;
                         float a4[4] = {0.f, 0.f, 0.f, 0.f};
                         int k = k_lo;
-                        if ((c_in & 3) == 0) {
+                        if ((c_in & 3) == 0 && k_hi - k_lo == kr && (kr == 32 || kr == 16)) {   // the common widths (256, 128): fully unrolled, every
+                            if (kr == 32) cs_head_dot<32>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);   // load in flight before the first FMA
+                            else cs_head_dot<16>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);            // (same summation order as the loop below)
+                            k = k_hi;
+                        } else if ((c_in & 3) == 0) {
                             for (; k + 4 <= k_hi; k += 4) {
                                 const float *xr = s_in + lane * (c_in + 1) + k;
                                 const float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
@@ -1098,6 +1184,7 @@ bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
     const int ppc = cs_points_per_cta(total);
     if (ppc > kCsMaxPts) return false;
     if ((ppc - 1) / n + 2 > kCsMaxSeg) return false;   // clouds one CTA may touch
+    if ((total + ppc - 1) / ppc > 255) return false;    // the statistics words count arrivals in one byte
     return true;
 }
 
@@ -1128,7 +1215,9 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     if (head) {
         P.H.tiles_per_cloud = P.slots_per_cloud;
         P.H.stat_rep = 1;
-        for (int i = 0; i < P.H.ru_num; i++) P.H.ru_rep[i] = (P.H.ru_stats[i] == stats[0]) ? 0 : 1;   // layer 1's statistics are analytic (canonical only)
+        // running statistics at the end of the head: the canonical [2C] blocks CTA 0 wrote on the way (ordered by the last layer's grid barrier),
+        // except for the last layer, whose accumulators are read in place
+        for (int i = 0; i < P.H.ru_num; i++) P.H.ru_rep[i] = (P.H.ru_stats[i] == stats[nconv - 1]) ? 1 : 0;
     }
     size_t smem = (size_t)kCsRing * kCsSlotBytes + 1024;
     if (head) {   // the fused tail reuses the same dynamic shared memory: input tile + partial sums + 8 weight rows

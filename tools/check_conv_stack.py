@@ -7,7 +7,7 @@ import samplenet_b200 as sb
 
 torch.manual_seed(0)
 ok = True
-QUICK = os.environ.get("SNB200_CS_DEBUG", "0") != "0"
+QUICK = os.environ.get("SNB200_CS_DEBUG", "0") != "0" or os.environ.get("CS_QUICK", "0") != "0"
 for (b, n, m, train) in ([] if QUICK else [(32, 1024, 64, True), (2, 1024, 64, True), (7, 1000, 64, True), (37, 1024, 64, True), (3, 77, 32, True), (70, 500, 64, True),
                          (32, 1024, 64, False), (5, 333, 32, False), (32, 1024, 32, True), (2, 2048, 64, True), (64, 512, 64, False)]):
     net = sb.SampleNet(m, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda()
@@ -41,7 +41,7 @@ for (b, n, m, train) in ([] if QUICK else [(32, 1024, 64, True), (2, 1024, 64, T
 print("ALL OK" if ok else "FAILED")
 
 net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda().train()
-x = torch.rand(32, 1024, 3, device="cuda") - 0.5
+x = torch.rand(int(os.environ.get("CS_TL_B", "32")), 1024, 3, device="cuda") - 0.5   # (CS_TL_B=28: 128 CTAs, none partially filled)
 conv, fc = net._layer_specs()
 with torch.no_grad():
     for _ in range(5):
@@ -54,7 +54,7 @@ with torch.no_grad():
     for l in range(4):
         for i, nm in enumerate(["layer start", "scale/shift", "operand stored/issued", "acc ready", "D loaded + stats", "atomics/pool out", "grid barrier done", "(barrier arrive issued)"]):
             names[3 + l * 8 + i] = "L%d %s" % (l + 2, nm)
-    names[36] = "head: start"; names[37] = "head: pooled"
+    names[35] = "conv stack left (CTA barrier)"; names[36] = "head: start"; names[37] = "head: pooled"
     for l in range(4):
         for i, nm in enumerate(["start", "input staged", "partials done", "combined", "BN scale/shift", "stored"]):
             names[39 + l * 6 + i] = "FC%d %s" % (l + 1, nm)
