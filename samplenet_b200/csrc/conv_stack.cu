@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 const uint32_t sbase = smem_u32(smem_raw) + slot * slot_bytes;
 #pragma unroll
                 for (int i = 0; i < 8; i++) adr[i] = sbase + toff[i];
+                if (!last) CS_TS(3 + (l - 1) * 8 + 7);
                 cs_write_chunk(v, sc, sh, Lp.relu ? 0.f : -INFINITY, npt, adr);
                 cs_fence_before();     // this thread's tcgen05.ld of the previous accumulator are complete (wait::ld) and ordered
                 fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
@@ -948,105 +949,113 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             float yv[8];                                              // finished pre-activation: row group g, lane = row, warp = channel
 #pragma unroll
             for (int gq = 0; gq < 8; gq++) yv[gq] = 0.f;
-#pragma unroll
-            for (int gq = 0; gq < 8; gq++) {
-                if (gq < nrg) {
-                    const int r0 = gq * 32, rn = min(32, H.b - r0);
-                    if (gq > 0 || cb != c_lo || l > 0) __syncthreads();   // the previous user of s_in / s_part is done
-                    if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride (conflict-free lane = row reads).  Lanes run
-                                      // along k (coalesced 16-byte loads), a thread's loads are requested together and re-requested
-                                      // until every word is present.
-                        const int ldi = c_in + 1;
-                        if ((c_in & 3) == 0) {
-                            const int q4 = c_in >> 2, items = 32 * q4;           // item = (row, 4 channels) = one 16-byte load
-                            for (int i0 = tid; i0 < items; i0 += kCsProducers * 4) {
-                                uint4 v[4];
-                                unsigned spin = 0;
-                                bool ok;
-                                do {
-                                    ok = true;
-#pragma unroll
-                                    for (int u = 0; u < 4; u++) {
-                                        const int i = i0 + u * kCsProducers;
-                                        const int r = i / q4, kq = i - r * q4;
-                                        if (i < items && r < rn) v[u] = cs_xchg_load4(llsrc + (size_t)(r0 + r) * c_in + 4 * kq);
-                                        else v[u] = make_uint4(1u, 1u, 1u, 1u);
-                                    }
-#pragma unroll
-                                    for (int u = 0; u < 4; u++) ok = ok && v[u].x != 0u && v[u].y != 0u && v[u].z != 0u && v[u].w != 0u;
-                                    if (++spin > (1u << 24)) __trap();
-                                } while (!ok);
+            // one row group (32 batch rows) of this channel group: stage the rows, partial products, fixed-order combine.  The common case (a batch
+            // of at most 32 rows) runs ONE compact copy of this code; the 8-way unrolled form exists only for larger batches.  This kernel executes
+            // every instruction of the head once per launch, so its pace is set by instruction fetch (ncu: 17 % of the warp samples are
+            // "no instruction", almost all at branch targets), and seven skipped copies per FC layer are seven jumps to cold cache lines
+            auto row_group = [&](const int gq, float &yout) {
+                const int r0 = gq * 32, rn = min(32, H.b - r0);
+                if (gq > 0 || cb != c_lo || l > 0) __syncthreads();   // the previous user of s_in / s_part is done
+                if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride (conflict-free lane = row reads).  Lanes run
+                                  // along k (coalesced 16-byte loads), a thread's loads are requested together and re-requested
+                                  // until every word is present.
+                    const int ldi = c_in + 1;
+                    if ((c_in & 3) == 0) {
+                        const int q4 = c_in >> 2, items = 32 * q4;           // item = (row, 4 channels) = one 16-byte load
+                        for (int i0 = tid; i0 < items; i0 += kCsProducers * 4) {
+                            uint4 v[4];
+                            unsigned spin = 0;
+                            bool ok;
+                            do {
+                                ok = true;
 #pragma unroll
                                 for (int u = 0; u < 4; u++) {
                                     const int i = i0 + u * kCsProducers;
-                                    if (i < items) {
-                                        const int r = i / q4, kq = i - r * q4;
-                                        float *d = s_in + r * ldi + 4 * kq;
-                                        const bool live = r < rn;
-                                        d[0] = live ? __uint_as_float(v[u].x) : 0.f; d[1] = live ? __uint_as_float(v[u].y) : 0.f;
-                                        d[2] = live ? __uint_as_float(v[u].z) : 0.f; d[3] = live ? __uint_as_float(v[u].w) : 0.f;
-                                    }
+                                    const int r = i / q4, kq = i - r * q4;
+                                    if (i < items && r < rn) v[u] = cs_xchg_load4(llsrc + (size_t)(r0 + r) * c_in + 4 * kq);
+                                    else v[u] = make_uint4(1u, 1u, 1u, 1u);
                                 }
-                            }
-                        } else {
-                            for (int e = tid; e < 32 * c_in; e += kCsProducers) {
-                                const int r = e / c_in, k = e - r * c_in;
-                                float xv = 0.f;
-                                if (r < rn) {
-                                    unsigned q, spin = 0;
-                                    do {
-                                        q = cs_xchg_load1(llsrc + (size_t)(r0 + r) * c_in + k);
-                                        if (++spin > (1u << 24)) __trap();
-                                    } while (q == 0u);
-                                    xv = __uint_as_float(q);
-                                }
-                                s_in[r * ldi + k] = xv;
-                            }
-                        }
-                    }
-                    if (cb == c_lo && gq == 0 && w_tma) mbar_wait(&hbar[l], 0);   // this layer's first weight rows have landed
-                    __syncthreads();
-                    CS_TS(39 + l * 6 + 1);
-                    if (producer) {   // warp -> (channel quad = warp & 1, K eighth = warp >> 1); lane = row
-                        const int cq = (warp & 1) * 4, k8 = warp >> 1;
-                        const int kr = ((c_in + 31) / 32) * 4;            // K per eighth, multiple of 4
-                        const int k_lo = min(c_in, k8 * kr), k_hi = min(c_in, k_lo + kr);
-                        const float *wq = s_wh + cq * c_in;
-                        float a4[4] = {0.f, 0.f, 0.f, 0.f};
-                        int k = k_lo;
-                        if ((c_in & 3) == 0 && k_hi - k_lo == kr && (kr == 32 || kr == 16)) {   // the common widths (256, 128): fully unrolled, every
-                            if (kr == 32) cs_head_dot<32>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);   // load in flight before the first FMA
-                            else cs_head_dot<16>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);            // (same summation order as the loop below)
-                            k = k_hi;
-                        } else if ((c_in & 3) == 0) {
-                            for (; k + 4 <= k_hi; k += 4) {
-                                const float *xr = s_in + lane * (c_in + 1) + k;
-                                const float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const float4 wv = *reinterpret_cast<const float4 *>(wq + j * c_in + k);
-                                    a4[j] = fmaf(x3, wv.w, fmaf(x2, wv.z, fmaf(x1, wv.y, fmaf(x0, wv.x, a4[j]))));
+                                for (int u = 0; u < 4; u++) ok = ok && v[u].x != 0u && v[u].y != 0u && v[u].z != 0u && v[u].w != 0u;
+                                if (++spin > (1u << 24)) __trap();
+                            } while (!ok);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int i = i0 + u * kCsProducers;
+                                if (i < items) {
+                                    const int r = i / q4, kq = i - r * q4;
+                                    float *d = s_in + r * ldi + 4 * kq;
+                                    const bool live = r < rn;
+                                    d[0] = live ? __uint_as_float(v[u].x) : 0.f; d[1] = live ? __uint_as_float(v[u].y) : 0.f;
+                                    d[2] = live ? __uint_as_float(v[u].z) : 0.f; d[3] = live ? __uint_as_float(v[u].w) : 0.f;
                                 }
                             }
                         }
-                        for (; k < k_hi; k++) {
-                            const float xv = s_in[lane * (c_in + 1) + k];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) a4[j] = fmaf(xv, wq[j * c_in + k], a4[j]);
+                    } else {
+                        for (int e = tid; e < 32 * c_in; e += kCsProducers) {
+                            const int r = e / c_in, k = e - r * c_in;
+                            float xv = 0.f;
+                            if (r < rn) {
+                                unsigned q, spin = 0;
+                                do {
+                                    q = cs_xchg_load1(llsrc + (size_t)(r0 + r) * c_in + k);
+                                    if (++spin > (1u << 24)) __trap();
+                                } while (q == 0u);
+                                xv = __uint_as_float(q);
+                            }
+                            s_in[r * ldi + k] = xv;
                         }
-#pragma unroll
-                        for (int j = 0; j < 4; j++) s_part[(k8 * 8 + cq + j) * 32 + lane] = a4[j];
-                    }
-                    __syncthreads();
-                    CS_TS(39 + l * 6 + 2);
-                    if (warp < 8)   // fixed-order combination of the 8 K eighths: warp = channel, lane = row
-                    {
-                        float t = 0.f;
-#pragma unroll
-                        for (int e8 = 0; e8 < 8; e8++) t += s_part[(e8 * 8 + warp) * 32 + lane];
-                        yv[gq] = t;
                     }
                 }
+                if (cb == c_lo && gq == 0 && w_tma) mbar_wait(&hbar[l], 0);   // this layer's first weight rows have landed
+                __syncthreads();
+                CS_TS(39 + l * 6 + 1);
+                if (producer) {   // warp -> (channel quad = warp & 1, K eighth = warp >> 1); lane = row
+                    const int cq = (warp & 1) * 4, k8 = warp >> 1;
+                    const int kr = ((c_in + 31) / 32) * 4;            // K per eighth, multiple of 4
+                    const int k_lo = min(c_in, k8 * kr), k_hi = min(c_in, k_lo + kr);
+                    const float *wq = s_wh + cq * c_in;
+                    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+                    int k = k_lo;
+                    if ((c_in & 3) == 0 && k_hi - k_lo == kr && (kr == 32 || kr == 16)) {   // the common widths (256, 128): fully unrolled, every
+                        if (kr == 32) cs_head_dot<32>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);   // load in flight before the first FMA
+                        else cs_head_dot<16>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);            // (same summation order as the loop below)
+                        k = k_hi;
+                    } else if ((c_in & 3) == 0) {
+                        for (; k + 4 <= k_hi; k += 4) {
+                            const float *xr = s_in + lane * (c_in + 1) + k;
+                            const float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float4 wv = *reinterpret_cast<const float4 *>(wq + j * c_in + k);
+                                a4[j] = fmaf(x3, wv.w, fmaf(x2, wv.z, fmaf(x1, wv.y, fmaf(x0, wv.x, a4[j]))));
+                            }
+                        }
+                    }
+                    for (; k < k_hi; k++) {
+                        const float xv = s_in[lane * (c_in + 1) + k];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) a4[j] = fmaf(xv, wq[j * c_in + k], a4[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) s_part[(k8 * 8 + cq + j) * 32 + lane] = a4[j];
+                }
+                __syncthreads();
+                CS_TS(39 + l * 6 + 2);
+                if (warp < 8)   // fixed-order combination of the 8 K eighths: warp = channel, lane = row
+                {
+                    float t = 0.f;
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; e8++) t += s_part[(e8 * 8 + warp) * 32 + lane];
+                    yout = t;
+                }
+            };
+            if (nrg == 1) {
+                row_group(0, yv[0]);
+            } else {
+#pragma unroll
+                for (int gq = 0; gq < 8; gq++)
+                    if (gq < nrg) row_group(gq, yv[gq]);
             }
             CS_TS(39 + l * 6 + 3);
             if (cvw) {

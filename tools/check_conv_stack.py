@@ -52,7 +52,7 @@ with torch.no_grad():
     ts = list(buf); t0 = ts[0]
     names = {0: "start", 1: "setup done", 2: "moments + barrier done"}
     for l in range(4):
-        for i, nm in enumerate(["layer start", "scale/shift", "operand stored/issued", "acc ready", "D loaded + stats", "atomics/pool out", "grid barrier done", "(barrier arrive issued)"]):
+        for i, nm in enumerate(["layer start", "scale/shift", "operand stored/issued", "acc ready", "D loaded + stats", "atomics/pool out", "grid barrier done", "(ring slot free: operand write starts; last layer: barrier arrive issued)"]):
             names[3 + l * 8 + i] = "L%d %s" % (l + 2, nm)
     names[35] = "conv stack left (CTA barrier)"; names[36] = "head: start"; names[37] = "head: pooled"
     for l in range(4):
