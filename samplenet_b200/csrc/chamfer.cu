@@ -87,25 +87,33 @@ struct ChamferBwdDir {
     const int *idx_other;    // (b, nt) index into own
     float *grad_own;         // (b, no, 3)
     int no, nt, tiles;
+    int lanes;               // threads per owned point: 1 or 32
 };
 struct ChamferBwdParams {
     ChamferBwdDir d[2];
 };
 
+// S = D.lanes threads share one owned point (S = 32 when a direction has few owners and a long index array to scan -- the 64 generated
+// points against 1024 input points at the headline size: one thread per owner would leave 64 threads walking 1024 entries each): lane s
+// scans entries s, s + S, ... and the partial sums are combined by a fixed shuffle tree, so the result stays bit-reproducible.
 __device__ __forceinline__ void chamfer_bwd_dir(const ChamferBwdDir &D, int tile, int bi, int *s_idx, float *s_g)
 {
-    const int j = tile * kBwdThreads + threadIdx.x;
+    const int S = D.lanes;
+    const int j = tile * (kBwdThreads / S) + (int)threadIdx.x / S;
+    const int sl = (int)threadIdx.x % S;
     const bool live = j < D.no;
     const float *own = D.own + (size_t)bi * D.no * 3;
     const float *oth = D.other + (size_t)bi * D.nt * 3;
     float ax = 0, ay = 0, az = 0, gx = 0, gy = 0, gz = 0;
     if (live) {
         ax = own[j * 3 + 0]; ay = own[j * 3 + 1]; az = own[j * 3 + 2];
-        const int j2 = D.idx_own[(size_t)bi * D.no + j];
-        const float g = D.g_own[(size_t)bi * D.no + j] * 2;
-        gx = g * (ax - oth[j2 * 3 + 0]);
-        gy = g * (ay - oth[j2 * 3 + 1]);
-        gz = g * (az - oth[j2 * 3 + 2]);
+        if (sl == 0) {
+            const int j2 = D.idx_own[(size_t)bi * D.no + j];
+            const float g = D.g_own[(size_t)bi * D.no + j] * 2;
+            gx = g * (ax - oth[j2 * 3 + 0]);
+            gy = g * (ay - oth[j2 * 3 + 1]);
+            gz = g * (az - oth[j2 * 3 + 2]);
+        }
     }
     for (int t0 = 0; t0 < D.nt; t0 += kBwdTile) {
         const int tn = min(kBwdTile, D.nt - t0);
@@ -116,8 +124,8 @@ __device__ __forceinline__ void chamfer_bwd_dir(const ChamferBwdDir &D, int tile
         }
         __syncthreads();
         if (live) {
-            for (int i = 0; i < tn; i++) {
-                if (s_idx[i] == j) {  // rare: on average nt/no hits per thread
+            for (int i = sl; i < tn; i += S) {
+                if (s_idx[i] == j) {  // rare: on average nt/no hits per owner
                     const float g = s_g[i] * 2;
                     gx -= g * (oth[(t0 + i) * 3 + 0] - ax);
                     gy -= g * (oth[(t0 + i) * 3 + 1] - ay);
@@ -126,7 +134,15 @@ __device__ __forceinline__ void chamfer_bwd_dir(const ChamferBwdDir &D, int tile
             }
         }
     }
-    if (live) {
+    if (S > 1) {   // (S = 32: a warp per owner; every lane of the warp takes part, live or not)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gx += __shfl_down_sync(kFullMask, gx, o);
+            gy += __shfl_down_sync(kFullMask, gy, o);
+            gz += __shfl_down_sync(kFullMask, gz, o);
+        }
+    }
+    if (live && sl == 0) {
         float *go = D.grad_own + ((size_t)bi * D.no + j) * 3;
         go[0] = gx; go[1] = gy; go[2] = gz;
     }
@@ -146,8 +162,9 @@ int launch_chamfer_backward(int b, int n, const float *xyz1, int m, const float 
                             const float *grad_dist2, const int *idx2, float *grad_xyz1, float *grad_xyz2, cudaStream_t stream)
 {
     ChamferBwdParams P;
-    P.d[0] = {xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, n, m, (n + kBwdThreads - 1) / kBwdThreads};
-    P.d[1] = {xyz2, xyz1, grad_dist2, idx2, grad_dist1, idx1, grad_xyz2, m, n, (m + kBwdThreads - 1) / kBwdThreads};
+    const int s1 = (n <= 256 && m >= 128) ? 32 : 1, s2 = (m <= 256 && n >= 128) ? 32 : 1;
+    P.d[0] = {xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, n, m, (n * s1 + kBwdThreads - 1) / kBwdThreads, s1};
+    P.d[1] = {xyz2, xyz1, grad_dist2, idx2, grad_dist1, idx1, grad_xyz2, m, n, (m * s2 + kBwdThreads - 1) / kBwdThreads, s2};
     dim3 grid(P.d[0].tiles + P.d[1].tiles, b);
     chamfer_backward_kernel<<<grid, kBwdThreads, 0, stream>>>(P);
     return check_launch("nn_distance_backward");
