@@ -49,6 +49,22 @@ struct FcBwdParams {
     float *g_weight, *g_bias, *g_gamma, *g_beta;   // (c_out, c_in), (c_out), (c_out), (c_out); any may be null
 };
 
+// (rows, cols) row-major global -> shared memory with row stride ld, 8 independent loads per thread and pass
+__device__ __forceinline__ void fcb_stage(float *dst, int ld, const float *__restrict__ src, int rows, int cols, int tid)
+{
+    const int total = rows * cols;
+    for (int e0 = tid; e0 < total; e0 += kFcbThreads * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int e = e0 + u * kFcbThreads; v[u] = e < total ? __ldg(src + e) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * kFcbThreads;
+            if (e < total) { const int r = e / cols, k = e - r * cols; dst[r * ld + k] = v[u]; }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kFcbThreads) fc_bwd_kernel(const __grid_constant__ FcBwdParams P)
 {
     extern __shared__ __align__(16) float fsm[];
@@ -59,18 +75,30 @@ __global__ void __launch_bounds__(kFcbThreads) fc_bwd_kernel(const __grid_consta
     float *sWr = sU + (size_t)(P.dz_up ? b * (P.c_up + 1) : 0);   // [8][I] this CTA's weight rows
     const int c = blockIdx.x * 8 + warp;               // the channel of this warp
     const bool cv = c < O;
-    for (int e = tid; e < b * I; e += kFcbThreads) { const int r = e / I, k = e - r * I; sA[r * (I + 1) + k] = P.a_in[e]; }
-    if (P.dz_up) for (int e = tid; e < b * P.c_up; e += kFcbThreads) { const int r = e / P.c_up, u = e - r * P.c_up; sU[r * (P.c_up + 1) + u] = P.dz_up[e]; }
-    for (int e = tid; e < 8 * I; e += kFcbThreads) { const int j = e / I, k = e - j * I; const int cc = blockIdx.x * 8 + j; sWr[e] = cc < O ? P.weight[(size_t)cc * I + k] : 0.f; }
+    float *sWu = sWr + 8 * I + warp * (P.dz_up ? P.c_up : 0);   // this warp's column of the upper layer's weight: w_up[u][c], u < c_up
+    if (P.dz_up && cv) {   // (this warp's own region: filled before the CTA barrier, in flight together with the staging loads)
+        for (int u0 = lane; u0 < P.c_up; u0 += 32 * 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const int u = u0 + 32 * j; v[j] = u < P.c_up ? __ldg(P.w_up + (size_t)u * O + c) : 0.f; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const int u = u0 + 32 * j; if (u < P.c_up) sWu[u] = v[j]; }
+        }
+        __syncwarp();
+    }
+    // staging: every load of a thread is in flight before its first store (one load -> one store per iteration cost an L2 round trip each:
+    // ncu put 60 % of this kernel's stall samples on these stores)
+    fcb_stage(sA, I + 1, P.a_in, b, I, tid);
+    if (P.dz_up) fcb_stage(sU, P.c_up + 1, P.dz_up, b, P.c_up, tid);
+    {
+        const int rows = min(8, O - (int)blockIdx.x * 8);
+        fcb_stage(sWr, I, P.weight + (size_t)blockIdx.x * 8 * I, rows, I, tid);
+        for (int e = rows * I + tid; e < 8 * I; e += kFcbThreads) sWr[e] = 0.f;
+    }
     __syncthreads();
     if (!cv) return;
     // rows r = lane, lane + 32 (b <= 64)
     float dout[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
-    float *sWu = sWr + 8 * I + warp * (P.dz_up ? P.c_up : 0);   // this warp's column of the upper layer's weight: w_up[u][c], u < c_up
-    if (P.dz_up) {
-        for (int u = lane; u < P.c_up; u += 32) sWu[u] = __ldg(P.w_up + (size_t)u * O + c);
-        __syncwarp();
-    }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int r = lane + 32 * h;
@@ -192,9 +220,13 @@ __global__ void __launch_bounds__(1024) pool_bwd_kernel(const __grid_constant__ 
     float best = -INFINITY; int bi = 0x7fffffff;
     if (c < C) {
         const float *zc = P.z + (size_t)cloud * P.n * C + c;
-        for (int p = grp; p < P.n; p += 8) {
-            const float y = sgn * zc[(size_t)p * C];
-            if (y > best) { best = y; bi = p; }
+        for (int p0 = grp; p0 < P.n; p0 += 64) {   // 8 of this thread's points per pass: the loads are independent, the compares stay in point order
+            float y8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int p = p0 + 8 * u; y8[u] = p < P.n ? sgn * __ldg(zc + (size_t)p * C) : -INFINITY; }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (y8[u] > best) { best = y8[u]; bi = p0 + 8 * u; }
         }
     }
     __syncthreads();
@@ -456,17 +488,36 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(const __grid_constant__ 
             if (blockIdx.x == 0 && warp == 0) { if (Q.g_gamma) Q.g_gamma[c] = (float)Q.s12[C + c]; if (Q.g_beta) Q.g_beta[c] = (float)Q.s12[c]; }
         }
     }
-    for (long long p = (long long)blockIdx.x * 8 + warp; p < Q.P; p += (long long)gridDim.x * 8) {
-        float x0, x1, x2;
-        if (Q.layout == SNB200_BNC) { x0 = Q.x[p * 3 + 0]; x1 = Q.x[p * 3 + 1]; x2 = Q.x[p * 3 + 2]; }
-        else { const long long cl = p / Q.n, pi = p - cl * Q.n; x0 = Q.x[(cl * 3 + 0) * Q.n + pi]; x1 = Q.x[(cl * 3 + 1) * Q.n + pi]; x2 = Q.x[(cl * 3 + 2) * Q.n + pi]; }
+    // 4 of this warp's points per pass: their loads are issued together (the loop is a chain of HBM round trips otherwise), the
+    // accumulation stays in point order
+    const long long pstride = (long long)gridDim.x * 8;
+    for (long long pb = (long long)blockIdx.x * 8 + warp; pb < Q.P; pb += 4 * pstride) {
+        float xs[4][3], zs[4][4], ds[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int c = lane + 32 * u;
-            if (c < C) {
-                const float z = Q.z[p * C + c], dy = Q.dy[p * C + c];
-                const float dz = coef[u] * (dy - m1[u] - (z - mean[u]) * inv[u] * m2[u]);
-                acc[u][0] = fmaf(dz, x0, acc[u][0]); acc[u][1] = fmaf(dz, x1, acc[u][1]); acc[u][2] = fmaf(dz, x2, acc[u][2]); acc[u][3] += dz;
+        for (int j = 0; j < 4; j++) {
+            const long long p = pb + j * pstride;
+            const bool in = p < Q.P;
+            const long long pc = in ? p : 0;
+            if (Q.layout == SNB200_BNC) { xs[j][0] = Q.x[pc * 3 + 0]; xs[j][1] = Q.x[pc * 3 + 1]; xs[j][2] = Q.x[pc * 3 + 2]; }
+            else { const long long cl = pc / Q.n, pi = pc - cl * Q.n; xs[j][0] = Q.x[(cl * 3 + 0) * Q.n + pi]; xs[j][1] = Q.x[(cl * 3 + 1) * Q.n + pi]; xs[j][2] = Q.x[(cl * 3 + 2) * Q.n + pi]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c = lane + 32 * u;
+                const bool ok = in && c < C;
+                zs[j][u] = ok ? __ldg(Q.z + pc * C + c) : 0.f;
+                ds[j][u] = ok ? __ldg(Q.dy + pc * C + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (pb + j * pstride < Q.P) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (lane + 32 * u < C) {
+                        const float dz = coef[u] * (ds[j][u] - m1[u] - (zs[j][u] - mean[u]) * inv[u] * m2[u]);
+                        acc[u][0] = fmaf(dz, xs[j][0], acc[u][0]); acc[u][1] = fmaf(dz, xs[j][1], acc[u][1]); acc[u][2] = fmaf(dz, xs[j][2], acc[u][2]); acc[u][3] += dz;
+                    }
+                }
             }
         }
     }
@@ -487,27 +538,73 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(const __grid_constant__ 
 // gradient = sum over the launch's CTAs of its partial, in CTA order (bit-reproducible)
 struct ReduceJob { const float *part; int nparts; int nw, nb; float *g_weight, *g_bias; };
 struct ReduceParams { int njobs; ReduceJob job[SNB200_MAX_CONV_LAYERS]; };
+// blockIdx.y = job (conv layer).  A CTA = 32 columns x 8 part groups; a column is V consecutive gradient elements (V = 4: one 16-byte load
+// per part), a group sums its contiguous share of the launch's CTA partials in CTA order with 8 loads in flight, the 8 group sums are then
+// added in group order: a fixed order, so the gradients are bit-reproducible.  (One thread per element walking all ~300 parts, as in the
+// first version, had 0.5 MB in flight on the whole GPU and ran at 10 % of HBM bandwidth.)
+constexpr int kRpGroups = 8;
+template <int V>
+__device__ __forceinline__ void reduce_partials_body(const ReduceJob &J, float (*sAcc)[32][4])
+{
+    const int total = J.nw + J.nb, ncol = (total + V - 1) / V;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int per = (J.nparts + kRpGroups - 1) / kRpGroups;
+    const int k0 = min(J.nparts, grp * per), k1 = min(J.nparts, k0 + per);
+    for (int c0 = blockIdx.x * 32; c0 < ncol; c0 += gridDim.x * 32) {
+        const int col = c0 + lane;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        if (col < ncol) {
+            const float *p = J.part + (size_t)col * V;
+            int k = k0;
+            for (; k + 8 <= k1; k += 8) {
+                float v[8][4];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (V == 4) {
+                        const float4 t = __ldcs(reinterpret_cast<const float4 *>(p + (size_t)(k + u) * total));
+                        v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+                    } else {
+                        v[u][0] = __ldcs(p + (size_t)(k + u) * total); v[u][1] = v[u][2] = v[u][3] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+#pragma unroll
+                    for (int i = 0; i < V; i++) s[i] += v[u][i];
+            }
+            for (; k < k1; k++) {
+                if (V == 4) {
+                    const float4 t = __ldcs(reinterpret_cast<const float4 *>(p + (size_t)k * total));
+                    s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
+                } else {
+                    s[0] += __ldcs(p + (size_t)k * total);
+                }
+            }
+        }
+        __syncthreads();   // (the previous column block's sums have been consumed)
+#pragma unroll
+        for (int i = 0; i < 4; i++) sAcc[grp][lane][i] = s[i];
+        __syncthreads();
+        if (grp == 0 && col < ncol) {
+#pragma unroll
+            for (int i = 0; i < V; i++) {
+                float t = 0.f;
+#pragma unroll
+                for (int g = 0; g < kRpGroups; g++) t += sAcc[g][lane][i];
+                const int e = col * V + i;
+                if (e < J.nw) { if (J.g_weight) J.g_weight[e] = t; }
+                else if (e < total && J.g_bias) J.g_bias[e - J.nw] = t;
+            }
+        }
+    }
+}
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const __grid_constant__ ReduceParams R)
 {
-    // blockIdx.y = job (conv layer); one thread per gradient element; the CTAs' partials are pulled 8 at a time (independent loads in flight)
-    // and added in CTA order
+    __shared__ float sAcc[kRpGroups][32][4];
     const ReduceJob &J = R.job[blockIdx.y];
     const int total = J.nw + J.nb;
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
-        const float *p = J.part + e;
-        float s = 0.f;
-        int k = 0;
-        for (; k + 8 <= J.nparts; k += 8) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = __ldcs(p + (size_t)(k + u) * total);
-#pragma unroll
-            for (int u = 0; u < 8; u++) s += v[u];
-        }
-        for (; k < J.nparts; k++) s += __ldcs(p + (size_t)k * total);
-        if (e < J.nw) { if (J.g_weight) J.g_weight[e] = s; }
-        else if (J.g_bias) J.g_bias[e - J.nw] = s;
-    }
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(J.part) & 15) == 0) reduce_partials_body<4>(J, sAcc);
+    else reduce_partials_body<1>(J, sAcc);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host side
@@ -669,7 +766,7 @@ int launch_generator_backward(int b, int n, int layout, const float *x, int ncon
         R.job[l].nw = conv[l].c_out * conv[l].c_in; R.job[l].nb = conv[l].c_out;
         R.job[l].g_weight = gconv[l].weight; R.job[l].g_bias = gconv[l].bias;
     }
-    reduce_partials_kernel<<<dim3(64, nconv), 256, 0, stream>>>(R);
+    reduce_partials_kernel<<<dim3(128, nconv), 256, 0, stream>>>(R);   // 128 x 32 columns x 4 elements = the widest layer in one sweep
     return check_launch("generator backward: reduce");
 }
 

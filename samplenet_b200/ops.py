@@ -237,7 +237,9 @@ class SoftProjectFunction(torch.autograd.Function):
         ctx.sigma_mode, ctx.sigma_floor = int(sigma_mode), float(sigma_floor)
         ctx.save_for_backward(points, query, sig, feats.contiguous() if feats is not None else None, o["idx"], o["weights"])
         proj = o.get("proj"); prop = o.get("prop")
-        ctx.mark_non_differentiable(o["idx"])
+        # weights / dist are returned for inspection (the TF SoftProjection returns them too); only the projection and the propagated features
+        # carry gradients, as in every reference caller -- marked so autograd does not pretend otherwise
+        ctx.mark_non_differentiable(o["idx"], o["weights"], o["dist"])
         ctx.sigma_shape = t.shape
         dev = points.device
         if proj is None:
