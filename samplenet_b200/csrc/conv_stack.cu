@@ -30,6 +30,7 @@
 namespace snb {
 
 constexpr int kCsMaxLayers = SNB200_MAX_CONV_LAYERS;
+constexpr int kCsMaxSlicesPerCta = 16; // 256-point slices one CTA may walk per layer (batches beyond one slice per SM)
 constexpr int kCsProducers = 512;     // 16 producer warps: warp & 3 = TMEM lane quarter (32 channels), warp >> 2 = column (point) group
 constexpr int kCsThreadsAll = kCsProducers;        // (17 warps would cap the kernel at 96 registers: 5 warps on one scheduler)
 constexpr int kCsIssuerWarp = 15;     // the producer warp whose lane 0 also issues the MMAs (q = 3: it owns a K chunk only in 128-wide layers)
@@ -72,6 +73,10 @@ struct CsParams {
     int self_clean;
     char *clean_ptr;
     unsigned clean_bytes;
+    // batches beyond one slice per SM: every CTA walks slices_per_cta slices (slice index = CTA + t * grid) layer by layer; the raw layer outputs
+    // of its own slices travel through act[l & 1] (or the layer's zsave) -- thread-private round trips, no cross-CTA dependency
+    int slices_per_cta, num_slices;
+    float *act[2];
     int dbg;                            // bring-up switches (env SNB200_CS_DEBUG; 0 in the product): 1 = skip the statistics atomics (timing experiments only)
 };
 
@@ -406,6 +411,18 @@ __device__ __forceinline__ void cs_save_rows(float *dst, int ld, const uint32_t 
     }
 }
 
+// ... and back: this thread's channel at its points from a (points x channels) buffer (columns beyond the valid ones read as zero)
+__device__ __forceinline__ void cs_load_rows(const float *src, int ld, uint32_t (&v)[kCsNPT], int npt, int nvalid)
+{
+#pragma unroll
+    for (int jb = 0; jb < kCsNPT / 8; jb++) {
+        if (jb * 8 < npt) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[jb * 8 + i] = (jb * 8 + i < nvalid) ? __float_as_uint(__ldcg(src + (size_t)(jb * 8 + i) * ld)) : 0u;
+        }
+    }
+}
+
 // MMA issue for K chunk c of the current layer (whole warp waits, lane 0 issues): 4 K steps x 3 MMAs (3xTF32), then the commits
 __device__ __forceinline__ void cs_issue_chunk(unsigned char *smem_raw, uint32_t slot_bytes, int ppc, uint32_t tmem0, uint32_t idesc, uint32_t gchunk,
                                                int c, int nchunks, uint64_t *bar_full, uint64_t *bar_ring, uint64_t *bar_acc, int lane)
@@ -439,6 +456,9 @@ __device__ __forceinline__ void cs_issue_chunk(unsigned char *smem_raw, uint32_t
 //   bar_full[s]    producers -> issuer : ring slot s holds a prepared 32-wide K chunk of the B operand      (128 arrivals: one quarter)
 //   bar_ring[s]    tensor core -> producers : the MMAs that read ring slot s have completed (tcgen05.commit)
 //   bar_acc        tensor core -> producers : every MMA of this layer has completed
+// kMulti: more than one 256-point slice per SM (large batches).  The single-slice instantiation keeps a layer's output in registers from
+// one layer to the next; the multi-slice one walks its slices inside every layer and parks the raw outputs in global memory (L2) in between.
+template <bool kMulti>
 __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __grid_constant__ CsParams P)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -477,23 +497,28 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     if (tid == 0) sBad = 0;
     // the points of this CTA and layer 1's weights
     const CsLayer &L1 = P.L[0];
-    if (producer) {
+    // slices of this CTA: slice index = CTA + t * grid (one slice, t = 0, unless kMulti)
+    const int nslices = kMulti ? (P.num_slices - (int)blockIdx.x + G - 1) / G : 1;
+    auto load_x_slice = [&](const long long P0s, const int nptss) {   // the slice's points -> sX (point-major xyz), zero beyond the batch
         if (P.layout == SNB200_BNC) {   // (b, n, 3): the flattened batch is contiguous
-            const float *src = P.x + P0 * 3;
-            const int nf = npts * 3;
+            const float *src = P.x + P0s * 3;
+            const int nf = nptss * 3;
             for (int e = tid; e < ppc * 3; e += kCsProducers) sX[e] = (e < nf) ? __ldg(src + e) : 0.f;
         } else {
             for (int e = tid; e < ppc * 3; e += kCsProducers) {
                 const int c = e / ppc, r = e - c * ppc;    // coalesced along points
-                float v = 0.f;
-                if (r < npts) {
-                    const long long gp = P0 + r;
+                float xv = 0.f;
+                if (r < nptss) {
+                    const long long gp = P0s + r;
                     const int cloud = (int)(gp / n), pi = (int)(gp - (long long)cloud * n);
-                    v = __ldg(P.x + ((size_t)cloud * 3 + c) * n + pi);
+                    xv = __ldg(P.x + ((size_t)cloud * 3 + c) * n + pi);
                 }
-                sX[r * 3 + c] = v;
+                sX[r * 3 + c] = xv;
             }
         }
+    };
+    if (producer) {
+        if (!kMulti) load_x_slice(P0, npts);
         for (int e = tid; e < L1.c_out * 3; e += kCsProducers) sW1[e] = __ldg(L1.weight + e);
         for (int e = tid; e < L1.c_out; e += kCsProducers) sB1[e] = L1.bias ? __ldg(L1.bias + e) : 0.f;
     }
@@ -519,14 +544,26 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
 
     // ---- phase 0: input moments (training + BN after layer 1): 9 sums over this CTA's points, fp64 atomics, grid barrier
     if (need_stats && L1.has_bn) {
+        const int mom_pts = kMulti ? ppc : npts;   // threads that hold a point (of some slice)
         if (producer) {
             float a9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if (tid < npts) {
-                const float px = sX[tid * 3 + 0], py = sX[tid * 3 + 1], pz = sX[tid * 3 + 2];
-                a9[0] = px; a9[1] = py; a9[2] = pz;
-                a9[3] = px * px; a9[4] = px * py; a9[5] = px * pz; a9[6] = py * py; a9[7] = py * pz; a9[8] = pz * pz;
+            for (int t = 0; t < nslices; t++) {
+                int nptss = npts;
+                if (kMulti) {
+                    const long long P0s = (long long)((int)blockIdx.x + t * G) * ppc;
+                    nptss = (int)min((long long)ppc, P.total - P0s);
+                    __syncthreads();
+                    load_x_slice(P0s, nptss);
+                    __syncthreads();
+                }
+                if (tid < nptss) {
+                    const float px = sX[tid * 3 + 0], py = sX[tid * 3 + 1], pz = sX[tid * 3 + 2];
+                    a9[0] += px; a9[1] += py; a9[2] += pz;
+                    a9[3] = fmaf(px, px, a9[3]); a9[4] = fmaf(px, py, a9[4]); a9[5] = fmaf(px, pz, a9[5]);
+                    a9[6] = fmaf(py, py, a9[6]); a9[7] = fmaf(py, pz, a9[7]); a9[8] = fmaf(pz, pz, a9[8]);
+                }
             }
-            if (warp * 32 < npts) {
+            if (warp * 32 < mom_pts) {
 #pragma unroll
                 for (int j = 0; j < 9; j++) {
                     float v = a9[j];
@@ -538,7 +575,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
         __syncthreads();
         if (tid < 9) {   // one thread per moment: this CTA's sum, the grid's accumulator, then the arrival word (release: after the add, and --
             double t = 0.0;   // through the CTA barrier above -- after every thread's share of the self-clean stores)
-            for (int w = 0; w * 32 < npts && w < kCsProducers / 32; w++) t += (double)sMomW[w][tid];
+            for (int w = 0; w * 32 < mom_pts && w < kCsProducers / 32; w++) t += (double)sMomW[w][tid];
             atomicAdd(P.mom + tid, t);
             cs_grid_arrive(reinterpret_cast<unsigned *>(P.mom + 9));
         }
@@ -559,24 +596,28 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
 
     // ---- layer 1 (3 -> C1) on CUDA cores: this thread's channel at its npt points (raw, with bias), kept in registers
     uint32_t v[kCsNPT];   // (float bit patterns: tcgen05.ld writes straight into this array)
-    if (producer && q * 32 < L1.c_out) {
-        const bool cv = ch < L1.c_out;
-        const float w0 = cv ? sW1[ch * 3 + 0] : 0.f, w1 = cv ? sW1[ch * 3 + 1] : 0.f, w2 = cv ? sW1[ch * 3 + 2] : 0.f, b1 = cv ? sB1[ch] : 0.f;
+    auto layer1_eval = [&](const long long P0s, const int nvalids) {   // from the slice staged in sX
+        if (producer && q * 32 < L1.c_out) {
+            const bool cv = ch < L1.c_out;
+            const float w0 = cv ? sW1[ch * 3 + 0] : 0.f, w1 = cv ? sW1[ch * 3 + 1] : 0.f, w2 = cv ? sW1[ch * 3 + 2] : 0.f, b1 = cv ? sB1[ch] : 0.f;
 #pragma unroll
-        for (int jb = 0; jb < kCsNPT / 8; jb++) {
-            if (jb * 8 < npt) {
-                // 8 points = 24 consecutive floats = six 16-byte broadcast reads (col0 and 8 jb are multiples of 8: 96-byte aligned)
-                const float4 *xq = reinterpret_cast<const float4 *>(sX + (col0 + jb * 8) * 3);
-                float xr[24];
+            for (int jb = 0; jb < kCsNPT / 8; jb++) {
+                if (jb * 8 < npt) {
+                    // 8 points = 24 consecutive floats = six 16-byte broadcast reads (col0 and 8 jb are multiples of 8: 96-byte aligned)
+                    const float4 *xq = reinterpret_cast<const float4 *>(sX + (col0 + jb * 8) * 3);
+                    float xr[24];
 #pragma unroll
-                for (int u = 0; u < 6; u++) { const float4 t4 = xq[u]; xr[u * 4 + 0] = t4.x; xr[u * 4 + 1] = t4.y; xr[u * 4 + 2] = t4.z; xr[u * 4 + 3] = t4.w; }
+                    for (int u = 0; u < 6; u++) { const float4 t4 = xq[u]; xr[u * 4 + 0] = t4.x; xr[u * 4 + 1] = t4.y; xr[u * 4 + 2] = t4.z; xr[u * 4 + 3] = t4.w; }
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[jb * 8 + i] = __float_as_uint(fmaf(w2, xr[i * 3 + 2], fmaf(w1, xr[i * 3 + 1], w0 * xr[i * 3 + 0])) + b1);
+                    for (int i = 0; i < 8; i++) v[jb * 8 + i] = __float_as_uint(fmaf(w2, xr[i * 3 + 2], fmaf(w1, xr[i * 3 + 1], w0 * xr[i * 3 + 0])) + b1);
+                }
             }
+            if (L1.zsave && cv) cs_save_rows(L1.zsave + (size_t)(P0s + col0) * L1.c_out + ch, L1.c_out, v, npt, nvalids);
         }
-        if (L1.zsave && cv) cs_save_rows(L1.zsave + (size_t)(P0 + col0) * L1.c_out + ch, L1.c_out, v, npt, nvalid);
-    }
+    };
+    if (!kMulti) layer1_eval(P0, nvalid);
 
+    uint32_t acc_uses = 0;              // completed accumulator phases (bar_acc parity)
     uint32_t gchunk = 0;                // global K-chunk counter (same sequence in producers and issuer): slot = gchunk % kCsRing
     // swizzle: point p's 128-byte row holds its 16-byte group c at position c ^ (p & 7); col0 is a multiple of 8, so p & 7 = j & 7.
     // toff[i]: byte offset inside a ring slot's hi plane of (row col0 + i, this thread's k = lane)
@@ -643,109 +684,169 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             if (issuer) {
                 cs_mbar_wait(&bar_w, (uint32_t)(l - 1) & 1u);   // every thread's slice of this layer's weights is in tensor memory
                 cs_fence_after();
-                for (int c = 0; c < min(nchunks, 3); c++)        // (this warp owns chunk 3)
-                    cs_issue_chunk(smem_raw, slot_bytes, ppc, tmem0, idesc, gchunk, c, nchunks, bar_full, bar_ring, &bar_acc, lane);
             }
-            if (q < nchunks) {
-                const uint32_t gi = gchunk + (uint32_t)q, slot = gi % kCsRing, use = gi / kCsRing;
-                if (use > 0) {   // the MMAs that read this ring slot last time must have completed
-                    cs_mbar_wait(&bar_ring[slot], (use - 1) & 1u);
-                    cs_fence_after();
-                }
-                uint32_t adr[8];
-                const uint32_t sbase = smem_u32(smem_raw) + slot * slot_bytes;
-#pragma unroll
-                for (int i = 0; i < 8; i++) adr[i] = sbase + toff[i];
-                if (!last) CS_TS(3 + (l - 1) * 8 + 7);
-                cs_write_chunk(v, sc, sh, Lp.relu ? 0.f : -INFINITY, npt, adr);
-                cs_fence_before();     // this thread's tcgen05.ld of the previous accumulator are complete (wait::ld) and ordered
-                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
-                cs_mbar_arrive(&bar_full[slot]);
-            }
-            if (issuer && nchunks > 3) cs_issue_chunk(smem_raw, slot_bytes, ppc, tmem0, idesc, gchunk, 3, nchunks, bar_full, bar_ring, &bar_acc, lane);
-            gchunk += (uint32_t)nchunks;
-            CS_TS(3 + (l - 1) * 8 + 2);
-            // (C) while the tensor core works: this layer's bias and the NEXT layer's weight row into registers
             const float bias = (ch < N && Lc.bias) ? __ldg(Lc.bias + ch) : 0.f;
-            if (!last) cs_load_w(P.L[l + 1], ch, g, wreg);
-            // (D) every MMA of this layer has completed
-            cs_mbar_wait(&bar_acc, (uint32_t)(l - 1) & 1u);
-            cs_fence_after();
-            CS_TS(3 + (l - 1) * 8 + 3);
-            // (E) the next layer's weights replace this layer's in tensor memory
-            if (!last) {
-                cs_store_w(tmem_lane, g, P.L[l + 1].c_in >> 2, wreg);
-                cs_fence_before();
-                cs_mbar_arrive(&bar_w);
-            }
-            // (F) the accumulator: lane = channel, this thread's npt columns -> registers (+bias); statistics / extrema on the way
-            const int cl_first = (int)(P0 / n);
-            const int nseg = (int)((P0 + npts - 1) / n) - cl_first + 1;
+            float sumL = 0.f, sqL = 0.f;                                     // (kMulti) this thread's statistics over all of its slices
+            const float *act_in = kMulti && l > 1 ? (Lp.zsave ? Lp.zsave : P.act[(l - 1) & 1]) : nullptr;
+            float *act_out = kMulti && !last ? (Lc.zsave ? Lc.zsave : P.act[l & 1]) : Lc.zsave;
+            // (cloud, slot) partial extrema of one slice (last layer); slot = the slice's rank among the slices that touch the cloud
+            auto write_tiles = [&](const int sl, const int cl_first, const int nseg, const float *sPmax, const float *sPmin) {
+                const int S = P.slots_per_cloud;
+                for (int e = tid; e < nseg * N; e += kCsProducers) {
+                    const int s = e / N, c = e - s * N;
+                    const int cl = cl_first + s;
+                    const int slot = sl - (int)(((long long)cl * n) / ppc);
+                    float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+                    for (int gg = 0; gg < 4; gg++) {
+                        mx = fmaxf(mx, sPmax[(gg * kCsMaxSeg + s) * 128 + c]);
+                        mn = fminf(mn, sPmin[(gg * kCsMaxSeg + s) * 128 + c]);
+                    }
+                    if (sBad) { mx = INFINITY; mn = -INFINITY; }   // a statistics partial left the fixed-point range: the pooled feature becomes +-Inf
+                                                                     // (fmaxf would drop a NaN) and the head's BatchNorm turns that into NaN rows
+                    P.tile_max[((size_t)cl * S + slot) * N + c] = mx;
+                    P.tile_min[((size_t)cl * S + slot) * N + c] = mn;
+                    // the slice that holds a cloud's last point also fills the slots no slice owns
+                    if ((int)((((long long)cl + 1) * n - 1) / ppc) == sl)
+                        for (int s2 = slot + 1; s2 < S; s2++) {
+                            P.tile_max[((size_t)cl * S + s2) * N + c] = -INFINITY;
+                            P.tile_min[((size_t)cl * S + s2) * N + c] = INFINITY;
+                        }
+                }
+            };
+            int cl_first = 0, nseg = 0;
             float *sPmax = reinterpret_cast<float *>(smem_raw);                       // [4 groups][kCsMaxSeg][128]
             float *sPmin = sPmax + 4 * kCsMaxSeg * 128;
-            if (q * 32 < N) {
-#pragma unroll
-                for (int jb = 0; jb < kCsNPT / 8; jb++)
-                    if (jb * 8 < npt) cs_ld8_issue(tmem_lane + (uint32_t)(col0 + jb * 8), v + jb * 8);
-                cs_ld_wait();
-                cs_fence_before();   // the next layer's first MMA overwrites these columns: ordered through the CTA barrier below
-                float sum = 0.f, sq = 0.f;
-                if (nvalid == npt) {   // (every CTA but the last: all columns are real points)
-#pragma unroll
-                    for (int jb = 0; jb < kCsNPT / 8; jb++) {
-                        if (jb * 8 < npt) {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const float u = __uint_as_float(v[jb * 8 + i]) + bias;
-                                v[jb * 8 + i] = __float_as_uint(u);
-                                sum += u; sq = fmaf(u, u, sq);
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kCsNPT; j++) {
-                        const float u = __uint_as_float(v[j]) + bias;
-                        v[j] = __float_as_uint(u);
-                        const float uu = j < nvalid ? u : 0.f;
-                        sum += uu; sq = fmaf(uu, uu, sq);
+            for (int t = 0; t < nslices; t++) {
+                // ---- this slice's geometry (kMulti: shadows the single-slice values of the kernel scope)
+                const int sl = kMulti ? (int)blockIdx.x + t * G : (int)blockIdx.x;
+                const long long P0 = (long long)sl * ppc;
+                const int npts = (int)min((long long)ppc, P.total - P0);
+                const int nvalid = max(0, min(npt, npts - col0));
+                const bool lastslice = !kMulti || t == nslices - 1;
+                if (kMulti) {   // the slice's input: layer 1 from the points, deeper layers from the raw outputs this thread parked a layer ago
+                    if (l == 1) {
+                        __syncthreads();
+                        load_x_slice(P0, npts);
+                        __syncthreads();
+                        layer1_eval(P0, nvalid);
+                    } else if (ch < K) {
+                        cs_load_rows(act_in + (size_t)(P0 + col0) * K + ch, K, v, npt, nvalid);
                     }
                 }
-                if (want_stats) { sRedS[g][ch] = sum; sRedQ[g][ch] = sq; }
-                // training with gradients: the raw outputs go to HBM / L2 as well (a warp stores 32 consecutive channels of a point)
-                if (Lc.zsave && ch < N) cs_save_rows(Lc.zsave + (size_t)(P0 + col0) * N + ch, N, v, npt, nvalid);
-                if (last) {   // per-cloud extrema of this thread's columns (the ring is dead: every MMA has completed)
-                    for (int sgi = 0; sgi < nseg; sgi++) { sPmax[(g * kCsMaxSeg + sgi) * 128 + ch] = -INFINITY; sPmin[(g * kCsMaxSeg + sgi) * 128 + ch] = INFINITY; }
-                    const long long gp0 = P0 + col0;
-                    const int cl = (int)(gp0 / n);
-                    const int first_nb = (int)((long long)(cl + 1) * n - gp0);   // column at which the next cloud starts
-                    if (nvalid == npt && first_nb >= npt) {   // the common case: all of this thread's columns belong to one cloud
-                        float mx = -INFINITY, mn = INFINITY;
+                if (issuer) {
+                    for (int c = 0; c < min(nchunks, 3); c++)        // (this warp owns chunk 3)
+                        cs_issue_chunk(smem_raw, slot_bytes, ppc, tmem0, idesc, gchunk, c, nchunks, bar_full, bar_ring, &bar_acc, lane);
+                }
+                if (q < nchunks) {
+                    const uint32_t gi = gchunk + (uint32_t)q, slot = gi % kCsRing, use = gi / kCsRing;
+                    if (use > 0) {   // the MMAs that read this ring slot last time must have completed
+                        cs_mbar_wait(&bar_ring[slot], (use - 1) & 1u);
+                        cs_fence_after();
+                    }
+                    uint32_t adr[8];
+                    const uint32_t sbase = smem_u32(smem_raw) + slot * slot_bytes;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) adr[i] = sbase + toff[i];
+                    if (!last) CS_TS(3 + (l - 1) * 8 + 7);
+                    cs_write_chunk(v, sc, sh, Lp.relu ? 0.f : -INFINITY, npt, adr);
+                    cs_fence_before();     // this thread's tcgen05.ld of the previous accumulator are complete (wait::ld) and ordered
+                    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core
+                    cs_mbar_arrive(&bar_full[slot]);
+                }
+                if (issuer && nchunks > 3) cs_issue_chunk(smem_raw, slot_bytes, ppc, tmem0, idesc, gchunk, 3, nchunks, bar_full, bar_ring, &bar_acc, lane);
+                gchunk += (uint32_t)nchunks;
+                CS_TS(3 + (l - 1) * 8 + 2);
+                // (C) while the tensor core works: the NEXT layer's weight row into registers
+                if (!last && lastslice) cs_load_w(P.L[l + 1], ch, g, wreg);
+                // (D) every MMA of this slice has completed
+                cs_mbar_wait(&bar_acc, acc_uses & 1u);
+                acc_uses++;
+                cs_fence_after();
+                CS_TS(3 + (l - 1) * 8 + 3);
+                // (E) the next layer's weights replace this layer's in tensor memory
+                if (!last && lastslice) {
+                    cs_store_w(tmem_lane, g, P.L[l + 1].c_in >> 2, wreg);
+                    cs_fence_before();
+                    cs_mbar_arrive(&bar_w);
+                }
+                // (F) the accumulator: lane = channel, this thread's npt columns -> registers (+bias); statistics / extrema on the way
+                cl_first = (int)(P0 / n);
+                nseg = (int)((P0 + npts - 1) / n) - cl_first + 1;
+                if (q * 32 < N) {
+#pragma unroll
+                    for (int jb = 0; jb < kCsNPT / 8; jb++)
+                        if (jb * 8 < npt) cs_ld8_issue(tmem_lane + (uint32_t)(col0 + jb * 8), v + jb * 8);
+                    cs_ld_wait();
+                    cs_fence_before();   // the next MMA into this accumulator overwrites these columns: ordered through a CTA barrier below
+                    float sum = 0.f, sq = 0.f;
+                    if (nvalid == npt) {   // (every slice but the last: all columns are real points)
 #pragma unroll
                         for (int jb = 0; jb < kCsNPT / 8; jb++) {
                             if (jb * 8 < npt) {
 #pragma unroll
-                                for (int i = 0; i < 8; i++) { mx = fmaxf(mx, __uint_as_float(v[jb * 8 + i])); mn = fminf(mn, __uint_as_float(v[jb * 8 + i])); }
+                                for (int i = 0; i < 8; i++) {
+                                    const float u = __uint_as_float(v[jb * 8 + i]) + bias;
+                                    v[jb * 8 + i] = __float_as_uint(u);
+                                    sum += u; sq = fmaf(u, u, sq);
+                                }
                             }
                         }
-                        sPmax[(g * kCsMaxSeg + cl - cl_first) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + cl - cl_first) * 128 + ch] = mn;
-                    } else {   // columns straddle cloud boundaries (or the batch ends inside them): one masked pass per cloud segment
-                        int jlo = 0;
-                        for (int c2 = cl; jlo < nvalid; c2++) {
-                            const int jhi = min(nvalid, (int)((long long)(c2 + 1) * n - gp0));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kCsNPT; j++) {
+                            const float u = __uint_as_float(v[j]) + bias;
+                            v[j] = __float_as_uint(u);
+                            const float uu = j < nvalid ? u : 0.f;
+                            sum += uu; sq = fmaf(uu, uu, sq);
+                        }
+                    }
+                    if (kMulti) { sumL += sum; sqL += sq; }
+                    else if (want_stats) { sRedS[g][ch] = sum; sRedQ[g][ch] = sq; }
+                    // training with gradients (and kMulti: the next layer's input): the raw outputs go to HBM / L2 as well (a warp stores 32
+                    // consecutive channels of a point)
+                    if (act_out && ch < N) cs_save_rows(act_out + (size_t)(P0 + col0) * N + ch, N, v, npt, nvalid);
+                    if (last) {   // per-cloud extrema of this thread's columns (the ring is dead: every MMA has completed)
+                        for (int sgi = 0; sgi < nseg; sgi++) { sPmax[(g * kCsMaxSeg + sgi) * 128 + ch] = -INFINITY; sPmin[(g * kCsMaxSeg + sgi) * 128 + ch] = INFINITY; }
+                        const long long gp0 = P0 + col0;
+                        const int cl = (int)(gp0 / n);
+                        const int first_nb = (int)((long long)(cl + 1) * n - gp0);   // column at which the next cloud starts
+                        if (nvalid == npt && first_nb >= npt) {   // the common case: all of this thread's columns belong to one cloud
                             float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
-                            for (int j = 0; j < kCsNPT; j++) {
-                                const bool in = j >= jlo && j < jhi;
-                                mx = in ? fmaxf(mx, __uint_as_float(v[j])) : mx;
-                                mn = in ? fminf(mn, __uint_as_float(v[j])) : mn;
+                            for (int jb = 0; jb < kCsNPT / 8; jb++) {
+                                if (jb * 8 < npt) {
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) { mx = fmaxf(mx, __uint_as_float(v[jb * 8 + i])); mn = fminf(mn, __uint_as_float(v[jb * 8 + i])); }
+                                }
                             }
-                            sPmax[(g * kCsMaxSeg + c2 - cl_first) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + c2 - cl_first) * 128 + ch] = mn;
-                            jlo = jhi;
+                            sPmax[(g * kCsMaxSeg + cl - cl_first) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + cl - cl_first) * 128 + ch] = mn;
+                        } else {   // columns straddle cloud boundaries (or the batch ends inside them): one masked pass per cloud segment
+                            int jlo = 0;
+                            for (int c2 = cl; jlo < nvalid; c2++) {
+                                const int jhi = min(nvalid, (int)((long long)(c2 + 1) * n - gp0));
+                                float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+                                for (int j = 0; j < kCsNPT; j++) {
+                                    const bool in = j >= jlo && j < jhi;
+                                    mx = in ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+                                    mn = in ? fminf(mn, __uint_as_float(v[j])) : mn;
+                                }
+                                sPmax[(g * kCsMaxSeg + c2 - cl_first) * 128 + ch] = mx; sPmin[(g * kCsMaxSeg + c2 - cl_first) * 128 + ch] = mn;
+                                jlo = jhi;
+                            }
                         }
                     }
                 }
+                if (kMulti) {   // every warp has read the accumulator (and written its extrema) before the next slice's MMAs / operand stores
+                    cs_named_sync(1, kCsProducers);
+                    if (last) {
+                        write_tiles(sl, cl_first, nseg, sPmax, sPmin);
+                        cs_named_sync(1, kCsProducers);   // ... and the extrema have been consumed
+                    }
+                }
             }
+            if (kMulti && want_stats && q * 32 < N) { sRedS[g][ch] = sumL; sRedQ[g][ch] = sqL; }
             CS_TS(3 + (l - 1) * 8 + 4);
             if (want_stats || last) cs_named_sync(1, kCsProducers);
             if (want_stats && g == 0 && ch < N) {
@@ -759,30 +860,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     sBad = 1;
                 }
             }
-            if (last) {   // (cloud, slot) partial extrema; slot = this CTA's rank among the CTAs that touch the cloud
-                const int S = P.slots_per_cloud;
-                for (int e = tid; e < nseg * N; e += kCsProducers) {
-                    const int s = e / N, c = e - s * N;
-                    const int cl = cl_first + s;
-                    const int slot = (int)blockIdx.x - (int)(((long long)cl * n) / ppc);
-                    float mx = -INFINITY, mn = INFINITY;
-#pragma unroll
-                    for (int gg = 0; gg < 4; gg++) {
-                        mx = fmaxf(mx, sPmax[(gg * kCsMaxSeg + s) * 128 + c]);
-                        mn = fminf(mn, sPmin[(gg * kCsMaxSeg + s) * 128 + c]);
-                    }
-                    if (sBad) { mx = INFINITY; mn = -INFINITY; }   // a statistics partial left the fixed-point range: the pooled feature becomes +-Inf
-                                                                     // (fmaxf would drop a NaN) and the head's BatchNorm turns that into NaN rows
-                    P.tile_max[((size_t)cl * S + slot) * N + c] = mx;
-                    P.tile_min[((size_t)cl * S + slot) * N + c] = mn;
-                    // the CTA that holds a cloud's last point also fills the slots no CTA owns
-                    if ((int)((((long long)cl + 1) * n - 1) / ppc) == (int)blockIdx.x)
-                        for (int s2 = slot + 1; s2 < S; s2++) {
-                            P.tile_max[((size_t)cl * S + s2) * N + c] = -INFINITY;
-                            P.tile_min[((size_t)cl * S + s2) * N + c] = INFINITY;
-                        }
-                }
-            }
+            if (last && !kMulti) write_tiles((int)blockIdx.x, cl_first, nseg, sPmax, sPmin);
             CS_TS(3 + (l - 1) * 8 + 5);
             if (want_stats && last) {   // grid barrier: every CTA's statistics and extrema are in (the head reads both)
                 cs_named_sync(1, kCsProducers);
@@ -1165,15 +1243,25 @@ static int cs_num_sms()
     return sms[dev];
 }
 
-// points per CTA: the batch spread evenly over the SMs, a multiple of 32 (4 column groups x 8-column tensor-memory loads)
-static int cs_points_per_cta(long long total)
+// Partition of the flattened batch: slices of ppc points (a multiple of 32: 4 column groups x 8-column tensor-memory loads; at most kCsMaxPts),
+// spread evenly over the SMs; batches beyond one slice per SM give every CTA several slices (slice = CTA + t * grid).
+struct CsPartition { int ppc, slices, grid, per_cta; };
+static CsPartition cs_partition(long long total)
 {
     const int sms = cs_num_sms();
-    long long ppc = (total + sms - 1) / sms;
+    const long long rounds = max(1ll, (total + (long long)sms * kCsMaxPts - 1) / ((long long)sms * kCsMaxPts));
+    long long ppc = (total + sms * rounds - 1) / (sms * rounds);
     ppc = (ppc + 31) / 32 * 32;
     if (ppc < kCsMinPts) ppc = kCsMinPts;
-    return (int)ppc;
+    if (ppc > kCsMaxPts) ppc = kCsMaxPts;
+    CsPartition R;
+    R.ppc = (int)ppc;
+    R.slices = (int)((total + ppc - 1) / ppc);
+    R.grid = min(sms, R.slices);
+    R.per_cta = (R.slices + R.grid - 1) / R.grid;
+    return R;
 }
+static int cs_points_per_cta(long long total) { return cs_partition(total).ppc; }
 
 int conv_stack_slots_per_cloud(int b, int n)
 {
@@ -1190,16 +1278,16 @@ bool conv_stack_supported(int b, int n, int nconv, const snb200_layer *conv)
         if (reinterpret_cast<uintptr_t>(conv[l].weight) & 15) return false;   // 16-byte row loads
     }
     const long long total = (long long)b * n;
-    const int ppc = cs_points_per_cta(total);
-    if (ppc > kCsMaxPts) return false;
-    if ((ppc - 1) / n + 2 > kCsMaxSeg) return false;   // clouds one CTA may touch
-    if ((total + ppc - 1) / ppc > 255) return false;    // the statistics words count arrivals in one byte
+    const CsPartition R = cs_partition(total);
+    if (R.per_cta > kCsMaxSlicesPerCta) return false;
+    if ((R.ppc - 1) / n + 2 > kCsMaxSeg) return false;   // clouds one slice may touch
+    if (R.grid > 255) return false;                      // the statistics words count arrivals in one byte
     return true;
 }
 
 int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const snb200_layer *conv, int training, double *const *stats,
                       double *mom, unsigned *barrier, float *tile_max, float *tile_min, int *tiles_per_cloud_out, const HeadParams *head,
-                      char *clean_ptr, size_t clean_bytes, cudaStream_t stream, float *const *zsave)
+                      char *clean_ptr, size_t clean_bytes, cudaStream_t stream, float *const *zsave, float *const *act)
 {
     CsParams P;
     memset(&P, 0, sizeof(P));
@@ -1207,7 +1295,11 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     if (head && clean_ptr) { P.self_clean = 1; P.clean_ptr = clean_ptr; P.clean_bytes = (unsigned)clean_bytes; }
     P.x = x; P.layout = layout; P.b = b; P.n = n;
     P.total = (long long)b * n;
-    P.ppc = cs_points_per_cta(P.total);
+    const CsPartition R = cs_partition(P.total);
+    P.ppc = R.ppc; P.slices_per_cta = R.per_cta; P.num_slices = R.slices;
+    const bool multi = R.per_cta > 1;
+    if (multi && !(act && act[0] && act[1])) { set_error("conv stack: %d slices per CTA need the activation workspace", R.per_cta); return SNB200_EINVAL; }
+    if (act) { P.act[0] = act[0]; P.act[1] = act[1]; }
     P.npt = P.ppc / 4;
     P.slots_per_cloud = (n - 1) / P.ppc + 2;
     P.num_layers = nconv; P.training = training;
@@ -1239,8 +1331,11 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
         smem = max(smem, hs);
     }
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
-    const int grid = (int)((P.total + P.ppc - 1) / P.ppc);
+    if (once.first()) {
+        cudaFuncSetAttribute(conv_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        cudaFuncSetAttribute(conv_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    }
+    const int grid = R.grid;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kCsThreadsAll); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -1248,7 +1343,7 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_stack_kernel, P);
+    cudaError_t e = multi ? cudaLaunchKernelEx(&cfg, conv_stack_kernel<true>, P) : cudaLaunchKernelEx(&cfg, conv_stack_kernel<false>, P);
     if (e != cudaSuccess) { set_error("conv stack: cooperative launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SNB200_ECUDA; }
     return check_launch("conv stack");
 }

@@ -220,13 +220,9 @@ __global__ void __launch_bounds__(1024) pool_bwd_kernel(const __grid_constant__ 
     float best = -INFINITY; int bi = 0x7fffffff;
     if (c < C) {
         const float *zc = P.z + (size_t)cloud * P.n * C + c;
-        for (int p0 = grp; p0 < P.n; p0 += 64) {   // 8 of this thread's points per pass: the loads are independent, the compares stay in point order
-            float y8[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { const int p = p0 + 8 * u; y8[u] = p < P.n ? sgn * __ldg(zc + (size_t)p * C) : -INFINITY; }
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (y8[u] > best) { best = y8[u]; bi = p0 + 8 * u; }
+        for (int p = grp; p < P.n; p += 8) {   // (batching these loads 8 at a time measured 3x slower: 60 vs 20 us under ncu)
+            const float y = sgn * zc[(size_t)p * C];
+            if (y > best) { best = y; bi = p; }
         }
     }
     __syncthreads();

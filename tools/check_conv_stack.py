@@ -9,7 +9,9 @@ torch.manual_seed(0)
 ok = True
 QUICK = os.environ.get("SNB200_CS_DEBUG", "0") != "0" or os.environ.get("CS_QUICK", "0") != "0"
 for (b, n, m, train) in ([] if QUICK else [(32, 1024, 64, True), (2, 1024, 64, True), (7, 1000, 64, True), (37, 1024, 64, True), (3, 77, 32, True), (70, 500, 64, True),
-                         (32, 1024, 64, False), (5, 333, 32, False), (32, 1024, 32, True), (2, 2048, 64, True), (64, 512, 64, False)]):
+                         (32, 1024, 64, False), (5, 333, 32, False), (32, 1024, 32, True), (2, 2048, 64, True), (64, 512, 64, False),
+                         # more than one 256-point slice per SM: the multi-slice instantiation (2, 3 and 4 slices per CTA, ragged last slices)
+                         (64, 1024, 64, True), (128, 1024, 64, True), (50, 2048, 64, True), (200, 777, 32, True), (128, 1024, 64, False), (41, 1999, 64, True)]):
     net = sb.SampleNet(m, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda()
     with torch.no_grad():
         for p in net.parameters():
