@@ -377,17 +377,18 @@ def run_ours(args, rank, world, local_rank):
         "bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops"],
         "peak_source": pk["source"] + " cuBLAS bf16 burst. `achieved` counts the ALGORITHMIC fp32 flops (2*M*N*K over the 5 conv + 4 FC layers = %.2f GFLOP "
                        "per launch); the kernel issues 3 TF32 MMAs per product (error compensation to fp32 accuracy) and TF32 runs at half the "
-                       "bf16 rate, so the ceiling for this number is peak/6; the launch is a dependent chain (5 BatchNorm statistics grid barriers, "
+                       "bf16 rate, so the ceiling for this number is peak/6; the launch is a dependent chain (one grid-wide BatchNorm statistics exchange per conv layer -- self-counting fixed-point words, one grid barrier left -- and "
                        "4 dependent FC layers on 32 rows): latency-bound, see profiles/ for the tensor-pipe share" % (gen_flops / 1e9),
         "frac_of_3xtf32_ceiling": ach_tf / (pk["bf16_tflops"] / 6.0), "traffic": traffic, "us_per_launch": kt["generator_us"],
         "algorithmic_flops_per_launch": gen_flops,
         "conv_phase_only": {"us": kt["conv_stack_us"], "achieved_tflops": conv_flops / (kt["conv_stack_us"] * 1e-6) / 1e12},
     }
-    if "sat_generator_us" in kt:   # same layer stack, B_SAT_GEN clouds per call (per-layer tcgen05 kernels + cluster head: 6 launches)
+    if "sat_generator_us" in kt:   # same layer stack, B_SAT_GEN clouds per call: the same persistent launch, every CTA walking several 256-point slices per layer
         sat_flops = gen_flops / B * B_SAT_GEN
         sat_tf = sat_flops / (kt["sat_generator_us"] * 1e-6) / 1e12
         roofline["saturated_B"] = {"clouds_per_call": B_SAT_GEN, "us": kt["sat_generator_us"], "clouds_per_s": B_SAT_GEN / (kt["sat_generator_us"] * 1e-6),
-                                   "achieved_tflops": sat_tf, "frac": sat_tf / pk["bf16_tflops"], "frac_of_3xtf32_ceiling": sat_tf / (pk["bf16_tflops"] / 6.0)}
+                                   "achieved_tflops": sat_tf, "frac": sat_tf / pk["bf16_tflops"], "frac_of_3xtf32_ceiling": sat_tf / (pk["bf16_tflops"] / 6.0),
+                                   "path": "conv_stack_kernel<multi-slice>: one cooperative launch, raw layer outputs parked in L2 between layers"}
     pair_bytes_sp = B * (12 * N + 12 * M + 12 * M)
     pair_bytes_cd = B * (12 * (N + M) + 8 * (N + M))
     roofline_pairwise = {

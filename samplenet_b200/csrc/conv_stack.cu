@@ -77,6 +77,7 @@ struct CsParams {
     // of its own slices travel through act[l & 1] (or the layer's zsave) -- thread-private round trips, no cross-CTA dependency
     int slices_per_cta, num_slices;
     float *act[2];
+    int head_rows;                      // batch rows the FC head stages per pass (32 ... 128, a multiple of 32)
     int dbg;                            // bring-up switches (env SNB200_CS_DEBUG; 0 in the product): 1 = skip the statistics atomics (timing experiments only)
 };
 
@@ -902,10 +903,11 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
     }
     const HeadParams &H = P.H;
     // shared memory of the head (the conv stack's buffers are dead): input row group | partial sums | first weight rows of every layer
-    float *s_in = reinterpret_cast<float *>(smem_raw);                 // [32 rows][c_in + 1] one row group of the input
+    float *s_in = reinterpret_cast<float *>(smem_raw);                 // [head_rows][c_in + 1] up to four row groups of the input
     int hcmax = H.c_feat, hcsum = 0;
     for (int l = 0; l < H.num_fc; l++) { hcmax = max(hcmax, H.fc[l].c_in); hcsum += H.fc[l].c_in; }
-    float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)hcmax * 33;   // [8 K slices][8 channels][32 rows]
+    const int RS = P.head_rows, gpb = RS >> 5;                                  // rows / row groups staged per pass
+    float *s_part = reinterpret_cast<float *>(smem_raw) + (size_t)RS * (hcmax + 1);   // [8 K slices][8 channels][32 rows]
     float *s_wall = s_part + 8 * 8 * 32;                                       // per layer [8 channels][c_in] weight rows
     __shared__ uint64_t hbar[SNB200_MAX_FC_LAYERS];
     const double inv_cnt_h = 1.0 / H.count;
@@ -1031,15 +1033,17 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             // of at most 32 rows) runs ONE compact copy of this code; the 8-way unrolled form exists only for larger batches.  This kernel executes
             // every instruction of the head once per launch, so its pace is set by instruction fetch (ncu: 17 % of the warp samples are
             // "no instruction", almost all at branch targets), and seven skipped copies per FC layer are seven jumps to cold cache lines
-            auto row_group = [&](const int gq, float &yout) {
-                const int r0 = gq * 32, rn = min(32, H.b - r0);
-                if (gq > 0 || cb != c_lo || l > 0) __syncthreads();   // the previous user of s_in / s_part is done
+            // Batch rows are staged up to head_rows (<= 128) at a time -- ONE polling pass over the exchange words for up to four row groups
+            // (staging every group of 32 rows separately put four exchange latencies in sequence per layer for a batch of 128) -- and then
+            // multiplied group by group: partial products, fixed-order combine.
+            auto stage_rows = [&](const int r0) {
+                const int rn = min(RS, H.b - r0), nr32 = (rn + 31) & ~31;   // live rows / rows written (dead rows are zero)
                 if (producer) {   // stage rows r0..r0+rn-1 row-major with an odd row stride (conflict-free lane = row reads).  Lanes run
                                   // along k (coalesced 16-byte loads), a thread's loads are requested together and re-requested
                                   // until every word is present.
                     const int ldi = c_in + 1;
                     if ((c_in & 3) == 0) {
-                        const int q4 = c_in >> 2, items = 32 * q4;           // item = (row, 4 channels) = one 16-byte load
+                        const int q4 = c_in >> 2, items = nr32 * q4;           // item = (row, 4 channels) = one 16-byte load
                         for (int i0 = tid; i0 < items; i0 += kCsProducers * 4) {
                             uint4 v[4];
                             unsigned spin = 0;
@@ -1070,7 +1074,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             }
                         }
                     } else {
-                        for (int e = tid; e < 32 * c_in; e += kCsProducers) {
+                        for (int e = tid; e < nr32 * c_in; e += kCsProducers) {
                             const int r = e / c_in, k = e - r * c_in;
                             float xv = 0.f;
                             if (r < rn) {
@@ -1085,9 +1089,8 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         }
                     }
                 }
-                if (cb == c_lo && gq == 0 && w_tma) mbar_wait(&hbar[l], 0);   // this layer's first weight rows have landed
-                __syncthreads();
-                CS_TS(39 + l * 6 + 1);
+            };
+            auto group_math = [&](const int rl0, float &yout) {   // rows rl0 .. rl0 + 31 of the staged block
                 if (producer) {   // warp -> (channel quad = warp & 1, K eighth = warp >> 1); lane = row
                     const int cq = (warp & 1) * 4, k8 = warp >> 1;
                     const int kr = ((c_in + 31) / 32) * 4;            // K per eighth, multiple of 4
@@ -1096,12 +1099,12 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     float a4[4] = {0.f, 0.f, 0.f, 0.f};
                     int k = k_lo;
                     if ((c_in & 3) == 0 && k_hi - k_lo == kr && (kr == 32 || kr == 16)) {   // the common widths (256, 128): fully unrolled, every
-                        if (kr == 32) cs_head_dot<32>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);   // load in flight before the first FMA
-                        else cs_head_dot<16>(s_in + lane * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);            // (same summation order as the loop below)
+                        if (kr == 32) cs_head_dot<32>(s_in + (rl0 + lane) * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);   // load in flight before the first FMA
+                        else cs_head_dot<16>(s_in + (rl0 + lane) * (c_in + 1) + k_lo, wq + k_lo, c_in, a4);            // (same summation order as the loop below)
                         k = k_hi;
                     } else if ((c_in & 3) == 0) {
                         for (; k + 4 <= k_hi; k += 4) {
-                            const float *xr = s_in + lane * (c_in + 1) + k;
+                            const float *xr = s_in + (rl0 + lane) * (c_in + 1) + k;
                             const float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
@@ -1111,7 +1114,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         }
                     }
                     for (; k < k_hi; k++) {
-                        const float xv = s_in[lane * (c_in + 1) + k];
+                        const float xv = s_in[(rl0 + lane) * (c_in + 1) + k];
 #pragma unroll
                         for (int j = 0; j < 4; j++) a4[j] = fmaf(xv, wq[j * c_in + k], a4[j]);
                     }
@@ -1127,6 +1130,17 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     for (int e8 = 0; e8 < 8; e8++) t += s_part[(e8 * 8 + warp) * 32 + lane];
                     yout = t;
                 }
+            };
+            auto row_group = [&](const int gq, float &yout) {
+                const bool first_of_block = gq % gpb == 0;
+                if (gq > 0 || cb != c_lo || l > 0) __syncthreads();   // the previous user of s_in / s_part is done
+                if (first_of_block) {
+                    stage_rows(gq * 32);
+                    if (cb == c_lo && gq == 0 && w_tma) mbar_wait(&hbar[l], 0);   // this layer's first weight rows have landed
+                    __syncthreads();
+                    CS_TS(39 + l * 6 + 1);
+                }
+                group_math((gq % gpb) * 32, yout);
             };
             if (nrg == 1) {
                 row_group(0, yv[0]);
@@ -1326,8 +1340,14 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
         for (int l = 0; l < head->num_fc; l++) hcmax = max(hcmax, head->fc[l].c_in);
         size_t hcsum = 0;
         for (int l = 0; l < head->num_fc; l++) hcsum += head->fc[l].c_in;
-        const size_t hs = ((size_t)hcmax * 33 + 2048 + (size_t)8 * hcsum) * sizeof(float) + 1024;
+        int rs = min(128, (b + 31) / 32 * 32);   // rows staged per pass: as many row groups as fit next to the partial sums and the weight rows
+        size_t hs = 0;
+        for (;; rs -= 32) {
+            hs = ((size_t)rs * (hcmax + 1) + 2048 + (size_t)8 * hcsum) * sizeof(float) + 1024;
+            if (hs <= 200 * 1024 || rs == 32) break;
+        }
         if (hs > 200 * 1024) { set_error("conv stack: FC width %d too large for the fused head", hcmax); return SNB200_EUNSUPPORTED; }
+        P.head_rows = rs;
         smem = max(smem, hs);
     }
     static PerDeviceOnce once;

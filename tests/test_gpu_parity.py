@@ -435,10 +435,11 @@ def test_generator_cuda_backward_vs_float64_autograd(sb, b, n, m, layout):
     np.testing.assert_allclose(_n(y), h.detach().float().cpu().numpy(), rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("b,n", [(32, 1024), (2, 1024), (7, 1000), (37, 1024), (3, 77), (70, 500)])
+@pytest.mark.parametrize("b,n", [(32, 1024), (2, 1024), (7, 1000), (37, 1024), (3, 77), (70, 500), (64, 1024), (128, 1024), (41, 1999)])
 def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
-    """The persistent cooperative conv-stack kernel (activations resident in TMEM) == the per-layer tensor-core kernels ==
-    the exact-fp32 CUDA-core path, training and eval mode, full and ragged tiles, one and two tiles per CTA."""
+    """The persistent cooperative conv-stack kernel (activations resident in registers / TMEM) == the per-layer tensor-core kernels ==
+    the exact-fp32 CUDA-core path, training and eval mode, full and ragged slices, one slice per CTA and (the last three shapes: more than 256
+    points per SM) two to four slices per CTA with the raw layer outputs parked in L2 between layers."""
     torch.manual_seed(b * 1000 + n)
     net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda()
     with torch.no_grad():
@@ -462,6 +463,33 @@ def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
                 if b < 3 and "bn_fc" in k:
                     continue
                 np.testing.assert_allclose(_n(outs[0][2][k]), _n(st[k]), rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+def test_conv_stack_statistics_range_guard(sb):
+    """The BatchNorm statistics between the conv layers travel as fixed-point words (conv_stack.cu, cs_fx_*): inputs of any scale stay exact
+    (layer 1 is normalised analytically), and a layer whose pre-activations leave the representable range (|z| beyond ~3e4) must poison the
+    launch -- NaN rows -- instead of returning numbers computed from clipped statistics."""
+    torch.manual_seed(5)
+    net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda().train()
+    conv, fc = net._layer_specs()
+    x = torch.rand(32, 1024, 3, device="cuda") - 0.5
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    for scale in (1.0, 1e3, 1e-3):
+        net.load_state_dict(sd)
+        o1, f1 = sb.ops.generator_forward(x * scale, "bnc", conv, fc, True, 64)
+        net.load_state_dict(sd)
+        o2, f2 = sb.ops.generator_forward(x * scale, "bnc", conv, fc, True, 64, per_layer_kernels=True)
+        assert torch.isfinite(o1).all()
+        np.testing.assert_allclose(_n(f1), _n(f2), rtol=3e-4, atol=3e-5)
+    with torch.no_grad():
+        net.conv2.weight.mul_(1e6)
+    conv, fc = net._layer_specs()
+    o3, _ = sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)
+    assert torch.isnan(o3).all()
+    net.load_state_dict(sd)
+    conv, fc = net._layer_specs()
+    o4, _ = sb.ops.generator_forward(x, "bnc", conv, fc, True, 64)   # the next launch is clean again
+    assert torch.isfinite(o4).all()
 
 
 def test_generator_rec_widths_and_ragged_sizes(sb):
