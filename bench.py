@@ -373,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "kernel": "conv_stack_kernel (the whole generator in one persistent cooperative launch: conv layers 2-5 as TRANSPOSED GEMMs on tcgen05.mma "
                   "kind::tf32 (3xTF32): weights = A operand in tensor memory, activations = B operand in swizzled shared memory, one channel per thread, "
-                  "224 points per CTA on all 148 SMs; max-pool; FC head; BatchNorm batch statistics via grid barriers)",
+                  "224 points per CTA on all 148 SMs; max-pool; FC head; BatchNorm batch statistics exchanged as self-counting fixed-point words, one grid barrier left)",
         "bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops"],
         "peak_source": pk["source"] + " cuBLAS bf16 burst. `achieved` counts the ALGORITHMIC fp32 flops (2*M*N*K over the 5 conv + 4 FC layers = %.2f GFLOP "
                        "per launch); the kernel issues 3 TF32 MMAs per product (error compensation to fp32 accuracy) and TF32 runs at half the "

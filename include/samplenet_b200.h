@@ -158,10 +158,13 @@ int snb200_encoder_forward(int b, int n, int layout, const float *x, int num_lay
                            int training, float *feat, void *workspace, size_t workspace_bytes, snb200_stream_t stream);
 
 /* The whole generator in one call: conv stack -> max-pool -> FC head -> out (b, c_out_last) [+ feat (b, c_conv_last), may be
- * NULL].  Default path: layers 2.. of the conv stack on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 error-compensated,
- * fp32 TMEM accumulators), layer 1 evaluated on the fly with its BatchNorm statistics derived from the input moments, and
- * the pool + all FC layers in ONE thread-block-cluster launch.  flags & SNB200_GEN_EXACT_FP32 selects the exact-fp32
- * CUDA-core conv stack instead (also taken automatically for widths the tensor path does not cover).  b <= 256. */
+ * NULL].  Default path: ONE persistent cooperative launch -- layers 2.. of the conv stack on the tensor cores (tcgen05.mma
+ * kind::tf32, 3xTF32 error-compensated, fp32 TMEM accumulators), layer 1 evaluated on the fly with its BatchNorm statistics
+ * derived from the input moments, the max-pool and all FC layers on the same grid (conv widths 32/64/128, up to 16 slices of
+ * 256 points per SM).  Other shapes: one tensor-core launch per layer + a thread-block-cluster FC head.  flags &
+ * SNB200_GEN_EXACT_FP32 selects the exact-fp32 CUDA-core conv stack instead (also taken automatically for widths the tensor
+ * path does not cover).  b <= 256.  Training-mode pre-BatchNorm activations must stay below ~3e4 in magnitude on the default
+ * path (fixed-point statistics exchange); beyond that the call returns NaN rows. */
 #define SNB200_GEN_EXACT_FP32 1
 #define SNB200_GEN_PER_LAYER_KERNELS 8 /* tensor-core path as one launch per layer instead of the persistent conv-stack kernel */
 #define SNB200_GEN_SEPARATE_HEAD 16 /* keep the pool + FC head as its own thread-block-cluster launch */

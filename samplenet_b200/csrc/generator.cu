@@ -6,8 +6,9 @@
 //                  conv_stack_kernel   conv 1..5 + pool + fc1..fc4, persistent cooperative   1      (conv_stack.cu)
 //   per-layer      memset; x_moments_kernel; tc_layer_kernel x4; fc_head_cluster_kernel      6      (encoder_tc.cu, here)
 //   exact fp32     memset; conv_layer_kernel x5; fc_head_cluster_kernel                      6      (encoder.cu, here)
-//   The default applies when the batch has at most 2 tiles of 128 points per SM and the conv widths are 32/64/128
-//   (conv_stack_supported); everything else falls through to the per-layer tensor-core path, then to exact fp32.
+//   The default applies when the conv widths are 32/64/128 and the batch has at most 16 slices of 256 points per SM
+//   (conv_stack_supported: one slice per SM keeps activations in registers, more than one parks them in L2 between layers -- still one
+//   launch); everything else falls through to the per-layer tensor-core path, then to exact fp32.
 //
 // fc_head_cluster_kernel: the FC head (samplenet.py:99-104: 128->256->256->256->3M on B rows, BatchNorm over the batch) is tiny
 // (7 MFLOP, 0.86 MB of weights) but has four layer-to-layer dependencies.  ONE thread-block cluster of 16 CTAs runs all of it:
