@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
                    "api": "samplenet_b200.GraphedStep / PipelinedHostStep (SampleNet.forward + get_simplification_loss in one CUDA graph)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "clouds/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                "sync": "every step's loss is read on the host; two steps in flight, H2D on a copy stream (samplenet_b200.PipelinedHostStep); the timed region starts and ends with an empty pipeline"},
+                "sync": "every step's loss is read on the host; two steps in flight, H2D on a copy stream, the 4-byte loss D2H on a third stream behind each graph (samplenet_b200.PipelinedHostStep); the timed region starts and ends with an empty pipeline"},
         "gpu_launches": int(step.launches_per_step) * args.steps,
         "launches_per_step": int(step.launches_per_step),
         "roofline": roofline,

@@ -77,6 +77,9 @@ struct CsParams {
     // of its own slices travel through act[l & 1] (or the layer's zsave) -- thread-private round trips, no cross-CTA dependency
     int slices_per_cta, num_slices;
     float *act[2];
+    int act_ld;                         // row stride (floats) of act[]: the widest parked layer, the SAME for every layer -- a slice's rows then occupy
+                                        // the same bytes whatever the layer, so CTAs that drift layers apart (eval mode: nothing synchronises the grid
+                                        // between layers) never touch each other's rows
     int head_rows;                      // batch rows the FC head stages per pass (32 ... 128, a multiple of 32)
     int dbg;                            // bring-up switches (env SNB200_CS_DEBUG; 0 in the product): 1 = skip the statistics atomics (timing experiments only)
 };
@@ -690,6 +693,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             float sumL = 0.f, sqL = 0.f;                                     // (kMulti) this thread's statistics over all of its slices
             const float *act_in = kMulti && l > 1 ? (Lp.zsave ? Lp.zsave : P.act[(l - 1) & 1]) : nullptr;
             float *act_out = kMulti && !last ? (Lc.zsave ? Lc.zsave : P.act[l & 1]) : Lc.zsave;
+            const int ld_in = (kMulti && !Lp.zsave) ? P.act_ld : K, ld_out = (kMulti && !last && !Lc.zsave) ? P.act_ld : N;
             // (cloud, slot) partial extrema of one slice (last layer); slot = the slice's rank among the slices that touch the cloud
             auto write_tiles = [&](const int sl, const int cl_first, const int nseg, const float *sPmax, const float *sPmin) {
                 const int S = P.slots_per_cloud;
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                         __syncthreads();
                         layer1_eval(P0, nvalid);
                     } else if (ch < K) {
-                        cs_load_rows(act_in + (size_t)(P0 + col0) * K + ch, K, v, npt, nvalid);
+                        cs_load_rows(act_in + (size_t)(P0 + col0) * ld_in + ch, ld_in, v, npt, nvalid);
                     }
                 }
                 if (issuer) {
@@ -806,7 +810,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     else if (want_stats) { sRedS[g][ch] = sum; sRedQ[g][ch] = sq; }
                     // training with gradients (and kMulti: the next layer's input): the raw outputs go to HBM / L2 as well (a warp stores 32
                     // consecutive channels of a point)
-                    if (act_out && ch < N) cs_save_rows(act_out + (size_t)(P0 + col0) * N + ch, N, v, npt, nvalid);
+                    if (act_out && ch < N) cs_save_rows(act_out + (size_t)(P0 + col0) * ld_out + ch, ld_out, v, npt, nvalid);
                     if (last) {   // per-cloud extrema of this thread's columns (the ring is dead: every MMA has completed)
                         for (int sgi = 0; sgi < nseg; sgi++) { sPmax[(g * kCsMaxSeg + sgi) * 128 + ch] = -INFINITY; sPmin[(g * kCsMaxSeg + sgi) * 128 + ch] = INFINITY; }
                         const long long gp0 = P0 + col0;
@@ -985,7 +989,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                 const float sh = lb - mean * sc;
                 v = sc >= 0.f ? fmaf(mx, sc, sh) : fmaf(mn, sc, sh);
             }
-            if (H.last_relu) v = fmaxf(v, 0.f);
+            if (H.last_relu) v = (v < 0.f) ? 0.f : v;
             cs_xchg_store(ll0 + e, v);
             H.feat[e] = v;
         }
@@ -1187,7 +1191,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     const int r = gq * 32 + lane;
                     if (r < H.b) {
                         float v = L.has_bn ? fmaf(yv[gq], scale, shift) : yv[gq];
-                        if (L.relu) v = fmaxf(v, 0.f);
+                        if (L.relu) v = (v < 0.f) ? 0.f : v;   // (not fmaxf: a NaN must stay a NaN, as in torch -- and the statistics range guard relies on it)
                         if (lastfc) {
                             const int oc = (H.out_inner > 0) ? (cw % H.out_inner) * (L.c_out / H.out_inner) + cw / H.out_inner : cw;
                             dst[(size_t)r * L.c_out + oc] = v;
@@ -1314,6 +1318,8 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     const bool multi = R.per_cta > 1;
     if (multi && !(act && act[0] && act[1])) { set_error("conv stack: %d slices per CTA need the activation workspace", R.per_cta); return SNB200_EINVAL; }
     if (act) { P.act[0] = act[0]; P.act[1] = act[1]; }
+    P.act_ld = 8;
+    for (int l = 0; l + 1 < nconv; l++) P.act_ld = max(P.act_ld, conv[l].c_out);   // (= the width carve_gen_ws sizes the two buffers for)
     P.npt = P.ppc / 4;
     P.slots_per_cloud = (n - 1) / P.ppc + 2;
     P.num_layers = nconv; P.training = training;

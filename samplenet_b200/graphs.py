@@ -51,11 +51,16 @@ class PipelinedHostStep:
         pipe.finish(); pipe.finish()
     """
 
-    def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None):
-        self.slots = [GraphedStep(net, batch_size, num_points, gamma, delta, device, loss_to_host=True) for _ in range(2)]
+    def __init__(self, net, batch_size, num_points, gamma=1, delta=0, device=None, side_readback=True):
+        # side_readback: the 4-byte loss read-back runs on its own stream behind the graph instead of being the graph's last node, so the next
+        # step's kernels (the other slot's graph, already queued) do not wait for a PCIe round trip between two steps
+        self.side_readback = bool(side_readback)
+        self.slots = [GraphedStep(net, batch_size, num_points, gamma, delta, device, loss_to_host=not self.side_readback) for _ in range(2)]
         self.device = self.slots[0].device
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.d2h_stream = torch.cuda.Stream(device=self.device)
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # input of the slot has arrived
+        self.computed = [torch.cuda.Event(), torch.cuda.Event()]   # the slot's graph has finished (side_readback)
         self.done = [torch.cuda.Event(), torch.cuda.Event()]       # graph + loss read-back of the slot have finished
         self.head = 0          # next slot to fill
         self.next_launch = 0   # next slot to launch
@@ -84,8 +89,15 @@ class PipelinedHostStep:
         st = torch.cuda.current_stream(self.device)
         st.wait_event(self.ready[k])
         g = self.slots[k]
-        g.replay()                                            # includes the loss read-back into g.loss_host
-        self.done[k].record(st)
+        g.replay()
+        if self.side_readback:
+            self.computed[k].record(st)
+            self.d2h_stream.wait_event(self.computed[k])
+            with torch.cuda.stream(self.d2h_stream), torch.no_grad():
+                g.loss_host.copy_(g.loss_flat, non_blocking=True)
+                self.done[k].record(self.d2h_stream)
+        else:                                                 # (the read-back into g.loss_host is the graph's last node)
+            self.done[k].record(st)
         self.inflight.append(k)
 
     def finish(self):

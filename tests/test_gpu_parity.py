@@ -465,6 +465,25 @@ def test_conv_stack_kernel_vs_per_layer_kernels_and_fp32(sb, b, n):
                 np.testing.assert_allclose(_n(outs[0][2][k]), _n(st[k]), rtol=1e-4, atol=1e-6, err_msg=k)
 
 
+@pytest.mark.parametrize("b", [56, 65])
+def test_conv_stack_multislice_eval_is_race_free(sb, b):
+    """Eval mode has no grid-wide synchronisation between the conv layers, so CTAs of a multi-slice launch drift layers apart: the parked
+    activations of a slice must occupy the same bytes in every layer (fixed row stride), or a fast CTA's 128-wide rows overwrite a slow CTA's
+    64-wide rows.  That race corrupted one cloud in about every second launch -- repeated launches against the exact-fp32 path."""
+    torch.manual_seed(b)
+    net = sb.SampleNet(64, 128, group_size=8, input_shape="bnc", output_shape="bnc").cuda().eval()
+    with torch.no_grad():
+        for bn in [net.bn1, net.bn2, net.bn3, net.bn4, net.bn5]:
+            bn.running_mean.copy_(0.1 * torch.randn_like(bn.running_mean)); bn.running_var.copy_(0.5 + torch.rand_like(bn.running_var))
+    x = torch.rand(b, 1024, 3, device="cuda") - 0.5
+    conv, fc = net._layer_specs()
+    ref = sb.ops.generator_forward(x, "bnc", conv, fc, False, 64, exact_fp32=True)[1].clone()
+    for _ in range(8):
+        for kw in (dict(), dict(separate_head=True)):
+            feat = sb.ops.generator_forward(x, "bnc", conv, fc, False, 64, **kw)[1]
+            np.testing.assert_allclose(_n(feat), _n(ref), rtol=3e-4, atol=3e-5)
+
+
 def test_conv_stack_statistics_range_guard(sb):
     """The BatchNorm statistics between the conv layers travel as fixed-point words (conv_stack.cu, cs_fx_*): inputs of any scale stay exact
     (layer 1 is normalised analytically), and a layer whose pre-activations leave the representable range (|z| beyond ~3e4) must poison the
