@@ -79,7 +79,8 @@ struct CsParams {
     float *act[2];
     int act_ld;                         // row stride (floats) of act[]: the widest parked layer, the SAME for every layer -- a slice's rows then occupy
                                         // the same bytes whatever the layer, so CTAs that drift layers apart (eval mode: nothing synchronises the grid
-                                        // between layers) never touch each other's rows
+                                        // between layers) never touch each other's rows.  0 = each layer's own width (training: the statistics
+                                        // exchange keeps the grid within one layer)
     int head_rows;                      // batch rows the FC head stages per pass (32 ... 128, a multiple of 32)
     int dbg;                            // bring-up switches (env SNB200_CS_DEBUG; 0 in the product): 1 = skip the statistics atomics (timing experiments only)
 };
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
             float sumL = 0.f, sqL = 0.f;                                     // (kMulti) this thread's statistics over all of its slices
             const float *act_in = kMulti && l > 1 ? (Lp.zsave ? Lp.zsave : P.act[(l - 1) & 1]) : nullptr;
             float *act_out = kMulti && !last ? (Lc.zsave ? Lc.zsave : P.act[l & 1]) : Lc.zsave;
-            const int ld_in = (kMulti && !Lp.zsave) ? P.act_ld : K, ld_out = (kMulti && !last && !Lc.zsave) ? P.act_ld : N;
+            const int ld_in = (kMulti && !Lp.zsave && P.act_ld) ? P.act_ld : K, ld_out = (kMulti && !last && !Lc.zsave && P.act_ld) ? P.act_ld : N;
             // (cloud, slot) partial extrema of one slice (last layer); slot = the slice's rank among the slices that touch the cloud
             auto write_tiles = [&](const int sl, const int cl_first, const int nseg, const float *sPmax, const float *sPmin) {
                 const int S = P.slots_per_cloud;
@@ -1318,8 +1319,13 @@ int launch_conv_stack(int b, int n, int layout, const float *x, int nconv, const
     const bool multi = R.per_cta > 1;
     if (multi && !(act && act[0] && act[1])) { set_error("conv stack: %d slices per CTA need the activation workspace", R.per_cta); return SNB200_EINVAL; }
     if (act) { P.act[0] = act[0]; P.act[1] = act[1]; }
-    P.act_ld = 8;
-    for (int l = 0; l + 1 < nconv; l++) P.act_ld = max(P.act_ld, conv[l].c_out);   // (= the width carve_gen_ws sizes the two buffers for)
+    // Training with BatchNorm on every layer: the statistics exchange orders the layers grid-wide (nobody starts layer l+1 before everybody has
+    // finished layer l), so the parked rows may use each layer's natural stride (half the L2 footprint for the 64-wide layers).  Otherwise one
+    // stride for all layers (the width carve_gen_ws sizes the two buffers for).
+    bool layers_ordered = training != 0;
+    for (int l = 0; l < nconv; l++) layers_ordered = layers_ordered && conv[l].bn_weight != nullptr;
+    P.act_ld = 0;
+    if (!layers_ordered) { P.act_ld = 8; for (int l = 0; l + 1 < nconv; l++) P.act_ld = max(P.act_ld, conv[l].c_out); }
     P.npt = P.ppc / 4;
     P.slots_per_cloud = (n - 1) / P.ppc + 2;
     P.num_layers = nconv; P.training = training;
