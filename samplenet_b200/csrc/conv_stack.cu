@@ -1187,11 +1187,10 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                     shift = pbet - mean * scale;
                 }
                 CS_TS(39 + l * 6 + 4);
-#pragma unroll
-                for (int gq = 0; gq < 8; gq++) {
+                auto store_group = [&](const int gq, const float y) {   // normalise + activate + hand over one row group of this channel
                     const int r = gq * 32 + lane;
                     if (r < H.b) {
-                        float v = L.has_bn ? fmaf(yv[gq], scale, shift) : yv[gq];
+                        float v = L.has_bn ? fmaf(y, scale, shift) : y;
                         if (L.relu) v = (v < 0.f) ? 0.f : v;   // (not fmaxf: a NaN must stay a NaN, as in torch -- and the statistics range guard relies on it)
                         if (lastfc) {
                             const int oc = (H.out_inner > 0) ? (cw % H.out_inner) * (L.c_out / H.out_inner) + cw / H.out_inner : cw;
@@ -1200,6 +1199,13 @@ __global__ void __launch_bounds__(kCsThreadsAll, 1) conv_stack_kernel(const __gr
                             cs_xchg_store(lldst + (size_t)r * L.c_out + cw, v);   // the next layer's consumers spin on these words
                         }
                     }
+                };
+                if (nrg == 1) {   // (one compact copy on the common path, see row_group above)
+                    store_group(0, yv[0]);
+                } else {
+#pragma unroll
+                    for (int gq = 0; gq < 8; gq++)
+                        if (gq < nrg) store_group(gq, yv[gq]);
                 }
                 if (L.has_bn && H.training && lane == 0) {   // running statistics: off the critical path
                     const float unb = H.b > 1 ? bn_q / (float)(H.b - 1) : bn_q * inv_b;
