@@ -13,15 +13,21 @@
 //     shuffle networks, no per-channel tables in shared memory; the raw outputs of a layer are read from tensor memory ONCE
 //     (tcgen05.ld, bias added) and stay in registers across the statistics grid barrier until they are normalised, split and stored
 //     as the next layer's B operand (a warp's 32 lanes are the 32 consecutive k of one swizzled 128-byte row: conflict-free STS.32);
-//   * training-mode BatchNorm needs the batch statistics of layer l before layer l+1 can start: per-CTA partial sums go to fp64
-//     global accumulators and a grid-wide barrier (cooperative launch, one counter) separates the layers.  Layer 1 (3 -> C) is
-//     evaluated on CUDA cores and its statistics follow analytically from the batch's 9 input moments (phase 0);
+//   * training-mode BatchNorm needs the batch statistics of layer l before layer l+1 can start: per-CTA partial sums are added as
+//     fixed-point words that carry their own arrival count (cs_fx_*: one 64-bit integer reduction per word, exact and order-
+//     independent; a consumer that reads "count == grid size" holds the total -- no flag, no fence, no grid barrier between the
+//     layers); only the last layer keeps fp64 accumulators and the one remaining grid barrier (the head needs every CTA's extrema
+//     anyway).  Layer 1 (3 -> C) is evaluated on CUDA cores and its statistics follow analytically from the batch's 9 input
+//     moments (phase 0);
 //   * the last layer never materialises: only per-(CTA, cloud) max / min leave the SM (the max-pool commutes with the monotone
 //     BN+ReLU map);
 //   * the max-pool finalise and the FC head (fc1..fc4 with BatchNorm over the batch) run as the tail of the same launch, 8 output
 //     channels per CTA; the 32 KB activation matrix of a layer travels between CTAs as self-validating words (a zeroed buffer,
 //     producers never store the bit pattern 0, consumers spin on the data itself): no grid barrier in the head.
-// Applicable when B*N <= 256 x #SMs, widths <= 128 and K in {32, 64, 128}; otherwise the per-layer kernels are used.
+//   * batches beyond one 256-point slice per SM: the <kMulti = true> instantiation gives every CTA several slices and walks them inside
+//     every layer, parking the raw layer outputs in global memory (L2) between layers; the <false> instantiation (the headline size)
+//     keeps them in registers.
+// Applicable to widths <= 128 with K in {32, 64, 128} and up to 16 slices per CTA; otherwise the per-layer kernels are used.
 #include "encoder_internal.cuh"
 #include <cooperative_groups.h>
 #include <string.h>
